@@ -1,0 +1,181 @@
+/*
+ * gwasdev.h -- C-ABI of the B200-native association hot path (libgwasdev.so).
+ *
+ * Drop-in boundary for libgwaspp's case/control association path: everything the reference's
+ * GenoTable virtuals and test-class functions do for that path, as plain C entry points with plain
+ * pointers and sizes. No C++ types, exceptions or torch types cross this boundary. All functions
+ * return 0 on success and a non-zero status otherwise; gwasdev_last_error() gives the message
+ * (the reference's convention on this path is assert/abort; the C++ adapter in
+ * libgwaspp_b200/host asserts on non-zero to mimic it).
+ *
+ * Citations are relative to the reference tree's src/libgwaspp/ unless stated otherwise.
+ * There is no CPU fallback: every compute entry point fails with GWASDEV_ENODEVICE without a GPU.
+ */
+#ifndef GWASDEV_H
+#define GWASDEV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GWASDEV_API __attribute__((visibility("default")))
+#else
+#define GWASDEV_API
+#endif
+
+#define GWASDEV_OK 0
+#define GWASDEV_EINVAL 1     /* bad argument / call order */
+#define GWASDEV_ENODEVICE 2  /* no CUDA device, or a CUDA runtime error */
+#define GWASDEV_ENOMEM 3
+#define GWASDEV_EOVERFLOW 4  /* caller's hit buffer too small; *n_hits holds the needed size */
+
+typedef struct gwasdev_store gwasdev_store;   /* device-resident genotype store, opaque */
+
+/* genetics/genotype/common_genotype.h:101-106 (marginal_information), byte-compatible: 192 bytes.
+ * frequency_table order is {aa, ab, bb, xx} (common_genotype.h:67-75). */
+typedef struct {
+    uint32_t margins[4], cases[4], controls[4];
+    double dMarginalEntropy, dMarginalEntropy_Y;
+    double dPbc[8];   /* P(genotype | class): cases[4] then controls[4] */
+    double dPca[8];   /* P(class | genotype): cases[4] then controls[4] */
+} gwasdev_marginal_information;
+
+/* Per-SNP association statistics written by the marginal scan (64 bytes).
+ * maf_ref_* is MinorAlleleFrequency() of algorithms/maf_func.h:46-54 (which returns max(f, 1-f));
+ * maf_pooled is the true minor-allele frequency over called genotypes of cases+controls.
+ * The chi-square tests have no counterpart in the reference; they are specified in DESIGN.md. */
+typedef struct {
+    double maf_ref_case, maf_ref_ctrl, maf_pooled, df_genotypic;
+    double chi2_allelic, p_allelic, chi2_genotypic, p_genotypic;
+} gwasdev_snp_stats;
+
+/* One screened SNP pair: SNPInteractionPair of algorithms/epistasis_func.h:59-60. */
+typedef struct {
+    uint32_t i, j;   /* i < j, table row indices */
+    double stat;     /* KSA screening statistic (epistasis_func.cpp:424-470) */
+} gwasdev_hit;
+
+typedef struct {
+    uint64_t pairs_tested;   /* pairs (i<j) this call covered */
+    uint64_t candidates;     /* pairs kept by the fp32 screen (threshold - margin) before exact re-scoring */
+    uint64_t hits;           /* pairs whose fp64 statistic exceeds the threshold */
+    uint64_t word_cells;     /* algorithmic 32-bit AND+POPC word-cells = pairs * 4 * (ceil(nca/32)+ceil(nco/32)) */
+    double screen_ms;        /* device time of the tiled screen kernel (CUDA events) */
+    double total_ms;         /* device time of the whole call incl. re-scoring */
+    uint32_t tiles, tiles_nine_cell;
+} gwasdev_pair_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+GWASDEV_API const char *gwasdev_last_error(void);
+GWASDEV_API int gwasdev_device_count(void);
+/* Replaces `new CompressedGenotypeTable5(markers, individs)` (genetics/genetic_data.cpp:60-79,
+ * genotype/compressed_genotype_table5.cpp:34-153): allocates the raw store in HBM on `device`. */
+GWASDEV_API int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_store **out);
+GWASDEV_API void gwasdev_destroy(gwasdev_store *s);
+/* Run this store's kernels on a caller-owned CUDA stream (cudaStream_t as void*); default is stream 0. */
+GWASDEV_API int gwasdev_set_stream(gwasdev_store *s, void *cuda_stream);
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+GWASDEV_API uint64_t gwasdev_launch_count(void);
+GWASDEV_API int gwasdev_synchronize(gwasdev_store *s);
+
+/* ---- geometry ------------------------------------------------------------------------------- */
+/* 16-bit blocks per bit-plane for n samples: pad4(n/16 + 1) (compressed_genotype_table5.cpp:55-64). */
+GWASDEV_API uint32_t gwasdev_plane_blocks(uint32_t n);
+
+/* ---- loading -------------------------------------------------------------------------------- */
+/* Host-side row packer with the reference's text semantics: GenoTable::addGenotypeRow(const char*, ...)
+ * (compressed_genotype_table5.cpp:277-365) incl. the first-seen label state machine
+ * (common_genotype.h:257-304). row receives [hdr][plane1: P][plane2: P] 16-bit blocks, P =
+ * gwasdev_plane_blocks(n_samples). Returns GWASDEV_EINVAL where the reference would abort. */
+GWASDEV_API int gwasdev_pack_row_text(const char *txt, size_t len, uint32_t n_samples, uint16_t *row);
+/* Upload / download n_rows rows in that layout (row stride 2P+1 blocks, host memory). */
+GWASDEV_API int gwasdev_put_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, const uint16_t *rows);
+GWASDEV_API int gwasdev_get_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint16_t *rows);
+/* GenoTable::operator()(r, c) + decodeGenotype (compressed_genotype_table5.cpp:400-432,1225-1231). */
+GWASDEV_API int gwasdev_call_at(gwasdev_store *s, uint64_t row, uint32_t col, char out[3]);
+
+/* Synthetic cohort generated directly in HBM: fixed-seed restatement of data/simulate_data.cpp:160-207
+ * over one panel of data/maf_spectrum.tab (bin_counts[b] = SNP count at MAF b %). missing_q32/2^32
+ * is the per-genotype missing probability. Labels are first-seen, as the text loader would give. */
+GWASDEV_API int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[51], uint32_t missing_q32);
+/* Host helper: exactly n_case cases (1) among n_samples, the rest controls (0). */
+GWASDEV_API int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, uint32_t n_case, uint8_t *pheno);
+
+/* ---- case / control ------------------------------------------------------------------------- */
+/* CaseControlSelectable::selectCaseControl (compressed_genotype_table5.cpp:443-575) with the stream
+ * masks of CaseControlSet (genetics/analyzable/case_control_set.cpp:77-150): P blocks each, bit c&15
+ * of block c>>4 set for member c. Builds the compacted case/control store (and, lazily, the
+ * SNP-tiled pairwise store) on the device; the raw store stays resident, so this can be called
+ * again with other masks. */
+GWASDEV_API int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask);
+GWASDEV_API int gwasdev_case_control_counts(gwasdev_store *s, uint32_t *n_case, uint32_t *n_ctrl);
+/* Compacted rows in the reference's layout [case p1: Pca][case p2: Pca][ctrl p1: Pco][ctrl p2: Pco]
+ * (16-bit blocks, Pca = gwasdev_plane_blocks(n_case)) -- layout-parity probe. */
+GWASDEV_API int gwasdev_get_selected_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint16_t *rows);
+
+/* ---- marginal scan (K1) --------------------------------------------------------------------- */
+/* Per SNP in [snp_begin, snp_end): case/control genotype counts
+ * (getCaseControlGenotypeDistribution(rIdx, ccgd, m), compressed_genotype_table5.cpp:703-747),
+ * marginal_information (computeMarginalInformation, genotype/common_genotype_func.cpp:173-219 ==
+ * computeMargins, algorithms/epistasis_func.cpp:706-721), MinorAlleleFrequency and the chi-square tests.
+ * counts: 8 per SNP = cases{aa,ab,bb,xx}, controls{aa,ab,bb,xx}. Any output pointer may be NULL.
+ * on_device = 0: outputs are host buffers (copied back inside the call); 1: device buffers. */
+GWASDEV_API int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *counts,
+                          gwasdev_marginal_information *mi, gwasdev_snp_stats *stats, int on_device);
+/* Device time (ms, CUDA events) of the scan kernel inside the last gwasdev_marginal_scan call. */
+GWASDEV_API double gwasdev_last_scan_ms(gwasdev_store *s);
+
+/* Counts through the other SingleMarkerAnalyzable overloads, for rows [snp_begin, snp_end) (host out):
+ * mode 0: getGenotypeDistribution, 4 per SNP {aa,ab,bb,xx} over the raw row (:577-607; xx = N - called,
+ *         i.e. what inline_maf_print prints, not the reference's padding-inflated xx -- defect D5);
+ * mode 1: mask-on-the-fly getCaseControlGenotypeDistribution(r, ccs, ccgd) (:609-657), 8 per SNP;
+ * mode 2: pre-selected getCaseControlGenotypeDistribution(r, ccgd) (:659-701), 8 per SNP. */
+GWASDEV_API int gwasdev_counts(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, int mode, uint32_t *out);
+
+/* ---- pair tables (K2, per-call virtuals and parity probes) ---------------------------------- */
+/* n pairs (pi[k], pj[k]) -> out[k] = case table[16] then control table[16], 4x4 row-major with the xx
+ * row/column (common_genotype.h:182-192).
+ * mode 0: getContingencyTable (:749-800), un-stratified, in the "case" half;
+ * mode 1: mask-on-the-fly getCaseControlContingencyTable(i, j, ccs, ccct) (:806-895);
+ * mode 2: pre-selected getCaseControlContingencyTable(i, j, ccct) (:896-987);
+ * mode 3: margins overload getCaseControlContingencyTable(i, j, m1, m2, ccct) (:989-1150) -- the hot one.
+ * Modes 0-2 reproduce the reference's xx cells including its padding / masked-out inflation. */
+GWASDEV_API int gwasdev_pair_tables(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, int mode,
+                        uint32_t *out);
+
+/* ---- exhaustive pairwise screen (K2+K3+K5) -------------------------------------------------- */
+/* computeBoost's pre-screening loop (algorithms/epistasis_func.cpp:397-486) over every pair i<j whose
+ * 64x64 SNP tile pair belongs to this shard (tile pairs are dealt round-robin: tile t is handled when
+ * t % n_shards == shard). Writes the pairs with stat > threshold, sorted by (i, j), into hits[0..*n_hits).
+ * hits / on_device as for the marginal scan. Requires gwasdev_select_case_control; computes the margins
+ * itself when gwasdev_marginal_scan has not been run over all SNPs. */
+GWASDEV_API int gwasdev_pairwise_scan(gwasdev_store *s, double threshold, uint32_t shard, uint32_t n_shards,
+                          gwasdev_hit *hits, uint64_t capacity, uint64_t *n_hits,
+                          gwasdev_pair_stats *stats, int on_device);
+/* KSA statistic in fp64 for given pairs (the re-scoring kernel on its own; parity probe). */
+GWASDEV_API int gwasdev_ksa(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, double *stat);
+/* Diagnostic: the screen kernel's fp32 epilogue evaluated on given pairs, to measure its distance from
+ * the fp64 statistic (the screen keeps pairs above threshold - margin). */
+GWASDEV_API int gwasdev_ksa_screen_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, float *stat);
+/* computeGTest (epistasis_func.cpp:508-704): exact log-linear G statistic by IPF and the allele-joint
+ * log-odds z for n pairs (host buffers). */
+GWASDEV_API int gwasdev_gtest(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, double *stat,
+                  double *z);
+/* pairwise_epi_test of src/test/pairwise.c:50-133 on n dense 3x3x2 tables (cs, ct: 9 ints each) and
+ * pchisq(ll, 4, 0, 0) (:44). */
+GWASDEV_API int gwasdev_pairwise_epi_test(int device, uint64_t n, const int32_t *cs, const int32_t *ct, double *ll,
+                              double *pval);
+
+/* ---- measurement helpers -------------------------------------------------------------------- */
+/* Register-only __popc throughput in 32-bit word-cells (AND+POPC) per second on `device`; the
+ * integer-pipe roofline denominator of the pairwise screen. */
+GWASDEV_API int gwasdev_popc_peak(int device, double *word_cells_per_s, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWASDEV_H */

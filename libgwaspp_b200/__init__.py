@@ -1,0 +1,319 @@
+"""libgwaspp_b200 -- B200-native association hot path of libgwaspp behind a C-ABI.
+
+This package is the thin Python plumbing over ``libgwasdev.so`` (hand-written sm_100a CUDA + the C-ABI
+declared in ``include/gwasdev.h``). The product is the shared library; Python only loads it, moves
+buffers and, for multi-GPU runs, gathers hits with ``torch.distributed``.
+
+There is no CPU path: without the compiled extension, or without a CUDA device, every compute entry
+point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .maf_spectrum import MAF_SPECTRUM, PANELS  # noqa: F401
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgwasdev.so")
+
+# genetics/genotype/common_genotype.h:101-106 of the reference (192 bytes)
+MI_DTYPE = np.dtype([("margins", "<u4", 4), ("cases", "<u4", 4), ("controls", "<u4", 4),
+                     ("dMarginalEntropy", "<f8"), ("dMarginalEntropy_Y", "<f8"), ("dPbc", "<f8", 8), ("dPca", "<f8", 8)])
+STATS_DTYPE = np.dtype([("maf_ref_case", "<f8"), ("maf_ref_ctrl", "<f8"), ("maf_pooled", "<f8"), ("df_genotypic", "<f8"),
+                        ("chi2_allelic", "<f8"), ("p_allelic", "<f8"), ("chi2_genotypic", "<f8"), ("p_genotypic", "<f8")])
+HIT_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("stat", "<f8")])
+assert MI_DTYPE.itemsize == 192 and STATS_DTYPE.itemsize == 64 and HIT_DTYPE.itemsize == 16
+
+
+class PairStats(C.Structure):
+    _fields_ = [("pairs_tested", C.c_uint64), ("candidates", C.c_uint64), ("hits", C.c_uint64),
+                ("word_cells", C.c_uint64), ("screen_ms", C.c_double), ("total_ms", C.c_double),
+                ("tiles", C.c_uint32), ("tiles_nine_cell", C.c_uint32)]
+
+
+class GwasDevError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/gwasdev.h declares (tests/test_abi.py checks header <-> library <-> this list)
+ABI_SYMBOLS = [
+    "gwasdev_last_error", "gwasdev_device_count", "gwasdev_create", "gwasdev_destroy", "gwasdev_set_stream",
+    "gwasdev_launch_count", "gwasdev_synchronize", "gwasdev_plane_blocks", "gwasdev_pack_row_text",
+    "gwasdev_put_rows", "gwasdev_get_rows", "gwasdev_call_at", "gwasdev_simulate", "gwasdev_simulate_phenotype",
+    "gwasdev_select_case_control", "gwasdev_case_control_counts", "gwasdev_get_selected_rows",
+    "gwasdev_marginal_scan", "gwasdev_last_scan_ms", "gwasdev_counts", "gwasdev_pair_tables",
+    "gwasdev_pairwise_scan", "gwasdev_ksa", "gwasdev_ksa_screen_f32", "gwasdev_gtest", "gwasdev_pairwise_epi_test",
+    "gwasdev_popc_peak",
+]
+
+
+def load_library():
+    """dlopen libgwasdev.so; fails loudly when it has not been built (python -m libgwaspp_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GwasDevError(f"{LIB_PATH} is missing: build it with `python libgwaspp_b200/build.py` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.gwasdev_last_error.restype = C.c_char_p
+    L.gwasdev_launch_count.restype = u64
+    L.gwasdev_plane_blocks.restype = u32
+    L.gwasdev_plane_blocks.argtypes = [u32]
+    L.gwasdev_last_scan_ms.restype = C.c_double
+    L.gwasdev_last_scan_ms.argtypes = [vp]
+    L.gwasdev_create.argtypes = [u64, u32, i32, C.POINTER(vp)]
+    L.gwasdev_destroy.argtypes = [vp]
+    L.gwasdev_destroy.restype = None
+    L.gwasdev_set_stream.argtypes = [vp, vp]
+    L.gwasdev_synchronize.argtypes = [vp]
+    L.gwasdev_pack_row_text.argtypes = [C.c_char_p, C.c_size_t, u32, vp]
+    L.gwasdev_put_rows.argtypes = [vp, u64, u64, vp]
+    L.gwasdev_get_rows.argtypes = [vp, u64, u64, vp]
+    L.gwasdev_call_at.argtypes = [vp, u64, u32, C.c_char_p]
+    L.gwasdev_simulate.argtypes = [vp, u64, vp, u32]
+    L.gwasdev_simulate_phenotype.argtypes = [u64, u32, u32, vp]
+    L.gwasdev_select_case_control.argtypes = [vp, vp, vp]
+    L.gwasdev_case_control_counts.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    L.gwasdev_get_selected_rows.argtypes = [vp, u64, u64, vp]
+    L.gwasdev_marginal_scan.argtypes = [vp, u64, u64, vp, vp, vp, i32]
+    L.gwasdev_counts.argtypes = [vp, u64, u64, i32, vp]
+    L.gwasdev_pair_tables.argtypes = [vp, u64, vp, vp, i32, vp]
+    L.gwasdev_pairwise_scan.argtypes = [vp, C.c_double, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(PairStats), i32]
+    L.gwasdev_ksa.argtypes = [vp, u64, vp, vp, vp]
+    L.gwasdev_ksa_screen_f32.argtypes = [vp, u64, vp, vp, vp]
+    L.gwasdev_gtest.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.gwasdev_pairwise_epi_test.argtypes = [i32, u64, vp, vp, vp, vp]
+    L.gwasdev_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise GwasDevError(f"{what}: status {rc}: {load_library().gwasdev_last_error().decode()}")
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    # torch tensor (host pinned or device): plain address
+    return C.c_void_p(a.data_ptr())
+
+
+def plane_blocks(n: int) -> int:
+    return int(load_library().gwasdev_plane_blocks(int(n)))
+
+
+def pack_row_text(line: bytes, n_samples: int) -> np.ndarray:
+    """Host-side packer with GenoTable::addGenotypeRow semantics -> [hdr][plane1][plane2] uint16 blocks."""
+    row = np.zeros(2 * plane_blocks(n_samples) + 1, np.uint16)
+    _check(load_library().gwasdev_pack_row_text(line, len(line), n_samples, _ptr(row)), "gwasdev_pack_row_text")
+    return row
+
+
+def stream_masks(pheno) -> tuple[np.ndarray, np.ndarray]:
+    """CaseControlSet stream masks (genetics/analyzable/case_control_set.cpp:77-150): bit c&15 of block c>>4.
+    pheno: 1 = case, 0 = control, anything else = neither."""
+    pheno = np.asarray(pheno)
+    n = len(pheno)
+    P = plane_blocks(n)
+    bits = np.zeros(P * 16, np.uint8)
+    ca, co = bits.copy(), bits.copy()
+    ca[:n] = pheno == 1
+    co[:n] = pheno == 0
+    w = (1 << np.arange(16, dtype=np.uint32)).astype(np.uint32)
+    return ((ca.reshape(P, 16) * w).sum(1).astype(np.uint16), (co.reshape(P, 16) * w).sum(1).astype(np.uint16))
+
+
+def simulate_phenotype(seed: int, n_samples: int, n_case: int) -> np.ndarray:
+    out = np.zeros(n_samples, np.uint8)
+    _check(load_library().gwasdev_simulate_phenotype(seed, n_samples, n_case, _ptr(out)), "gwasdev_simulate_phenotype")
+    return out
+
+
+def popc_peak(device: int = 0) -> tuple[float, float]:
+    r, mhz = C.c_double(), C.c_double()
+    _check(load_library().gwasdev_popc_peak(device, C.byref(r), C.byref(mhz)), "gwasdev_popc_peak")
+    return r.value, mhz.value
+
+
+def pairwise_epi_test(cs, ct, device: int = 0):
+    cs = np.ascontiguousarray(cs, np.int32).reshape(-1, 9)
+    ct = np.ascontiguousarray(ct, np.int32).reshape(-1, 9)
+    ll = np.zeros(len(cs))
+    p = np.zeros(len(cs))
+    _check(load_library().gwasdev_pairwise_epi_test(device, len(cs), _ptr(cs), _ptr(ct), _ptr(ll), _ptr(p)),
+           "gwasdev_pairwise_epi_test")
+    return ll, p
+
+
+def launch_count() -> int:
+    return int(load_library().gwasdev_launch_count())
+
+
+class GenoStore:
+    """Device-resident genotype store: the handle behind the reference's GenoTable for this path."""
+
+    def __init__(self, n_snps: int, n_samples: int, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        _check(self.L.gwasdev_create(n_snps, n_samples, device, C.byref(self.h)), "gwasdev_create")
+        self.n_snps, self.n_samples, self.device = n_snps, n_samples, device
+        self.P = plane_blocks(n_samples)
+        self.n_case = self.n_ctrl = None
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.gwasdev_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- loading
+    def set_stream(self, cuda_stream: int):
+        _check(self.L.gwasdev_set_stream(self.h, C.c_void_p(cuda_stream)), "gwasdev_set_stream")
+
+    def synchronize(self):
+        _check(self.L.gwasdev_synchronize(self.h), "gwasdev_synchronize")
+
+    def put_rows(self, rows: np.ndarray, first_row: int = 0):
+        rows = np.ascontiguousarray(rows, np.uint16)
+        assert rows.ndim == 2 and rows.shape[1] == 2 * self.P + 1, rows.shape
+        _check(self.L.gwasdev_put_rows(self.h, first_row, rows.shape[0], _ptr(rows)), "gwasdev_put_rows")
+
+    def put_text_rows(self, lines, first_row: int = 0):
+        self.put_rows(np.stack([pack_row_text(l, self.n_samples) for l in lines]), first_row)
+
+    def get_rows(self, first_row: int = 0, n_rows: int | None = None) -> np.ndarray:
+        n_rows = self.n_snps - first_row if n_rows is None else n_rows
+        out = np.zeros((n_rows, 2 * self.P + 1), np.uint16)
+        _check(self.L.gwasdev_get_rows(self.h, first_row, n_rows, _ptr(out)), "gwasdev_get_rows")
+        return out
+
+    def call_at(self, row: int, col: int) -> str:
+        buf = C.create_string_buffer(3)
+        _check(self.L.gwasdev_call_at(self.h, row, col, buf), "gwasdev_call_at")
+        return buf.value.decode()
+
+    def simulate(self, seed: int, panel: str = "affy6", missing_rate: float = 0.0):
+        bins = np.asarray(MAF_SPECTRUM[panel], np.uint32)
+        q = int(missing_rate * 4294967296.0) & 0xFFFFFFFF
+        _check(self.L.gwasdev_simulate(self.h, seed, _ptr(bins), q), "gwasdev_simulate")
+
+    # -- case/control
+    def select_case_control(self, pheno=None, *, case_mask=None, ctrl_mask=None):
+        if pheno is not None:
+            case_mask, ctrl_mask = stream_masks(pheno)
+        case_mask = np.ascontiguousarray(case_mask, np.uint16)
+        ctrl_mask = np.ascontiguousarray(ctrl_mask, np.uint16)
+        assert len(case_mask) == self.P and len(ctrl_mask) == self.P
+        _check(self.L.gwasdev_select_case_control(self.h, _ptr(case_mask), _ptr(ctrl_mask)), "gwasdev_select_case_control")
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(self.L.gwasdev_case_control_counts(self.h, C.byref(a), C.byref(b)), "gwasdev_case_control_counts")
+        self.n_case, self.n_ctrl = a.value, b.value
+
+    def get_selected_rows(self, first_row: int = 0, n_rows: int | None = None) -> np.ndarray:
+        n_rows = self.n_snps - first_row if n_rows is None else n_rows
+        S = 2 * (plane_blocks(self.n_case) + plane_blocks(self.n_ctrl))
+        out = np.zeros((n_rows, S), np.uint16)
+        _check(self.L.gwasdev_get_selected_rows(self.h, first_row, n_rows, _ptr(out)), "gwasdev_get_selected_rows")
+        return out
+
+    # -- marginal scan
+    def marginal_scan(self, snp_begin: int = 0, snp_end: int | None = None, *, counts=True, mi=True, stats=True):
+        """Host-buffer call (the e2e path): returns dict of numpy arrays."""
+        snp_end = self.n_snps if snp_end is None else snp_end
+        n = snp_end - snp_begin
+        out = {}
+        if counts:
+            out["counts"] = np.zeros((n, 8), np.uint32)
+        if mi:
+            out["mi"] = np.zeros(n, MI_DTYPE)
+        if stats:
+            out["stats"] = np.zeros(n, STATS_DTYPE)
+        _check(self.L.gwasdev_marginal_scan(self.h, snp_begin, snp_end, _ptr(out.get("counts")), _ptr(out.get("mi")),
+                                            _ptr(out.get("stats")), 0), "gwasdev_marginal_scan")
+        return out
+
+    def marginal_scan_into(self, snp_begin, snp_end, counts=None, mi=None, stats=None, on_device=True):
+        """Raw-pointer call: buffers are torch tensors / numpy arrays / int addresses (device when on_device)."""
+        _check(self.L.gwasdev_marginal_scan(self.h, snp_begin, snp_end, _ptr(counts), _ptr(mi), _ptr(stats),
+                                            1 if on_device else 0), "gwasdev_marginal_scan")
+
+    def last_scan_ms(self) -> float:
+        return float(self.L.gwasdev_last_scan_ms(self.h))
+
+    def counts(self, mode: int, snp_begin: int = 0, snp_end: int | None = None) -> np.ndarray:
+        snp_end = self.n_snps if snp_end is None else snp_end
+        out = np.zeros((snp_end - snp_begin, 4 if mode == 0 else 8), np.uint32)
+        _check(self.L.gwasdev_counts(self.h, snp_begin, snp_end, mode, _ptr(out)), "gwasdev_counts")
+        return out
+
+    # -- pairs
+    def _pairs(self, pi, pj):
+        pi = np.ascontiguousarray(pi, np.uint32).ravel()
+        pj = np.ascontiguousarray(pj, np.uint32).ravel()
+        assert len(pi) == len(pj)
+        return pi, pj
+
+    def pair_tables(self, pi, pj, mode: int = 3) -> np.ndarray:
+        pi, pj = self._pairs(pi, pj)
+        out = np.zeros((len(pi), 32), np.uint32)
+        _check(self.L.gwasdev_pair_tables(self.h, len(pi), _ptr(pi), _ptr(pj), mode, _ptr(out)), "gwasdev_pair_tables")
+        return out
+
+    def ksa(self, pi, pj) -> np.ndarray:
+        pi, pj = self._pairs(pi, pj)
+        out = np.zeros(len(pi))
+        _check(self.L.gwasdev_ksa(self.h, len(pi), _ptr(pi), _ptr(pj), _ptr(out)), "gwasdev_ksa")
+        return out
+
+    def ksa_screen_f32(self, pi, pj) -> np.ndarray:
+        pi, pj = self._pairs(pi, pj)
+        out = np.zeros(len(pi), np.float32)
+        _check(self.L.gwasdev_ksa_screen_f32(self.h, len(pi), _ptr(pi), _ptr(pj), _ptr(out)), "gwasdev_ksa_screen_f32")
+        return out
+
+    def gtest(self, pi, pj):
+        pi, pj = self._pairs(pi, pj)
+        s, z = np.zeros(len(pi)), np.zeros(len(pi))
+        _check(self.L.gwasdev_gtest(self.h, len(pi), _ptr(pi), _ptr(pj), _ptr(s), _ptr(z)), "gwasdev_gtest")
+        return s, z
+
+    def pairwise_scan(self, threshold: float = 30.0, shard: int = 0, n_shards: int = 1, capacity: int = 1 << 20,
+                      hits=None, on_device: bool = False):
+        """computeBoost's pre-screen. Returns (hits[HIT_DTYPE] sorted by (i, j), PairStats).
+        With on_device=True, `hits` must be a device buffer of capacity*16 bytes (torch tensor or address)."""
+        st = PairStats()
+        n = C.c_uint64()
+        own = hits is None
+        if own:
+            assert not on_device
+            hits = np.zeros(capacity, HIT_DTYPE)
+        rc = self.L.gwasdev_pairwise_scan(self.h, threshold, shard, n_shards, _ptr(hits), capacity, C.byref(n),
+                                          C.byref(st), 1 if on_device else 0)
+        if rc == 4 and own:   # GWASDEV_EOVERFLOW: grow and retry once
+            return self.pairwise_scan(threshold, shard, n_shards, int(n.value), None, False)
+        _check(rc, "gwasdev_pairwise_scan")
+        return (hits[: n.value].copy() if own else int(n.value)), st

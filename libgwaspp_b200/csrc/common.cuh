@@ -1,0 +1,145 @@
+// Internal definitions shared by the translation units of libgwasdev.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "gwasdev.h"
+
+namespace gwasdev {
+
+// ---- error plumbing ------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern unsigned long long g_launches;   // kernels launched by this library (gwasdev_launch_count)
+
+#define GW_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            gwasdev::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,   \
+                               __LINE__);                                                          \
+            return e_ == cudaErrorMemoryAllocation ? GWASDEV_ENOMEM : GWASDEV_ENODEVICE;           \
+        }                                                                                          \
+    } while (0)
+
+#define GW_LAUNCHED()                                                                              \
+    do {                                                                                           \
+        ++gwasdev::g_launches;                                                                     \
+        GW_CUDA(cudaGetLastError());                                                               \
+    } while (0)
+
+#define GW_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            gwasdev::set_error(__VA_ARGS__);                                                       \
+            return GWASDEV_EINVAL;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+// ---- geometry ------------------------------------------------------------------------------------
+constexpr int TILE = 64;   // SNPs per side of a pairwise tile
+
+__host__ __device__ inline uint32_t plane_blocks(uint32_t n) {   // pad4(n/16 + 1), 16-bit blocks
+    uint32_t b = n / 16 + 1;
+    return (b + 3u) & ~3u;
+}
+__host__ __device__ inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+// ---- first-seen genotype labelling ---------------------------------------------------------------
+// Genotype "encodings" are 4*idx(c1)+idx(c2) over the alphabet ACGT; 0, 5, 10, 15 are homozygous.
+// Codes: first homozygote seen in the row -> 1 (plane1), heterozygote -> 2 (plane2), second
+// homozygote -> 3 (both). The 16-bit row header keeps state<<12 | enc(code1)<<8 | enc(code2)<<4 |
+// enc(code3) with the same bit pattern the reference's header state machine leaves behind
+// (genetics/genotype/common_genotype.h:257-304), so stored headers round-trip through decodeGenotype.
+struct Labeler {
+    uint16_t head;
+    uint64_t codes;   // 4 bits per encoding, 0 = not seen yet
+    __host__ __device__ void reset() { head = 0; codes = 0; }
+    // returns 1..3, or -1 for a sequence the reference rejects (third spelling of a kind)
+    __host__ __device__ int code(int enc) {
+        int c = (int)((codes >> (4 * enc)) & 0xF);
+        if (c) return c;
+        const bool hom = (enc == 0 || enc == 5 || enc == 10 || enc == 15);
+        const uint16_t state = head & 0xF000;
+        uint16_t keep, next;
+        int shift;
+        if (state == 0x0000)      { keep = 0x0000; if (hom) { next = 0x1000; shift = 8; c = 1; } else { next = 0x2000; shift = 4; c = 2; } }
+        else if (state == 0x1000) { keep = 0x0F00; if (hom) { next = 0x3000; shift = 0; c = 3; } else { next = 0x4000; shift = 4; c = 2; } }
+        else if (state == 0x2000) { if (!hom) return -1; keep = 0x00F0; next = 0x4000; shift = 8; c = 1; }
+        else if (state == 0x3000) { if (hom) return -1;  keep = 0x0F0F; next = 0x7000; shift = 4; c = 2; }
+        else if (state == 0x4000) { if (!hom) return -1; keep = 0x0FF0; next = 0x7000; shift = 0; c = 3; }
+        else return -1;
+        head = (uint16_t)((head & keep) | next | (enc << shift));
+        codes |= (uint64_t)c << (4 * enc);
+        return c;
+    }
+};
+
+// ---- counter-based generator for the synthetic cohort ("synthetic cohort") ---------
+__host__ __device__ inline uint64_t sim_hash(uint64_t seed, uint64_t a, uint64_t b) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (a + 1) + 0xD1B54A32D192ED03ULL * (b + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+constexpr uint64_t SIM_STREAM_BIN = 0xFFFFFFFF00000001ULL;
+constexpr uint64_t SIM_STREAM_FREQ = 0xFFFFFFFF00000002ULL;
+constexpr uint64_t SIM_STREAM_PHENO = 0xFFFFFFFF00000003ULL;
+constexpr uint64_t SIM_STREAM_MISS = 0x8000000000000000ULL;
+
+// ---- per-SNP record used by the pairwise screen's fp32 epilogue -----------------------------------
+// For SNP x with class counts c_k[g] (k: 0 case, 1 control; g: aa, ab, bb), margins m[g] = c_0[g]+c_1[g]
+// and class sizes n_k (incl. missing):
+//   pca[k][g]  = c_k[g] / m[g]                       P(class | genotype)      (row role, SNP "A")
+//   lpca[k][g] = ln pca[k][g]            (0 when c_k[g] == 0)
+//   w[k][g]    = (c_k[g] / n_k) / m[g]               P(genotype | class)/m    (column role, SNP "B"; NaN when m[g]==0)
+//   lw[k][g]   = ln(c_k[g] / n_k) - ln m[g]  (0 when c_k[g] == 0)
+struct __align__(16) PairSide {
+    float pca[2][3];
+    float lpca[2][3];
+    float w[2][3];
+    float lw[2][3];
+    uint32_t cnt[2][4];   // c_k[aa, ab, bb, xx]
+};
+static_assert(sizeof(PairSide) == 128, "PairSide is 128 bytes");
+
+}  // namespace gwasdev
+
+// ---- the store -----------------------------------------------------------------------------------
+struct gwasdev_store {
+    int device = 0;
+    cudaStream_t stream = 0;
+    uint64_t M = 0;        // SNPs (rows)
+    uint32_t N = 0;        // samples (columns)
+    uint32_t P = 0;        // 16-bit blocks per raw plane (reference geometry)
+    uint32_t Wr = 0;       // 32-bit words per raw plane on the device (multiple of 4 -> 16-byte rows)
+    uint16_t *d_hdr = nullptr;    // [M] row headers
+    uint32_t *d_raw = nullptr;    // [M][2][Wr]: plane1 (codes 1,3), plane2 (codes 2,3); sample c = bit c&31 of word c>>5
+
+    // case/control selection
+    bool selected = false;
+    uint32_t n_case = 0, n_ctrl = 0;
+    uint32_t Pca = 0, Pco = 0;    // reference geometry of the compacted streams (16-bit blocks)
+    uint32_t Wc = 0, Wt = 0;      // words per plane per class in the scan layout (multiples of 4)
+    uint32_t Kc = 0, Kt = 0;      // tight word counts ceil(n/32) (pairwise layout)
+    uint32_t *d_case_mask = nullptr, *d_ctrl_mask = nullptr;   // [Wr]
+    uint32_t *d_case_idx = nullptr, *d_ctrl_idx = nullptr;     // sample index of the k-th case / control
+    uint32_t *d_sel = nullptr;    // scan layout [M][case p1: Wc][case p2: Wc][ctrl p1: Wt][ctrl p2: Wt]
+
+    // pairwise layout: one-hot planes, word-major so that a 64-SNP tile row is 256 contiguous bytes
+    bool pw_built = false;
+    uint64_t Mpad = 0;            // M rounded up to a multiple of TILE
+    uint32_t *d_pw = nullptr;     // [3 planes aa,ab,bb][K = Kc + Kt][Mpad]
+    void *tmap = nullptr;         // host copy of the CUtensorMap over d_pw (128 bytes, 64-byte aligned)
+
+    // margins
+    bool mi_valid = false;
+    gwasdev_marginal_information *d_mi = nullptr;   // [M]
+    gwasdev::PairSide *d_side = nullptr;            // [Mpad]
+    uint8_t *d_tile_missing = nullptr;              // [Mpad/TILE] 1 when any SNP of the tile has missing calls
+    bool side_valid = false;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    double last_scan_ms = 0.0;
+};

@@ -1,0 +1,293 @@
+// K1: per-SNP marginal scan over the compacted case/control store.
+//
+// One pass over HBM: every warp streams whole SNP rows with 128-bit loads, reduces the six popcount
+// sums with REDUX (warp-level integer reduce), parks the totals of SNP (base+l) in lane l, and after
+// 32 SNPs every lane finishes one SNP in fp64: genotype counts (compressed_genotype_table5.cpp:703-747),
+// marginal_information (genotype/common_genotype_func.cpp:173-219), MinorAlleleFrequency
+// (algorithms/maf_func.h:46-54) and the allelic / genotypic chi-square tests (no reference
+// counterpart). Bound: HBM bandwidth; algorithmic bytes = n_samples / 4 per SNP.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gwasdev {
+
+__device__ __forceinline__ uint32_t popc4(const uint4 v) {
+    return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+}
+__device__ __forceinline__ uint4 and4(const uint4 a, const uint4 b) {
+    return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {   // read-once data: do not allocate in L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// chi-square upper tail for df in {1, 2}: pchisq(x, df, lower=0) == gsl_cdf_chisq_Q(x, df)
+__device__ __forceinline__ double chisq_upper(double x, int df) {
+    if (!(x > 0.0)) return x != x ? x : 1.0;
+    return df == 1 ? erfc(sqrt(0.5 * x)) : exp(-0.5 * x);
+}
+
+// fp64 arithmetic below uses the _rn intrinsics so that nvcc cannot contract a*b+c into an FMA: the
+// reference is compiled for x86-64 without FMA and rounds every product and sum separately.
+__device__ __forceinline__ void fill_marginal_information(const uint32_t ca[4], const uint32_t co[4],
+                                                          uint32_t n_individs, gwasdev_marginal_information &m) {
+    const uint32_t n_ca = ca[3] + ca[0] + ca[1] + ca[2], n_co = co[3] + co[0] + co[1] + co[2];
+    double h = 0.0, hy = 0.0;
+    const double n = (double)n_individs;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t mar = ca[g] + co[g];
+        m.margins[g] = mar; m.cases[g] = ca[g]; m.controls[g] = co[g];
+        // zero-count classes are left unwritten by the reference and read as 0.0 under its zeroing
+        // oracle allocator (SURVEY.md defect D1): write the zeros explicitly.
+        double pbc_ca = 0.0, pca_ca = 0.0, pbc_co = 0.0, pca_co = 0.0;
+        if (mar > 0) { const double t = __ddiv_rn((double)mar, n); h = __dadd_rn(h, __dmul_rn(-t, log(t))); }
+        if (ca[g] > 0) {
+            const double t = __ddiv_rn((double)ca[g], n);
+            hy = __dadd_rn(hy, __dmul_rn(-t, log(t)));
+            pbc_ca = __ddiv_rn((double)ca[g], (double)n_ca);
+            pca_ca = __ddiv_rn((double)ca[g], (double)mar);
+        }
+        if (co[g] > 0) {
+            const double t = __ddiv_rn((double)co[g], n);
+            hy = __dadd_rn(hy, __dmul_rn(-t, log(t)));
+            pbc_co = __ddiv_rn((double)co[g], (double)n_co);
+            pca_co = __ddiv_rn((double)co[g], (double)mar);
+        }
+        m.dPbc[g] = pbc_ca; m.dPbc[4 + g] = pbc_co; m.dPca[g] = pca_ca; m.dPca[4 + g] = pca_co;
+    }
+    m.dMarginalEntropy = h;
+    m.dMarginalEntropy_Y = hy;
+}
+
+__device__ __forceinline__ double maf_reference(const uint32_t ft[4]) {   // algorithms/maf_func.h:46-54
+    double tot = ft[0], maf = 2.0 * tot;
+    tot += ft[1]; maf += ft[1];
+    tot += ft[2];
+    maf /= tot;
+    if (maf < 0.5) maf = 1.0 - maf;
+    return maf;
+}
+
+__device__ __forceinline__ void fill_stats(const uint32_t ca[4], const uint32_t co[4], gwasdev_snp_stats &o) {
+    o.maf_ref_case = maf_reference(ca);
+    o.maf_ref_ctrl = maf_reference(co);
+    const double a_ca = 2.0 * ca[0] + ca[1], b_ca = 2.0 * ca[2] + ca[1];
+    const double a_co = 2.0 * co[0] + co[1], b_co = 2.0 * co[2] + co[1];
+    const double r1 = a_ca + b_ca, r2 = a_co + b_co, c1 = a_ca + a_co, c2 = b_ca + b_co, t = r1 + r2;
+    o.maf_pooled = t > 0 ? fmin(c1, c2) / t : nan("");
+    // allelic 2x2, df 1
+    if (r1 == 0 || r2 == 0 || c1 == 0 || c2 == 0) { o.chi2_allelic = 0.0; o.p_allelic = 1.0; }
+    else {
+        const double d = a_ca * b_co - b_ca * a_co;
+        o.chi2_allelic = t * d * d / (r1 * r2 * c1 * c2);
+        o.p_allelic = chisq_upper(o.chi2_allelic, 1);
+    }
+    // genotypic 2x3 Pearson over non-empty genotype columns
+    const double g1 = (double)ca[0] + ca[1] + ca[2], g2 = (double)co[0] + co[1] + co[2], gt = g1 + g2;
+    int cols = 0;
+    double x = 0.0;
+    if (g1 > 0 && g2 > 0) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const double c = (double)ca[g] + co[g];
+            if (c == 0) continue;
+            ++cols;
+            const double e1 = g1 * c / gt, e2 = g2 * c / gt;
+            x += (ca[g] - e1) * (ca[g] - e1) / e1 + (co[g] - e2) * (co[g] - e2) / e2;
+        }
+    }
+    const int df = cols > 1 ? cols - 1 : 0;
+    o.df_genotypic = df;
+    if (df == 0) { o.chi2_genotypic = 0.0; o.p_genotypic = 1.0; }
+    else { o.chi2_genotypic = x; o.p_genotypic = chisq_upper(x, df); }
+}
+
+// grid: persistent, 4 CTAs of 256 threads per SM; warp w takes batches of 32 consecutive SNPs.
+__global__ void __launch_bounds__(256, 4)
+marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Wc4, uint32_t Wt4,
+                     uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
+                     uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
+                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_snps = snp_end - snp_begin, n_batches = (n_snps + 31) / 32;
+    for (uint64_t batch = warp; batch < n_batches; batch += n_warps) {
+        const uint64_t base = snp_begin + batch * 32;
+        const uint32_t in_batch = (uint32_t)min((uint64_t)32, snp_end - base);
+        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // this lane's SNP totals
+        for (uint32_t sidx = 0; sidx < in_batch; ++sidx) {
+            const uint4 *row = sel + (base + sidx) * (uint64_t)stride4;
+            uint32_t s1 = 0, s2 = 0, sb = 0, t1 = 0, t2 = 0, tb = 0;
+            for (uint32_t c = lane; c < Wc4; c += 32) {
+                const uint4 x = ld_stream(row + c), y = ld_stream(row + Wc4 + c);
+                s1 += popc4(x); s2 += popc4(y); sb += popc4(and4(x, y));
+            }
+            const uint4 *ctl = row + 2 * Wc4;
+            for (uint32_t c = lane; c < Wt4; c += 32) {
+                const uint4 x = ld_stream(ctl + c), y = ld_stream(ctl + Wt4 + c);
+                t1 += popc4(x); t2 += popc4(y); tb += popc4(and4(x, y));
+            }
+            s1 = __reduce_add_sync(0xffffffffu, s1); s2 = __reduce_add_sync(0xffffffffu, s2);
+            sb = __reduce_add_sync(0xffffffffu, sb); t1 = __reduce_add_sync(0xffffffffu, t1);
+            t2 = __reduce_add_sync(0xffffffffu, t2); tb = __reduce_add_sync(0xffffffffu, tb);
+            if (lane == sidx) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
+        }
+        if (lane < in_batch) {
+            const uint64_t snp = base + lane, o = snp - out_base;
+            uint32_t ca[4], co[4];
+            ca[0] = m1c - mbc; ca[1] = m2c - mbc; ca[2] = mbc; ca[3] = n_case - ca[0] - ca[1] - ca[2];
+            co[0] = m1t - mbt; co[1] = m2t - mbt; co[2] = mbt; co[3] = n_ctrl - co[0] - co[1] - co[2];
+            if (counts) {
+                uint4 *dst = reinterpret_cast<uint4 *>(counts + 8 * o);
+                dst[0] = make_uint4(ca[0], ca[1], ca[2], ca[3]);
+                dst[1] = make_uint4(co[0], co[1], co[2], co[3]);
+            }
+            if (mi) {
+                gwasdev_marginal_information m;
+                fill_marginal_information(ca, co, n_case + n_ctrl, m);
+                mi[o] = m;
+            }
+            if (stats) {
+                gwasdev_snp_stats st;
+                fill_stats(ca, co, st);
+                stats[o] = st;
+            }
+        }
+    }
+}
+
+// Counts on the RAW rows, optionally through the case/control stream masks (mask-on-the-fly overloads
+// compressed_genotype_table5.cpp:577-607 and :609-657). One warp per SNP.
+__global__ void raw_counts_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, const uint32_t *__restrict__ mca,
+                                  const uint32_t *__restrict__ mco, uint32_t n_a, uint32_t n_b, uint64_t snp_begin,
+                                  uint64_t snp_end, uint32_t *__restrict__ out, int per_snp) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t snp = snp_begin + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (snp >= snp_end) return;
+    const uint32_t *p1 = raw + snp * 2ull * Wr, *p2 = p1 + Wr;
+    uint32_t s1 = 0, s2 = 0, sb = 0, t1 = 0, t2 = 0, tb = 0;
+    for (uint32_t w = lane; w < Wr; w += 32) {
+        const uint32_t x = p1[w], y = p2[w];
+        const uint32_t ma = mca ? mca[w] : 0xffffffffu;
+        s1 += __popc(x & ma); s2 += __popc(y & ma); sb += __popc(x & y & ma);
+        if (mco) { const uint32_t mb = mco[w]; t1 += __popc(x & mb); t2 += __popc(y & mb); tb += __popc(x & y & mb); }
+    }
+    s1 = __reduce_add_sync(0xffffffffu, s1); s2 = __reduce_add_sync(0xffffffffu, s2); sb = __reduce_add_sync(0xffffffffu, sb);
+    t1 = __reduce_add_sync(0xffffffffu, t1); t2 = __reduce_add_sync(0xffffffffu, t2); tb = __reduce_add_sync(0xffffffffu, tb);
+    if (lane == 0) {
+        uint32_t *o = out + (snp - snp_begin) * per_snp;
+        o[0] = s1 - sb; o[1] = s2 - sb; o[2] = sb; o[3] = n_a - s1 - s2 + sb;
+        if (per_snp == 8) { o[4] = t1 - tb; o[5] = t2 - tb; o[6] = tb; o[7] = n_b - t1 - t2 + tb; }
+    }
+}
+
+}  // namespace gwasdev
+
+using namespace gwasdev;
+
+// Launch the scan with DEVICE output pointers (any may be NULL). Outputs are indexed from snp_begin.
+int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
+                          gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats) {
+    int sms = 0;
+    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const uint64_t batches = (snp_end - snp_begin + 31) / 32;
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 4, (batches + 7) / 8));
+    GW_CUDA(cudaEventRecord(s->ev0, s->stream));
+    marginal_scan_kernel<<<blocks, 256, 0, s->stream>>>(
+        reinterpret_cast<const uint4 *>(s->d_sel), (2 * (s->Wc + s->Wt)) / 4, s->Wc / 4, s->Wt / 4, s->n_case,
+        s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+    GW_LAUNCHED();
+    GW_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return GWASDEV_OK;
+}
+
+extern "C" {
+
+int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *counts,
+                          gwasdev_marginal_information *mi, gwasdev_snp_stats *stats, int on_device) {
+    GW_REQUIRE(s != nullptr, "gwasdev_marginal_scan: NULL store");
+    GW_REQUIRE(s->selected, "gwasdev_marginal_scan: call gwasdev_select_case_control first");
+    GW_REQUIRE(snp_begin <= snp_end && snp_end <= s->M, "gwasdev_marginal_scan: bad SNP range [%llu, %llu)",
+               (unsigned long long)snp_begin, (unsigned long long)snp_end);
+    if (snp_begin == snp_end) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint64_t n = snp_end - snp_begin;
+    const bool full = snp_begin == 0 && snp_end == s->M;
+    if (on_device) {
+        int rc = gwasdev_internal_scan(s, snp_begin, snp_end, counts, mi, stats);
+        return rc;
+    }
+    uint32_t *d_counts = nullptr;
+    gwasdev_marginal_information *d_mi = nullptr;
+    gwasdev_snp_stats *d_stats = nullptr;
+    bool own_mi = false;
+    if (counts) GW_CUDA(cudaMalloc(&d_counts, n * 8 * sizeof(uint32_t)));
+    if (stats) GW_CUDA(cudaMalloc(&d_stats, n * sizeof(gwasdev_snp_stats)));
+    if (mi) {
+        if (full) {   // keep the full-table margins resident for the pairwise screen
+            if (!s->d_mi) GW_CUDA(cudaMalloc(&s->d_mi, s->M * sizeof(gwasdev_marginal_information)));
+            d_mi = s->d_mi;
+        } else { GW_CUDA(cudaMalloc(&d_mi, n * sizeof(gwasdev_marginal_information))); own_mi = true; }
+    }
+    int rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, d_mi, d_stats);
+    cudaError_t e = cudaSuccess;
+    if (rc == GWASDEV_OK) {
+        if (counts) e = cudaMemcpyAsync(counts, d_counts, n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess && stats) e = cudaMemcpyAsync(stats, d_stats, n * sizeof(gwasdev_snp_stats), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess && mi) e = cudaMemcpyAsync(mi, d_mi, n * sizeof(gwasdev_marginal_information), cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    }
+    cudaFree(d_counts); cudaFree(d_stats);
+    if (own_mi) cudaFree(d_mi);
+    if (rc != GWASDEV_OK) return rc;
+    if (e != cudaSuccess) { set_error("gwasdev_marginal_scan: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    if (mi && full) { s->mi_valid = true; s->side_valid = false; }
+    return GWASDEV_OK;
+}
+
+double gwasdev_last_scan_ms(gwasdev_store *s) {
+    if (!s || !s->ev0) return -1.0;
+    cudaSetDevice(s->device);
+    if (cudaEventSynchronize(s->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    return ms;
+}
+
+int gwasdev_counts(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, int mode, uint32_t *out) {
+    GW_REQUIRE(s && out, "gwasdev_counts: NULL argument");
+    GW_REQUIRE(mode >= 0 && mode <= 2, "gwasdev_counts: mode %d", mode);
+    GW_REQUIRE(snp_begin <= snp_end && snp_end <= s->M, "gwasdev_counts: bad SNP range");
+    GW_REQUIRE(mode == 0 || s->selected, "gwasdev_counts: mode %d needs gwasdev_select_case_control", mode);
+    if (snp_begin == snp_end) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint64_t n = snp_end - snp_begin;
+    const int per = mode == 0 ? 4 : 8;
+    uint32_t *d_out = nullptr;
+    GW_CUDA(cudaMalloc(&d_out, n * per * sizeof(uint32_t)));
+    int rc = GWASDEV_OK;
+    cudaError_t e = cudaSuccess;
+    if (mode == 2) rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_out, nullptr, nullptr);
+    else {
+        const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
+        raw_counts_kernel<<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, mode == 1 ? s->d_case_mask : nullptr,
+                                                         mode == 1 ? s->d_ctrl_mask : nullptr,
+                                                         mode == 1 ? s->n_case : s->N, s->n_ctrl, snp_begin, snp_end, d_out, per);
+        ++g_launches;
+        e = cudaGetLastError();
+    }
+    if (rc == GWASDEV_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * per * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
+    if (rc == GWASDEV_OK && e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_out);
+    if (rc != GWASDEV_OK) return rc;
+    if (e != cudaSuccess) { set_error("gwasdev_counts: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    return GWASDEV_OK;
+}
+
+}  // extern "C"

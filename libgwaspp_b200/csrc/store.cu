@@ -1,0 +1,473 @@
+// Device-resident genotype store: creation, row upload/download, synthetic cohort generation,
+// case/control compaction (K0) and the SNP-tiled pairwise layout.
+//
+// Replaces CompressedGenotypeTable5's host table (genetics/genotype/compressed_genotype_table5.cpp:
+// initialize :34-153, addGenotypeRow :277-365, operator() :400-432, selectCaseControl :443-575).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gwasdev {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+// ---- kernels -------------------------------------------------------------------------------------
+
+// reference row [hdr][plane1: P][plane2: P] (16-bit blocks, odd stride) -> hdr[], raw[M][2][Wr] words
+__global__ void unpack_rows_kernel(const uint16_t *__restrict__ rows, uint32_t P, uint32_t Wr,
+                                   uint16_t *__restrict__ hdr, uint32_t *__restrict__ raw,
+                                   uint64_t first_row) {
+    const uint64_t r = blockIdx.x;
+    const uint16_t *src = rows + r * (2ull * P + 1);
+    uint32_t *dst = raw + (first_row + r) * 2ull * Wr;
+    if (threadIdx.x == 0) hdr[first_row + r] = src[0];
+    for (uint32_t w = threadIdx.x; w < 2 * Wr; w += blockDim.x) {
+        const uint32_t plane = w / Wr, k = w % Wr;
+        uint32_t v = 0;
+        if (2 * k < P) v = src[1 + plane * P + 2 * k];
+        if (2 * k + 1 < P) v |= (uint32_t)src[1 + plane * P + 2 * k + 1] << 16;
+        dst[w] = v;
+    }
+}
+
+__global__ void pack_rows_kernel(const uint16_t *__restrict__ hdr, const uint32_t *__restrict__ raw,
+                                 uint32_t P, uint32_t Wr, uint16_t *__restrict__ rows, uint64_t first_row) {
+    const uint64_t r = blockIdx.x;
+    uint16_t *dst = rows + r * (2ull * P + 1);
+    const uint32_t *src = raw + (first_row + r) * 2ull * Wr;
+    if (threadIdx.x == 0) dst[0] = hdr[first_row + r];
+    for (uint32_t b = threadIdx.x; b < 2 * P; b += blockDim.x) {
+        const uint32_t plane = b / P, k = b % P;
+        dst[1 + b] = (uint16_t)(src[plane * Wr + (k >> 1)] >> ((k & 1) * 16));
+    }
+}
+
+// K0. One thread builds one 32-bit output word of both planes of one class by gathering the bits of
+// the class members (idx[k] = sample index of the k-th member, ascending), i.e. the dense streams of
+// selectCaseControl (compressed_genotype_table5.cpp:520-572) without its bit-serial walk.
+__global__ void select_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, const uint32_t *__restrict__ idx,
+                              uint32_t n_class, uint32_t Wout, uint32_t *__restrict__ sel,
+                              uint32_t sel_stride, uint32_t class_off) {
+    const uint64_t snp = blockIdx.x;
+    const uint32_t *p1 = raw + snp * 2ull * Wr, *p2 = p1 + Wr;
+    uint32_t *o1 = sel + snp * (uint64_t)sel_stride + class_off, *o2 = o1 + Wout;
+    for (uint32_t w = threadIdx.x; w < Wout; w += blockDim.x) {
+        uint32_t a = 0, b = 0;
+        const uint32_t k0 = w * 32;
+        for (uint32_t t = 0; t < 32 && k0 + t < n_class; ++t) {
+            const uint32_t s = idx[k0 + t];
+            a |= ((p1[s >> 5] >> (s & 31)) & 1u) << t;
+            b |= ((p2[s >> 5] >> (s & 31)) & 1u) << t;
+        }
+        o1[w] = a;
+        o2[w] = b;
+    }
+}
+
+// scan layout -> pairwise layout: one-hot planes aa = p1&~p2, ab = p2&~p1, bb = p1&p2, word-major
+// [plane][k][snp] so that 64 consecutive SNPs of one word index are 256 contiguous bytes (one TMA row).
+__global__ void build_pairwise_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc,
+                                      uint32_t Wt, uint32_t Kc, uint32_t Kt, uint64_t M, uint64_t Mpad,
+                                      uint32_t *__restrict__ pw) {
+    const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = blockIdx.y * blockDim.y + threadIdx.y, K = Kc + Kt;
+    if (snp >= Mpad || k >= K) return;
+    uint32_t p1 = 0, p2 = 0;
+    if (snp < M) {
+        const uint32_t *row = sel + snp * (uint64_t)sel_stride;
+        if (k < Kc) { p1 = row[k]; p2 = row[Wc + k]; }
+        else { p1 = row[2 * Wc + (k - Kc)]; p2 = row[2 * Wc + Wt + (k - Kc)]; }
+    }
+    const uint32_t bb = p1 & p2;
+    pw[(0ull * K + k) * Mpad + snp] = p1 ^ bb;
+    pw[(1ull * K + k) * Mpad + snp] = p2 ^ bb;
+    pw[(2ull * K + k) * Mpad + snp] = bb;
+}
+
+// compacted rows back in the reference's 16-bit block layout (layout-parity probe)
+__global__ void export_selected_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc,
+                                       uint32_t Wt, uint32_t Pca, uint32_t Pco, uint16_t *__restrict__ out,
+                                       uint64_t first_row) {
+    const uint64_t r = blockIdx.x;
+    const uint32_t *row = sel + (first_row + r) * (uint64_t)sel_stride;
+    const uint32_t S = 2 * (Pca + Pco);
+    uint16_t *dst = out + r * (uint64_t)S;
+    for (uint32_t b = threadIdx.x; b < S; b += blockDim.x) {
+        uint32_t off, k;
+        if (b < Pca) { off = 0; k = b; }
+        else if (b < 2 * Pca) { off = Wc; k = b - Pca; }
+        else if (b < 2 * Pca + Pco) { off = 2 * Wc; k = b - 2 * Pca; }
+        else { off = 2 * Wc + Wt; k = b - 2 * Pca - Pco; }
+        const uint32_t W = (b < 2 * Pca) ? Wc : Wt;
+        const uint32_t word = (k >> 1) < W ? row[off + (k >> 1)] : 0u;
+        dst[b] = (uint16_t)(word >> ((k & 1) * 16));
+    }
+}
+
+// Synthetic cohort, one thread per SNP (sequential selection sampling over the 2N allele slots).
+// Distribution restated from data/simulate_data.cpp:160-207; see DESIGN.md "synthetic cohort".
+__global__ void simulate_kernel(uint64_t seed, const uint32_t *__restrict__ cum_bins, uint32_t N,
+                                uint32_t missing_q32, uint16_t *__restrict__ hdr,
+                                uint32_t *__restrict__ raw, uint32_t Wr, uint64_t M) {
+    const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (snp >= M) return;
+    const uint64_t total = cum_bins[50];
+    const uint64_t r = sim_hash(seed, snp, SIM_STREAM_BIN) % total;
+    int bin = 50;
+    for (int b = 0; b < 51; ++b)
+        if (r < cum_bins[b]) { bin = b; break; }
+    const uint64_t frac = sim_hash(seed, snp, SIM_STREAM_FREQ) % 1000;
+    const uint64_t slots = 2ull * N;
+    const uint64_t want = ((1000ull * bin + frac) * slots) / 100000ull;   // floor(p * 2N)
+    uint64_t chosen = 0;
+    Labeler lab;
+    lab.reset();
+    uint32_t *p1 = raw + snp * 2ull * Wr, *p2 = p1 + Wr;
+    const uint32_t words = (N + 31) / 32;
+    for (uint32_t w = 0; w < Wr; ++w) {
+        uint32_t a = 0, b = 0;
+        if (w < words) {
+            for (uint32_t t = 0; t < 32; ++t) {
+                const uint32_t s = w * 32 + t;
+                if (s >= N) break;
+                int minor = 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint64_t slot = 2ull * s + h, left = slots - slot;
+                    const uint64_t u = sim_hash(seed, snp, slot) >> 32;
+                    if (((u * left) >> 32) < want - chosen) { ++minor; ++chosen; }
+                }
+                bool missing = false;
+                if (missing_q32)
+                    missing = (uint32_t)(sim_hash(seed, snp, SIM_STREAM_MISS | s) >> 32) < missing_q32;
+                if (!missing) {
+                    const int enc = minor == 0 ? 0 : (minor == 1 ? 1 : 5);   // "AA", "AC", "CC"
+                    const int c = lab.code(enc);
+                    a |= (uint32_t)(c & 1) << t;
+                    b |= (uint32_t)((c >> 1) & 1) << t;
+                }
+            }
+        }
+        p1[w] = a;
+        p2[w] = b;
+    }
+    hdr[snp] = lab.head;
+}
+
+}  // namespace gwasdev
+
+using namespace gwasdev;
+
+// ---- C-ABI ---------------------------------------------------------------------------------------
+extern "C" {
+
+const char *gwasdev_last_error(void) { return g_err; }
+uint64_t gwasdev_launch_count(void) { return g_launches; }
+uint32_t gwasdev_plane_blocks(uint32_t n) { return plane_blocks(n); }
+
+int gwasdev_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_store **out) {
+    GW_REQUIRE(out != nullptr, "gwasdev_create: out is NULL");
+    *out = nullptr;
+    GW_REQUIRE(n_snps > 0 && n_samples > 0, "gwasdev_create: empty table (%llu x %u)",
+               (unsigned long long)n_snps, n_samples);
+    GW_REQUIRE(n_snps < (1ull << 31), "gwasdev_create: more than 2^31 SNPs");
+    const int ndev = gwasdev_device_count();
+    if (ndev == 0 || device < 0 || device >= ndev) {
+        set_error("gwasdev_create: CUDA device %d not available (%d visible); this library has no CPU path",
+                  device, ndev);
+        return GWASDEV_ENODEVICE;
+    }
+    GW_CUDA(cudaSetDevice(device));
+    gwasdev_store *s = new gwasdev_store();
+    s->device = device;
+    s->M = n_snps;
+    s->N = n_samples;
+    s->P = plane_blocks(n_samples);
+    s->Wr = round_up(s->P / 2, 4);
+    s->Mpad = (n_snps + TILE - 1) / TILE * TILE;
+    cudaError_t e = cudaMalloc(&s->d_hdr, n_snps * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_raw, n_snps * 2ull * s->Wr * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_hdr, 0, n_snps * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_raw, 0, n_snps * 2ull * s->Wr * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
+    if (e != cudaSuccess) {
+        set_error("gwasdev_create: %s", cudaGetErrorString(e));
+        gwasdev_destroy(s);
+        return e == cudaErrorMemoryAllocation ? GWASDEV_ENOMEM : GWASDEV_ENODEVICE;
+    }
+    *out = s;
+    return GWASDEV_OK;
+}
+
+static void free_selection(gwasdev_store *s) {
+    cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
+    cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
+    s->d_case_mask = s->d_ctrl_mask = s->d_case_idx = s->d_ctrl_idx = s->d_sel = s->d_pw = nullptr;
+    s->d_mi = nullptr; s->d_side = nullptr; s->d_tile_missing = nullptr;
+    free(s->tmap); s->tmap = nullptr;
+    s->selected = s->pw_built = s->mi_valid = s->side_valid = false;
+}
+
+void gwasdev_destroy(gwasdev_store *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    free_selection(s);
+    cudaFree(s->d_hdr); cudaFree(s->d_raw);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->ev3) cudaEventDestroy(s->ev3);
+    delete s;
+}
+
+int gwasdev_set_stream(gwasdev_store *s, void *cuda_stream) {
+    GW_REQUIRE(s != nullptr, "gwasdev_set_stream: NULL store");
+    s->stream = (cudaStream_t)cuda_stream;
+    return GWASDEV_OK;
+}
+
+int gwasdev_synchronize(gwasdev_store *s) {
+    GW_REQUIRE(s != nullptr, "gwasdev_synchronize: NULL store");
+    GW_CUDA(cudaSetDevice(s->device));
+    GW_CUDA(cudaStreamSynchronize(s->stream));
+    return GWASDEV_OK;
+}
+
+int gwasdev_pack_row_text(const char *txt, size_t len, uint32_t n_samples, uint16_t *row) {
+    GW_REQUIRE(txt && row, "gwasdev_pack_row_text: NULL argument");
+    const uint32_t P = plane_blocks(n_samples);
+    memset(row, 0, sizeof(uint16_t) * (2 * (size_t)P + 1));
+    static const signed char allele[256] = {
+        // index of the allele letter in "ACGT", 4 = unknown (compressed_genotype_table5.cpp:94-100)
+#define X4 4, 4, 4, 4
+#define X16 X4, X4, X4, X4
+        X16, X16, X16, X16,                                        /* 0..63 */
+        4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4,            /* @ A B C D E F G ... */
+        4, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,            /* P Q R S T ... */
+        X16, X16, X16, X16, X16, X16, X16, X16, X16, X16
+#undef X16
+#undef X4
+    };
+    Labeler lab;
+    lab.reset();
+    size_t pos = 0;
+    for (uint32_t col = 0; col < n_samples && pos + 1 < len; ++col, pos += 3) {
+        const int a = allele[(unsigned char)txt[pos]], b = allele[(unsigned char)txt[pos + 1]];
+        if (a < 4 && b < 4) {
+            const int c = lab.code(4 * a + b);
+            if (c < 0) {
+                set_error("gwasdev_pack_row_text: column %u introduces a third genotype spelling of one kind; "
+                          "the reference aborts here (compressed_genotype_table5.cpp:325)", col);
+                return GWASDEV_EINVAL;
+            }
+            if (c & 1) row[1 + (col >> 4)] |= (uint16_t)(1u << (col & 15));
+            if (c & 2) row[1 + P + (col >> 4)] |= (uint16_t)(1u << (col & 15));
+        }
+    }
+    row[0] = lab.head;
+    return GWASDEV_OK;
+}
+
+static const uint64_t STAGE_BYTES = 64ull << 20;
+
+int gwasdev_put_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, const uint16_t *rows) {
+    GW_REQUIRE(s && rows, "gwasdev_put_rows: NULL argument");
+    GW_REQUIRE(first_row + n_rows <= s->M, "gwasdev_put_rows: rows [%llu, %llu) outside the table of %llu",
+               (unsigned long long)first_row, (unsigned long long)(first_row + n_rows), (unsigned long long)s->M);
+    if (n_rows == 0) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint64_t row_bytes = (2ull * s->P + 1) * sizeof(uint16_t);
+    const uint64_t chunk = std::max<uint64_t>(1, STAGE_BYTES / row_bytes);
+    uint16_t *d_stage = nullptr;
+    GW_CUDA(cudaMalloc(&d_stage, std::min(chunk, n_rows) * row_bytes));
+    for (uint64_t r = 0; r < n_rows; r += chunk) {
+        const uint64_t n = std::min(chunk, n_rows - r);
+        cudaError_t e = cudaMemcpyAsync(d_stage, (const char *)rows + r * row_bytes, n * row_bytes,
+                                        cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) {
+            unpack_rows_kernel<<<(unsigned)n, 128, 0, s->stream>>>(d_stage, s->P, s->Wr, s->d_hdr, s->d_raw, first_row + r);
+            ++g_launches;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) { cudaFree(d_stage); set_error("gwasdev_put_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    }
+    cudaFree(d_stage);
+    s->selected = false; s->mi_valid = false; s->side_valid = false; s->pw_built = false;
+    return GWASDEV_OK;
+}
+
+int gwasdev_get_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint16_t *rows) {
+    GW_REQUIRE(s && rows, "gwasdev_get_rows: NULL argument");
+    GW_REQUIRE(first_row + n_rows <= s->M, "gwasdev_get_rows: rows outside the table");
+    if (n_rows == 0) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint64_t row_bytes = (2ull * s->P + 1) * sizeof(uint16_t);
+    const uint64_t chunk = std::max<uint64_t>(1, STAGE_BYTES / row_bytes);
+    uint16_t *d_stage = nullptr;
+    GW_CUDA(cudaMalloc(&d_stage, std::min(chunk, n_rows) * row_bytes));
+    for (uint64_t r = 0; r < n_rows; r += chunk) {
+        const uint64_t n = std::min(chunk, n_rows - r);
+        pack_rows_kernel<<<(unsigned)n, 128, 0, s->stream>>>(s->d_hdr, s->d_raw, s->P, s->Wr, d_stage, first_row + r);
+        ++g_launches;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync((char *)rows + r * row_bytes, d_stage, n * row_bytes, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) { cudaFree(d_stage); set_error("gwasdev_get_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    }
+    cudaFree(d_stage);
+    return GWASDEV_OK;
+}
+
+int gwasdev_call_at(gwasdev_store *s, uint64_t row, uint32_t col, char out[3]) {
+    GW_REQUIRE(s && out, "gwasdev_call_at: NULL argument");
+    GW_REQUIRE(row < s->M && col < s->N, "gwasdev_call_at: (%llu, %u) outside the table", (unsigned long long)row, col);
+    GW_CUDA(cudaSetDevice(s->device));
+    uint16_t h = 0;
+    uint32_t w1 = 0, w2 = 0;
+    GW_CUDA(cudaStreamSynchronize(s->stream));
+    GW_CUDA(cudaMemcpy(&h, s->d_hdr + row, sizeof h, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(&w1, s->d_raw + row * 2ull * s->Wr + (col >> 5), 4, cudaMemcpyDeviceToHost));
+    GW_CUDA(cudaMemcpy(&w2, s->d_raw + row * 2ull * s->Wr + s->Wr + (col >> 5), 4, cudaMemcpyDeviceToHost));
+    const int b1 = (w1 >> (col & 31)) & 1, b2 = (w2 >> (col & 31)) & 1;
+    int enc;
+    if (b1 && b2) enc = h & 0xF;
+    else if (b1) enc = (h >> 8) & 0xF;
+    else if (b2) enc = (h >> 4) & 0xF;
+    else { out[0] = '0'; out[1] = '0'; out[2] = 0; return GWASDEV_OK; }
+    out[0] = "ACGT"[enc >> 2]; out[1] = "ACGT"[enc & 3]; out[2] = 0;
+    return GWASDEV_OK;
+}
+
+int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[51], uint32_t missing_q32) {
+    GW_REQUIRE(s && bin_counts, "gwasdev_simulate: NULL argument");
+    GW_CUDA(cudaSetDevice(s->device));
+    uint32_t cum[51];
+    uint64_t t = 0;
+    for (int b = 0; b < 51; ++b) { t += bin_counts[b]; cum[b] = (uint32_t)t; }
+    GW_REQUIRE(t > 0 && t < (1ull << 32), "gwasdev_simulate: bad MAF histogram (total %llu)", (unsigned long long)t);
+    uint32_t *d_cum = nullptr;
+    GW_CUDA(cudaMalloc(&d_cum, sizeof cum));
+    GW_CUDA(cudaMemcpyAsync(d_cum, cum, sizeof cum, cudaMemcpyHostToDevice, s->stream));
+    const unsigned threads = 64, blocks = (unsigned)((s->M + threads - 1) / threads);
+    simulate_kernel<<<blocks, threads, 0, s->stream>>>(seed, d_cum, s->N, missing_q32, s->d_hdr, s->d_raw, s->Wr, s->M);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_cum);
+    if (e != cudaSuccess) { set_error("gwasdev_simulate: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    s->selected = false; s->mi_valid = false; s->side_valid = false; s->pw_built = false;
+    return GWASDEV_OK;
+}
+
+int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, uint32_t n_case, uint8_t *pheno) {
+    GW_REQUIRE(pheno && n_case <= n_samples, "gwasdev_simulate_phenotype: bad argument");
+    uint64_t chosen = 0;
+    for (uint32_t i = 0; i < n_samples; ++i) {
+        const uint64_t left = n_samples - i, u = sim_hash(seed, SIM_STREAM_PHENO, i) >> 32;
+        if (((u * left) >> 32) < n_case - chosen) { pheno[i] = 1; ++chosen; } else pheno[i] = 0;
+    }
+    return GWASDEV_OK;
+}
+
+int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask) {
+    GW_REQUIRE(s && case_mask && ctrl_mask, "gwasdev_select_case_control: NULL argument");
+    GW_CUDA(cudaSetDevice(s->device));
+    // member lists; a sample flagged in both masks is a case (compressed_genotype_table5.cpp:541-561)
+    std::vector<uint32_t> ca, co, mca(s->Wr, 0), mco(s->Wr, 0);
+    for (uint32_t c = 0; c < s->N; ++c) {
+        const bool is_ca = (case_mask[c >> 4] >> (c & 15)) & 1, is_co = (ctrl_mask[c >> 4] >> (c & 15)) & 1;
+        if (is_ca) { ca.push_back(c); mca[c >> 5] |= 1u << (c & 31); }
+        else if (is_co) { co.push_back(c); }
+        if (is_co) mco[c >> 5] |= 1u << (c & 31);
+    }
+    GW_REQUIRE(!ca.empty() || !co.empty(), "gwasdev_select_case_control: both masks are empty");
+    free_selection(s);
+    s->n_case = (uint32_t)ca.size();
+    s->n_ctrl = (uint32_t)co.size();
+    s->Pca = plane_blocks(s->n_case);
+    s->Pco = plane_blocks(s->n_ctrl);
+    s->Kc = (s->n_case + 31) / 32;
+    s->Kt = (s->n_ctrl + 31) / 32;
+    s->Wc = round_up(std::max(s->Kc, 1u), 4);
+    s->Wt = round_up(std::max(s->Kt, 1u), 4);
+    const uint32_t stride = 2 * (s->Wc + s->Wt);
+    GW_CUDA(cudaMalloc(&s->d_case_mask, s->Wr * 4ull));
+    GW_CUDA(cudaMalloc(&s->d_ctrl_mask, s->Wr * 4ull));
+    GW_CUDA(cudaMalloc(&s->d_case_idx, std::max<size_t>(1, ca.size()) * 4));
+    GW_CUDA(cudaMalloc(&s->d_ctrl_idx, std::max<size_t>(1, co.size()) * 4));
+    GW_CUDA(cudaMalloc(&s->d_sel, s->M * (uint64_t)stride * 4));
+    GW_CUDA(cudaMemcpyAsync(s->d_case_mask, mca.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
+    GW_CUDA(cudaMemcpyAsync(s->d_ctrl_mask, mco.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
+    if (!ca.empty()) GW_CUDA(cudaMemcpyAsync(s->d_case_idx, ca.data(), ca.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    if (!co.empty()) GW_CUDA(cudaMemcpyAsync(s->d_ctrl_idx, co.data(), co.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    select_kernel<<<(unsigned)s->M, 128, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_idx, s->n_case, s->Wc, s->d_sel, stride, 0);
+    GW_LAUNCHED();
+    select_kernel<<<(unsigned)s->M, 128, 0, s->stream>>>(s->d_raw, s->Wr, s->d_ctrl_idx, s->n_ctrl, s->Wt, s->d_sel, stride, 2 * s->Wc);
+    GW_LAUNCHED();
+    GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
+    s->selected = true;
+    return GWASDEV_OK;
+}
+
+int gwasdev_case_control_counts(gwasdev_store *s, uint32_t *n_case, uint32_t *n_ctrl) {
+    GW_REQUIRE(s && s->selected, "gwasdev_case_control_counts: no case/control selection");
+    if (n_case) *n_case = s->n_case;
+    if (n_ctrl) *n_ctrl = s->n_ctrl;
+    return GWASDEV_OK;
+}
+
+int gwasdev_get_selected_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint16_t *rows) {
+    GW_REQUIRE(s && rows, "gwasdev_get_selected_rows: NULL argument");
+    GW_REQUIRE(s->selected, "gwasdev_get_selected_rows: call gwasdev_select_case_control first");
+    GW_REQUIRE(first_row + n_rows <= s->M, "gwasdev_get_selected_rows: rows outside the table");
+    if (n_rows == 0) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint64_t S = 2ull * (s->Pca + s->Pco);
+    uint16_t *d_out = nullptr;
+    GW_CUDA(cudaMalloc(&d_out, n_rows * S * 2));
+    export_selected_kernel<<<(unsigned)n_rows, 128, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, s->Pca, s->Pco, d_out, first_row);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rows, d_out, n_rows * S * 2, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { set_error("gwasdev_get_selected_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    return GWASDEV_OK;
+}
+
+}  // extern "C"
+
+// Builds the pairwise layout on first use (called from pairwise.cu).
+int gwasdev_internal_build_pairwise(gwasdev_store *s) {
+    if (s->pw_built) return GWASDEV_OK;
+    GW_REQUIRE(s->selected, "pairwise layout: call gwasdev_select_case_control first");
+    const uint32_t K = s->Kc + s->Kt;
+    GW_CUDA(cudaMalloc(&s->d_pw, 3ull * K * s->Mpad * 4));
+    dim3 block(32, 8), grid((unsigned)((s->Mpad + 31) / 32), (K + 7) / 8);
+    build_pairwise_kernel<<<grid, block, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, s->Kc, s->Kt, s->M, s->Mpad, s->d_pw);
+    GW_LAUNCHED();
+    s->pw_built = true;
+    return GWASDEV_OK;
+}

@@ -90,6 +90,8 @@ class Oracle:
         L.go_sim_hash.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.go_sim_row_codes.argtypes = [C.c_uint64, C.c_void_p, C.c_long, C.c_int, C.c_uint32, C.c_void_p]
         L.go_sim_phenotype.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p]
+        L.go_sim_minor_alleles.restype = C.c_uint64
+        L.go_sim_minor_alleles.argtypes = [C.c_uint64, C.c_void_p, C.c_long, C.c_int]
         L.go_pack_row_text.argtypes = [C.c_char_p, C.c_long, C.c_int, C.c_void_p]
 
     # -- geometry
@@ -250,6 +252,15 @@ class Oracle:
         pheno = np.zeros(n_samples, np.uint8)
         self.L.go_sim_phenotype(seed, n_samples, n_case, _p(pheno))
         return codes, pheno
+
+
+def _minor_alleles(self, seed, n_snps, n_samples, panel="affy6", first_snp=0):
+    bins = np.asarray(MAF_SPECTRUM[panel], np.uint32)
+    return np.array([self.L.go_sim_minor_alleles(seed, _p(bins), first_snp + r, n_samples) for r in range(n_snps)],
+                    np.uint64)
+
+
+Oracle.minor_alleles = _minor_alleles
 
 
 class Ref:

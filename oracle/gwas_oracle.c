@@ -567,16 +567,20 @@ uint64_t go_sim_hash(uint64_t seed, uint64_t a, uint64_t b) {
 #define GO_SIM_STREAM_MISS  0x8000000000000000ULL
 #define GO_SIM_STREAM_PHENO 0xFFFFFFFF00000003ULL
 
-void go_sim_row_codes(uint64_t seed, const uint32_t bin_counts[51], long snp, int n_samples,
-                      uint32_t missing_q32, uint8_t *codes) {
+uint64_t go_sim_minor_alleles(uint64_t seed, const uint32_t bin_counts[51], long snp, int n_samples) {
     uint64_t total = 0;
     for (int b = 0; b < 51; ++b) total += bin_counts[b];
     uint64_t r = go_sim_hash(seed, (uint64_t)snp, GO_SIM_STREAM_BIN) % total, cum = 0;
     int bin = 50;
     for (int b = 0; b < 51; ++b) { cum += bin_counts[b]; if (r < cum) { bin = b; break; } }
     uint64_t frac = go_sim_hash(seed, (uint64_t)snp, GO_SIM_STREAM_FREQ) % 1000;
+    return ((1000ULL * (uint64_t)bin + frac) * 2ULL * (uint64_t)n_samples) / 100000ULL;   /* floor(p * 2N) */
+}
+
+void go_sim_row_codes(uint64_t seed, const uint32_t bin_counts[51], long snp, int n_samples,
+                      uint32_t missing_q32, uint8_t *codes) {
     uint64_t slots = 2ULL * (uint64_t)n_samples;
-    uint64_t want = ((1000ULL * (uint64_t)bin + frac) * slots) / 100000ULL;   /* floor(p * 2N) */
+    uint64_t want = go_sim_minor_alleles(seed, bin_counts, snp, n_samples);
     uint64_t chosen = 0;
     for (int s = 0; s < n_samples; ++s) {
         int minor = 0;

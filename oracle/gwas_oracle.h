@@ -102,6 +102,8 @@ uint64_t go_sim_hash(uint64_t seed, uint64_t a, uint64_t b);
 void go_sim_row_codes(uint64_t seed, const uint32_t bin_counts[51], long snp, int n_samples,
                       uint32_t missing_q32, uint8_t *codes);
 void go_sim_phenotype(uint64_t seed, int n_samples, int n_case, uint8_t *pheno);
+/* number of minor alleles the generator places in SNP `snp` (= floor(p * 2N)) */
+uint64_t go_sim_minor_alleles(uint64_t seed, const uint32_t bin_counts[51], long snp, int n_samples);
 
 #ifdef __cplusplus
 }

