@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py -- measures the association hot path on B200(s) and prints ONE JSON line (rank 0).
+
+Headline (`value`): marginal-scan throughput in GB/s of 2-bit genotype data (algorithmic bytes =
+n_snps * n_samples / 4) on BASELINE.json configs[1] -- 5 000 cases / 5 000 controls x 500 000 SNPs,
+allelic + genotypic chi-square -- with the store resident in HBM; roofline = HBM bandwidth.
+`e2e`: the reference's `select_cc_maf` call surface (algorithms/maf_func.cpp:238-269) end to end through
+the C-ABI with HOST buffers: case/control masks from host memory -> compaction (K0) -> scan (K1) ->
+counts + statistics copied back to pinned host memory, every step.
+`pairwise`: the exhaustive SNP x SNP screen (configs[2], 2 000/2 000 x 50 000 SNPs = 1 249 975 000 pairs)
+in pairs/s with its integer-popcount roofline, its own e2e (computeBoost call surface) and CPU baseline.
+
+N > 1 (torchrun): weak scaling for the marginal scan (each rank scans its own 500 000-SNP shard, no
+collective on the data path); the pairwise screen shards tile pairs round-robin over the ranks and
+all-gathers the hit lists over NCCL inside the timed region.
+
+--impl reference: the reference's own CPU implementation (oracle/_ref, the unmodified sources) on all
+host cores, same metric, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20121127
+MARGINAL = dict(n_snps=500_000, n_samples=10_000, n_case=5_000)       # BASELINE.json configs[1]
+PAIRWISE = dict(n_snps=50_000, n_samples=4_000, n_case=2_000)         # BASELINE.json configs[2]
+CPU_MARGINAL_SAMPLE_SNPS = 2_000
+CPU_PAIRWISE_SAMPLE_SNPS = 1_500
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import libgwaspp_b200 as gw
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    peaks, peak_src = measured_peaks()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K, W = args.steps, args.warmup
+    out = {}
+
+    # ------------------------------------------------------------------ marginal scan (headline)
+    M, N, NCASE = args.snps or MARGINAL["n_snps"], args.samples or MARGINAL["n_samples"], args.cases or MARGINAL["n_case"]
+    st = gw.GenoStore(M, N, device=local)
+    st.set_stream(stream.cuda_stream)
+    st.simulate(SEED + rank)                                   # each rank owns a different 500k-SNP shard
+    pheno = gw.simulate_phenotype(SEED, N, NCASE)
+    case_mask, ctrl_mask = gw.stream_masks(pheno)
+    st.select_case_control(case_mask=case_mask, ctrl_mask=ctrl_mask)
+    d_counts = torch.empty((M, 8), dtype=torch.int32, device="cuda")
+    d_stats = torch.empty((M, 8), dtype=torch.float64, device="cuda")
+    bytes_per_step = M * N / 4.0                               # algorithmic bytes (2 bits per genotype)
+
+    for _ in range(W):
+        st.marginal_scan_into(0, M, counts=d_counts, stats=d_stats)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0, t0 = gw.launch_count(), time.perf_counter()
+    ev0.record(stream)
+    for _ in range(K):
+        st.marginal_scan_into(0, M, counts=d_counts, stats=d_stats)
+    ev1.record(stream)
+    barrier()
+    t1, launches = time.perf_counter(), gw.launch_count() - l0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_per_step = ms_total / K
+    value = world * bytes_per_step / (ms_per_step * 1e-3) / 1e9
+    clocks = sampler.window(t0, t1) if rank == 0 else None
+
+    # per-launch duration of the dominant kernel, CUDA events on the launching stream (inside the library)
+    kms = []
+    for _ in range(min(K, 10)):
+        st.marginal_scan_into(0, M, counts=d_counts, stats=d_stats)
+        kms.append(st.last_scan_ms())
+    k_ms = float(np.mean(kms))
+    achieved = bytes_per_step / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": args.traffic_bytes,
+                "kernel": "marginal_scan_kernel", "kernel_ms": round(k_ms, 4), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_step}
+
+    # e2e: select_cc_maf call surface with host buffers
+    h_counts = torch.empty((M, 8), dtype=torch.int32, pin_memory=True)
+    h_stats = torch.empty((M, 8), dtype=torch.float64, pin_memory=True)
+    e2e_steps = max(3, min(K, 10))
+    for it in range(2 + e2e_steps):
+        if it == 2:
+            barrier()
+            te0 = time.perf_counter()
+        st.select_case_control(case_mask=case_mask, ctrl_mask=ctrl_mask)
+        st.marginal_scan_into(0, M, counts=h_counts, stats=h_stats, on_device=False)
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - te0) / e2e_steps)
+    h2d = int(case_mask.nbytes + ctrl_mask.nbytes + 4 * N + 2 * 4 * ((st.P // 2 + 3) // 4 * 4))
+    d2h = int(h_counts.numel() * 4 + h_stats.numel() * 8)
+    e2e = {"value": round(world * bytes_per_step / e2e_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
+           "what": "gwasdev_select_case_control(host masks) + gwasdev_marginal_scan(host pinned outputs)"}
+    # sanity: the device and host paths agree, and the scan did real work
+    assert torch.equal(h_counts, d_counts.cpu()) and int(h_counts[:, :4].sum(1).min()) == NCASE
+    st.close()
+    del d_counts, d_stats, h_counts, h_stats
+    torch.cuda.empty_cache()
+
+    out.update({
+        "metric": "marginal-scan GB/s vs HBM peak", "value": round(value, 1), "unit": "GB/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 bit-planes (popcount) + f64 statistics", "data": "synthetic",
+        "config": {"workload": f"configs[1]: {NCASE} cases / {N - NCASE} controls x {M} SNPs per GPU, marginal allelic + "
+                               "genotypic chi-square scan (counts + statistics written)",
+                   "generator": "simulate_data.cpp restated, affy6 panel of maf_spectrum.tab, seed 20121127",
+                   "l2": f"inputs larger than L2 ({bytes_per_step / 1e6:.0f} MB streamed per step vs 126 MB L2)",
+                   "parallelism": "one process per GPU, SNP-range shards, no data-path collective"},
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    })
+
+    # ------------------------------------------------------------------ pairwise screen
+    if not args.no_pairwise:
+        out["pairwise"] = pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks,
+                                       sum_over_ranks, sampler)
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_baseline_marginal(N, NCASE, threads=1, steps=3)
+            out["cpu_baseline"] = cb
+            if "pairwise" in out:
+                out["pairwise"]["cpu_baseline"] = cpu_baseline_pairwise(args.pw_samples or PAIRWISE["n_samples"],
+                                                                        args.pw_cases or PAIRWISE["n_case"])
+        sampler.stop()
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks, sum_over_ranks, sampler):
+    M, N, NCASE = args.pw_snps or PAIRWISE["n_snps"], args.pw_samples or PAIRWISE["n_samples"], args.pw_cases or PAIRWISE["n_case"]
+    K, W = max(1, min(args.steps, args.pw_steps)), min(args.warmup, 3)
+    st = gw.GenoStore(M, N, device=local)
+    st.set_stream(stream.cuda_stream)
+    st.simulate(SEED)                                          # the store is replicated on every rank
+    pheno = gw.simulate_phenotype(SEED, N, NCASE)
+    case_mask, ctrl_mask = gw.stream_masks(pheno)
+    st.select_case_control(case_mask=case_mask, ctrl_mask=ctrl_mask)
+    cap = 1 << 20
+    d_hits = torch.empty((cap, 2), dtype=torch.int64, device="cuda")     # 16-byte gwasdev_hit records
+
+    def step():
+        n, stats = st.pairwise_scan(30.0, shard=rank, n_shards=world, capacity=cap, hits=d_hits, on_device=True)
+        if world > 1:   # top-k / hit gather over NCCL: counts, then the padded hit buffers
+            cnt = torch.tensor([n], dtype=torch.int64, device="cuda")
+            cnts = [torch.zeros_like(cnt) for _ in range(world)]
+            dist.all_gather(cnts, cnt)
+            mx = max(1, int(max(c.item() for c in cnts)))
+            bufs = [torch.empty((mx, 2), dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(bufs, d_hits[:mx].contiguous())
+            n = int(sum(c.item() for c in cnts))
+        return n, stats
+
+    for _ in range(W):
+        step()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0, t0 = gw.launch_count(), time.perf_counter()
+    ev0.record(stream)
+    screen_ms, pairs, cells, n_hits, cand = [], 0, 0, 0, 0
+    for _ in range(K):
+        n_hits, s = step()
+        screen_ms.append(s.screen_ms)
+        pairs, cells, cand = s.pairs_tested, s.word_cells, s.candidates
+    ev1.record(stream)
+    barrier()
+    t1, launches = time.perf_counter(), gw.launch_count() - l0
+    ms_per_step = max_over_ranks(ev0.elapsed_time(ev1)) / K
+    total_pairs = sum_over_ranks(float(pairs))
+    value = total_pairs / (ms_per_step * 1e-3)
+    k_ms = float(np.mean(screen_ms))
+    peak_cells, clk = gw.popc_peak(local)
+    achieved = cells / (k_ms * 1e-3)
+    res = {
+        "metric": "pairwise SNP x SNP tests/sec", "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": round(ms_per_step, 3), "scaling": "strong", "hits": int(n_hits), "candidates": int(cand),
+        "config": {"workload": f"configs[2]: exhaustive pairwise epistasis {NCASE}/{N - NCASE} samples x {M} SNPs "
+                               f"({M * (M - 1) // 2} pairs), 3x3x2 contingency + KSA statistic, threshold 30",
+                   "parallelism": f"64x64 SNP tile pairs dealt round-robin over {world} rank(s); NCCL all_gather of hits"},
+        "roofline": {"bound": "int_popc", "achieved": round(achieved / 1e12, 4), "peak": round(peak_cells / 1e12, 4),
+                     "unit": "T word-cells/s (32-bit AND+POPC)", "frac": round(achieved / peak_cells, 4), "traffic": None,
+                     "kernel": "pair_screen_kernel<false>", "kernel_ms": round(k_ms, 3),
+                     "peak_source": f"register-only __popc microbenchmark run in this process (clock attr {clk:.0f} MHz); "
+                                    "nominal 148 SMs x 16 POPC/clk x 1.965 GHz = 4.65",
+                     "algorithmic_word_cells_per_launch": int(cells)},
+        "gpu_launches": int(launches),
+        "clocks": sampler.window(t0, t1) if rank == 0 else None,
+    }
+    # e2e: computeBoost call surface: masks from host -> select -> margins -> screen -> G-test -> hits on host
+    e2e_steps = 3
+    for it in range(1 + e2e_steps):
+        if it == 1:
+            barrier()
+            te0 = time.perf_counter()
+        st.select_case_control(case_mask=case_mask, ctrl_mask=ctrl_mask)
+        hits, s = st.pairwise_scan(30.0, shard=rank, n_shards=world)
+        if len(hits):
+            st.gtest(hits["i"], hits["j"])
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - te0) / e2e_steps)
+    res["e2e"] = {"value": round(total_pairs / e2e_s, 1), "unit": "pairs/s", "ms_per_step": round(e2e_s * 1e3, 2),
+                  "h2d_bytes_per_step": int(case_mask.nbytes + ctrl_mask.nbytes + 4 * N),
+                  "d2h_bytes_per_step": int(32 * max(1, len(hits))), "steps": e2e_steps,
+                  "what": "select_case_control + pairwise_scan (margins, screen, fp64 re-score, sort) + gtest, host buffers"}
+    st.close()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baselines (the reference itself when oracle/_ref is present, else the C port)
+# ---------------------------------------------------------------------------------------------------
+def _ref_marginal_sample(seed, n_snps, N, NCASE):
+    import oracle
+    O = oracle.Oracle()
+    codes, pheno = O.simulate(seed, n_snps, N, NCASE)
+    if oracle.have_ref():
+        R = oracle.Ref(n_snps, N, 5)
+        R.add_codes(codes)
+        R.set_case_control(pheno)
+        return "reference", R, None
+    rows = O.pack_codes(codes)
+    return "port", O, (rows, pheno, N)
+
+
+def _marginal_step(kind, obj, extra):
+    """one select_cc_maf-equivalent pass: (t_select, t_scan) seconds."""
+    if kind == "reference":
+        return obj.time_phase(0, 1), obj.time_phase(2, 1)
+    rows, pheno, N = extra
+    t0 = time.perf_counter()
+    sel, nca, nco = obj.select(rows, N, pheno)
+    t1 = time.perf_counter()
+    obj.cc_counts_selected(sel, nca, nco)
+    return t1 - t0, time.perf_counter() - t1
+
+
+def cpu_baseline_marginal(N, NCASE, threads=1, steps=3):
+    kind, obj, extra = _ref_marginal_sample(SEED, CPU_MARGINAL_SAMPLE_SNPS, N, NCASE)
+    _marginal_step(kind, obj, extra)
+    ts = [_marginal_step(kind, obj, extra) for _ in range(steps)]
+    t_sel, t_scan = float(np.median([t[0] for t in ts])), float(np.median([t[1] for t in ts]))
+    b = CPU_MARGINAL_SAMPLE_SNPS * N / 4.0
+    return {"value": round(b / t_scan / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": kind,
+            "sample": f"{CPU_MARGINAL_SAMPLE_SNPS} SNPs x {N} samples of the same cohort; value = pre-selected per-SNP counts + "
+                      "MinorAlleleFrequency loop (select_cc_maf body without its per-SNP timer/stream writes), "
+                      f"{t_scan * 1e3:.1f} ms; selectCaseControl alone {t_sel * 1e3:.1f} ms",
+            "e2e_value": round(b / (t_sel + t_scan) / 1e9, 5)}
+
+
+def cpu_baseline_pairwise(N, NCASE):
+    import oracle
+    O = oracle.Oracle()
+    n = CPU_PAIRWISE_SAMPLE_SNPS
+    codes, pheno = O.simulate(SEED, n, N, NCASE)
+    pairs = n * (n - 1) // 2
+    if oracle.have_ref():
+        R = oracle.Ref(n, N, 5)
+        R.add_codes(codes)
+        R.set_case_control(pheno)
+        t = R.time_phase(3, 1)
+        kind = "reference"
+        what = "compute(computeBoost): selectCaseControl + computeMargins + pre-screen + G-test"
+    else:
+        rows = O.pack_codes(codes)
+        t0 = time.perf_counter()
+        sel, nca, nco = O.select(rows, N, pheno)
+        mar = O.margins(sel, nca, nco)
+        O.boost_screen(sel, mar, nca, nco)
+        t = time.perf_counter() - t0
+        kind, what = "port", "oracle select + margins + boost_screen"
+    return {"value": round(pairs / t, 1), "unit": "pairs/s", "cores": 1, "kind": kind,
+            "sample": f"first {n} SNPs x {N} samples ({pairs} pairs): {what}, {t:.2f} s"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation on all host cores
+# ---------------------------------------------------------------------------------------------------
+def _ref_worker(widx, N, NCASE, warmup, steps, start_evt, q):
+    kind, obj, extra = _ref_marginal_sample(SEED + 1000 + widx, CPU_MARGINAL_SAMPLE_SNPS, N, NCASE)
+    for _ in range(warmup):
+        _marginal_step(kind, obj, extra)
+    q.put(("ready", widx, kind))
+    start_evt.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _marginal_step(kind, obj, extra)
+    q.put(("done", widx, time.perf_counter() - t0))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import oracle
+    oracle.build_oracle()
+    N, NCASE = args.samples or MARGINAL["n_samples"], args.cases or MARGINAL["n_case"]
+    cores = args.ref_procs or len(os.sched_getaffinity(0))
+    ctx = mp.get_context("fork")
+    q, evt = ctx.Queue(), ctx.Event()
+    procs = [ctx.Process(target=_ref_worker, args=(w, N, NCASE, args.warmup, args.steps, evt, q)) for w in range(cores)]
+    for p in procs:
+        p.start()
+    kind = "port"
+    for _ in range(cores):
+        _, _, kind = q.get()
+    t0 = time.perf_counter()
+    evt.set()
+    times = [q.get()[2] for _ in range(cores)]
+    wall = time.perf_counter() - t0
+    for p in procs:
+        p.join()
+    b = CPU_MARGINAL_SAMPLE_SNPS * N / 4.0
+    value = cores * args.steps * b / max(times) / 1e9
+    sample = (f"each of {cores} processes: {args.steps} steps of selectCaseControl + per-SNP case/control counts + "
+              f"MinorAlleleFrequency over {CPU_MARGINAL_SAMPLE_SNPS} SNPs x {N} samples (select_cc_maf call surface)")
+    line = {
+        "impl": "reference", "metric": "marginal-scan GB/s vs HBM peak", "value": round(value, 5), "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(max(times) / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 words + LUT popcount (reference)", "data": "synthetic",
+        "config": {"workload": f"configs[1] shape: {NCASE} cases / {N - NCASE} controls, bounded sample of "
+                               f"{CPU_MARGINAL_SAMPLE_SNPS} SNPs per process"},
+        "cpu_baseline": {"value": round(value, 5), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 5), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": round(wall, 2),
+    }
+    if not args.no_pairwise:
+        line["pairwise"] = {"impl": "reference", **cpu_baseline_pairwise(args.pw_samples or PAIRWISE["n_samples"],
+                                                                         args.pw_cases or PAIRWISE["n_case"])}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--snps", type=int, default=0)
+    ap.add_argument("--samples", type=int, default=0)
+    ap.add_argument("--cases", type=int, default=0)
+    ap.add_argument("--pw-snps", type=int, default=0)
+    ap.add_argument("--pw-samples", type=int, default=0)
+    ap.add_argument("--pw-cases", type=int, default=0)
+    ap.add_argument("--pw-steps", type=int, default=5)
+    ap.add_argument("--no-pairwise", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram__bytes_read+write per launch of the scan kernel from the committed ncu capture")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

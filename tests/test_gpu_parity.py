@@ -216,6 +216,7 @@ def test_full_size_marginal_scan_properties(orc):
         minor = np.minimum(2 * first + het, 2 * second + het)
         idx = np.arange(0, M, 997)
         want = np.array([orc.minor_alleles(SEED, 1, N, first_snp=int(s))[0] for s in idx], np.int64)
+        want = np.minimum(want, 2 * N - want)                                    # bins reach 50.999 %: the drawn allele can be the major one
         assert np.array_equal(minor[idx], want)
         # spot rows against the oracle end to end (pack -> select -> count -> statistics)
         rows = st.get_rows(123_456, 4)
