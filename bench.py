@@ -183,7 +183,8 @@ def gpu_arm(args):
         st.marginal_scan_into(0, M, counts=h_counts, stats=h_stats, on_device=False)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - te0) / e2e_steps)
-    h2d = int(case_mask.nbytes + ctrl_mask.nbytes + 4 * N + 2 * 4 * ((st.P // 2 + 3) // 4 * 4))
+    wr = (st.P // 2 + 3) // 4 * 4                              # device words per raw plane
+    h2d = int(2 * 4 * wr + 2 * 4 * (7 * wr + 1) + 4 * ((NCASE + 31) // 32 + (N - NCASE + 31) // 32))   # masks + compaction tables
     d2h = int(h_counts.numel() * 4 + h_stats.numel() * 8)
     e2e = {"value": round(world * bytes_per_step / e2e_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
@@ -295,7 +296,7 @@ def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - te0) / e2e_steps)
     res["e2e"] = {"value": round(total_pairs / e2e_s, 1), "unit": "pairs/s", "ms_per_step": round(e2e_s * 1e3, 2),
-                  "h2d_bytes_per_step": int(case_mask.nbytes + ctrl_mask.nbytes + 4 * N),
+                  "h2d_bytes_per_step": int(64 * ((N // 32 + 4) // 4 * 4) + 8 * len(hits)),
                   "d2h_bytes_per_step": int(32 * max(1, len(hits))), "steps": e2e_steps,
                   "what": "select_case_control + pairwise_scan (margins, screen, fp64 re-score, sort) + gtest, host buffers"}
     st.close()

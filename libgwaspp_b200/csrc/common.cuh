@@ -46,6 +46,15 @@ __host__ __device__ inline uint32_t plane_blocks(uint32_t n) {   // pad4(n/16 + 
 }
 __host__ __device__ inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
+// Scan layout of one compacted SNP row (device-private; gwasdev_get_selected_rows converts back to the
+// reference's layout): cases then controls; inside a class the two bit-planes are interleaved in
+// 16-byte chunks, [p1 words 0-3][p2 words 0-3][p1 words 4-7][p2 words 4-7]..., so that one 32-byte
+// load brings 128 samples of both planes. Wc / Wt = words per plane per class (multiples of 4); the
+// control block starts at word 2*Wc; row stride = 2*(Wc+Wt) words.
+__host__ __device__ inline uint32_t sel_word(uint32_t class_off, uint32_t plane, uint32_t w) {
+    return class_off + (w >> 2) * 8 + plane * 4 + (w & 3);
+}
+
 // ---- first-seen genotype labelling ---------------------------------------------------------------
 // Genotype "encodings" are 4*idx(c1)+idx(c2) over the alphabet ACGT; 0, 5, 10, 15 are homozygous.
 // Codes: first homozygote seen in the row -> 1 (plane1), heterozygote -> 2 (plane2), second
@@ -125,7 +134,8 @@ struct gwasdev_store {
     uint32_t Kc = 0, Kt = 0;      // tight word counts ceil(n/32) (pairwise layout)
     uint32_t *d_case_mask = nullptr, *d_ctrl_mask = nullptr;   // [Wr]
     uint32_t *d_case_idx = nullptr, *d_ctrl_idx = nullptr;     // sample index of the k-th case / control
-    uint32_t *d_sel = nullptr;    // scan layout [M][case p1: Wc][case p2: Wc][ctrl p1: Wt][ctrl p2: Wt]
+    uint32_t *d_sel = nullptr;    // scan layout [M][cases: Wc/4 x (p1 chunk, p2 chunk)][controls: Wt/4 x (p1 chunk, p2 chunk)]
+    size_t cap_sel = 0, cap_case_idx = 0, cap_ctrl_idx = 0, cap_mask = 0;   // bytes allocated (grow-only)
 
     // pairwise layout: one-hot planes, word-major so that a 64-SNP tile row is 256 contiguous bytes
     bool pw_built = false;
@@ -140,6 +150,38 @@ struct gwasdev_store {
     uint8_t *d_tile_missing = nullptr;              // [Mpad/TILE] 1 when any SNP of the tile has missing calls
     bool side_valid = false;
 
+    size_t cap_pw = 0, cap_mi = 0, cap_side = 0, cap_tile = 0;
+    bool any_missing = false, any_clean = false;     // over tiles, valid with side_valid
+
+    // grow-only scratch, so that steady-state calls never touch cudaMalloc / cudaFree (both cost
+    // milliseconds and cudaFree synchronises the device)
+    struct Scratch { void *p = nullptr; size_t cap = 0; };
+    Scratch sc_out_counts, sc_out_stats, sc_out_mi;          // host-output staging of the marginal scan
+    Scratch sc_cnt, sc_cand, sc_keys, sc_keys2, sc_vals, sc_vals2, sc_sort, sc_hits;   // pairwise scan
+    Scratch sc_pi, sc_pj, sc_a, sc_b;                        // pair probes
+    Scratch sc_stage;                                        // row upload / download staging
+    unsigned long long *h_cnt = nullptr;                     // pinned host counters
+
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     double last_scan_ms = 0.0;
 };
+
+namespace gwasdev {
+// make sure sc holds at least `bytes`; contents are not preserved
+inline cudaError_t reserve(gwasdev_store::Scratch &sc, size_t bytes) {
+    if (bytes <= sc.cap) return cudaSuccess;
+    if (sc.p) cudaFree(sc.p);
+    sc.p = nullptr; sc.cap = 0;
+    cudaError_t e = cudaMalloc(&sc.p, bytes);
+    if (e == cudaSuccess) sc.cap = bytes;
+    return e;
+}
+template <class T> inline cudaError_t reserve_raw(T *&p, size_t &cap, size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void **)&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+}
+}  // namespace gwasdev

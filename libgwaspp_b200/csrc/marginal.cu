@@ -1,8 +1,14 @@
 // K1: per-SNP marginal scan over the compacted case/control store.
 //
-// One pass over HBM: every warp streams whole SNP rows with 128-bit loads, reduces the six popcount
-// sums with REDUX (warp-level integer reduce), parks the totals of SNP (base+l) in lane l, and after
-// 32 SNPs every lane finishes one SNP in fp64: genotype counts (compressed_genotype_table5.cpp:703-747),
+// One pass over HBM. A warp owns a contiguous range of SNP rows (ranges are balanced to one row across
+// all resident warps). G lanes (8, 16 or 32, chosen on the host so that no lane idles for the cohort's
+// row length) cooperate on one row, 32/G rows are in flight per warp, and every lane streams 32-byte
+// chunk pairs (128 samples of both bit-planes) four at a time. The three popcount streams the counts
+// need -- |p1|, |p2|, |p1&p2| -- are accumulated with carry-save adders (Harley-Seal): three LOP3 pairs
+// fold four words into ones/twos state and a single POPC of the fours carry, so the XU pipe (POPC runs
+// at 16 lanes/clk/SM and was the limiter of the first version, ncu r1a) sees ~3x fewer instructions.
+// Totals are reduced inside the lane group with REDUX and parked in lane (row % 32); after 32 rows every
+// lane finishes one SNP in fp64: genotype counts (compressed_genotype_table5.cpp:703-747),
 // marginal_information (genotype/common_genotype_func.cpp:173-219), MinorAlleleFrequency
 // (algorithms/maf_func.h:46-54) and the allelic / genotypic chi-square tests (no reference
 // counterpart). Bound: HBM bandwidth; algorithmic bytes = n_samples / 4 per SNP.
@@ -12,17 +18,60 @@
 
 namespace gwasdev {
 
-__device__ __forceinline__ uint32_t popc4(const uint4 v) {
-    return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+struct ChunkPair { uint4 x, y; };   // 4 words of plane 1, 4 words of plane 2 (same 128 samples)
+
+__device__ __forceinline__ ChunkPair ld_pair(const uint4 *p, bool pred) {   // read-once: keep out of L1
+    ChunkPair c;
+    c.x = make_uint4(0, 0, 0, 0); c.y = make_uint4(0, 0, 0, 0);
+    if (pred) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(c.x.x), "=r"(c.x.y), "=r"(c.x.z), "=r"(c.x.w) : "l"(p));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(c.y.x), "=r"(c.y.y), "=r"(c.y.z), "=r"(c.y.w) : "l"(p + 1));
+    }
+    return c;
 }
-__device__ __forceinline__ uint4 and4(const uint4 a, const uint4 b) {
-    return make_uint4(a.x & b.x, a.y & b.y, a.z & b.z, a.w & b.w);
+
+// carry-save adder: (hi, lo) = a + b + c per bit position
+__device__ __forceinline__ void csa(uint32_t &hi, uint32_t &lo, uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t u = a ^ b;
+    hi = (a & b) | (u & c);
+    lo = u ^ c;
 }
-__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {   // read-once data: do not allocate in L1
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
+// one popcount stream: bit-sliced running count (ones, twos) plus a scalar count of fours
+struct HS { uint32_t ones, twos, fours4; };
+__device__ __forceinline__ void hs_add4(HS &h, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    uint32_t ta, tb, f;
+    csa(ta, h.ones, h.ones, w0, w1);
+    csa(tb, h.ones, h.ones, w2, w3);
+    csa(f, h.twos, h.twos, ta, tb);
+    h.fours4 += __popc(f);
+}
+__device__ __forceinline__ uint32_t hs_total(const HS &h) { return 4 * h.fours4 + 2 * __popc(h.twos) + __popc(h.ones); }
+
+__device__ __forceinline__ void accumulate_pair(const ChunkPair &c, HS &h1, HS &h2, HS &hb) {
+    hs_add4(h1, c.x.x, c.x.y, c.x.z, c.x.w);
+    hs_add4(h2, c.y.x, c.y.y, c.y.z, c.y.w);
+    hs_add4(hb, c.x.x & c.y.x, c.x.y & c.y.y, c.x.z & c.y.z, c.x.w & c.y.w);
+}
+
+// one class of one row: lane l of its G-lane group takes chunk pairs l, l+G, ... of Q
+template <int G>
+__device__ __forceinline__ void scan_class(const uint4 *__restrict__ base, uint32_t Q, uint32_t l, bool row_valid,
+                                           uint32_t &s1, uint32_t &s2, uint32_t &sb) {
+    HS h1 = {0, 0, 0}, h2 = {0, 0, 0}, hb = {0, 0, 0};
+    for (uint32_t q0 = l; q0 < Q; q0 += 4 * G) {
+        ChunkPair c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t q = q0 + u * G;
+            c[u] = ld_pair(base + 2 * q, row_valid && q < Q);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (q0 + u * G < Q) accumulate_pair(c[u], h1, h2, hb);
+    }
+    s1 = hs_total(h1); s2 = hs_total(h2); sb = hs_total(hb);
 }
 
 // chi-square upper tail for df in {1, 2}: pchisq(x, df, lower=0) == gsl_cdf_chisq_Q(x, df)
@@ -107,36 +156,36 @@ __device__ __forceinline__ void fill_stats(const uint32_t ca[4], const uint32_t 
     else { o.chi2_genotypic = x; o.p_genotypic = chisq_upper(x, df); }
 }
 
-// grid: persistent, 4 CTAs of 256 threads per SM; warp w takes batches of 32 consecutive SNPs.
-__global__ void __launch_bounds__(256, 4)
-marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Wc4, uint32_t Wt4,
+// grid: persistent, 3 CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows.
+template <int G>
+__global__ void __launch_bounds__(256, 3)
+marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
                      uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
                      uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
                      gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
-    const uint32_t lane = threadIdx.x & 31;
+    constexpr uint32_t R = 32 / G;                 // rows in flight per warp
+    const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
+    const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t n_snps = snp_end - snp_begin, n_batches = (n_snps + 31) / 32;
-    for (uint64_t batch = warp; batch < n_batches; batch += n_warps) {
-        const uint64_t base = snp_begin + batch * 32;
-        const uint32_t in_batch = (uint32_t)min((uint64_t)32, snp_end - base);
-        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // this lane's SNP totals
-        for (uint32_t sidx = 0; sidx < in_batch; ++sidx) {
-            const uint4 *row = sel + (base + sidx) * (uint64_t)stride4;
-            uint32_t s1 = 0, s2 = 0, sb = 0, t1 = 0, t2 = 0, tb = 0;
-            for (uint32_t c = lane; c < Wc4; c += 32) {
-                const uint4 x = ld_stream(row + c), y = ld_stream(row + Wc4 + c);
-                s1 += popc4(x); s2 += popc4(y); sb += popc4(and4(x, y));
-            }
-            const uint4 *ctl = row + 2 * Wc4;
-            for (uint32_t c = lane; c < Wt4; c += 32) {
-                const uint4 x = ld_stream(ctl + c), y = ld_stream(ctl + Wt4 + c);
-                t1 += popc4(x); t2 += popc4(y); tb += popc4(and4(x, y));
-            }
-            s1 = __reduce_add_sync(0xffffffffu, s1); s2 = __reduce_add_sync(0xffffffffu, s2);
-            sb = __reduce_add_sync(0xffffffffu, sb); t1 = __reduce_add_sync(0xffffffffu, t1);
-            t2 = __reduce_add_sync(0xffffffffu, t2); tb = __reduce_add_sync(0xffffffffu, tb);
-            if (lane == sidx) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
+    const uint64_t n_snps = snp_end - snp_begin;
+    const uint64_t r_begin = snp_begin + warp * n_snps / n_warps, r_end = snp_begin + (warp + 1) * n_snps / n_warps;
+    for (uint64_t base = r_begin; base < r_end; base += 32) {
+        const uint32_t in_batch = (uint32_t)min((uint64_t)32, r_end - base);
+        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of row (base + lane)
+        // pass `it`: group g works on batch row g*G + it, so the totals of row L end up in L's own group
+        for (uint32_t it = 0; it < G; ++it) {
+            const uint32_t brow = g * G + it;
+            if (it >= in_batch) break;                                  // warp-uniform: no group has work left
+            const bool valid = brow < in_batch;
+            const uint4 *row = sel + (base + (valid ? brow : 0)) * (uint64_t)stride4;
+            uint32_t s1, s2, sb, t1, t2, tb;
+            scan_class<G>(row, Qc, l, valid, s1, s2, sb);
+            scan_class<G>(row + 2 * Qc, Qt, l, valid, t1, t2, tb);
+            s1 = __reduce_add_sync(group_mask, s1); s2 = __reduce_add_sync(group_mask, s2);
+            sb = __reduce_add_sync(group_mask, sb); t1 = __reduce_add_sync(group_mask, t1);
+            t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
+            if (l == it) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
         }
         if (lane < in_batch) {
             const uint64_t snp = base + lane, o = snp - out_base;
@@ -196,12 +245,25 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
                           gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats) {
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    const uint64_t batches = (snp_end - snp_begin + 31) / 32;
-    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 4, (batches + 7) / 8));
+    const uint32_t Qc = s->Wc / 4, Qt = s->Wt / 4, stride4 = 2 * (Qc + Qt);
+    // lanes per row: the width that wastes the fewest lane slots for this cohort, narrower on ties
+    int G = 8;
+    double best = 1e30;
+    for (int cand : {8, 16, 32}) {
+        const double used = (double)((Qc + cand - 1) / cand + (Qt + cand - 1) / cand) * cand;
+        const double waste = used / (double)(Qc + Qt);
+        if (waste < best - 1e-9) { best = waste; G = cand; }
+    }
+    const uint64_t n = snp_end - snp_begin;
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 3, (n + 255) / 256));
+    const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
-    marginal_scan_kernel<<<blocks, 256, 0, s->stream>>>(
-        reinterpret_cast<const uint4 *>(s->d_sel), (2 * (s->Wc + s->Wt)) / 4, s->Wc / 4, s->Wt / 4, s->n_case,
-        s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+    if (G == 8)
+        marginal_scan_kernel<8><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+    else if (G == 16)
+        marginal_scan_kernel<16><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+    else
+        marginal_scan_kernel<32><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
     GW_LAUNCHED();
     GW_CUDA(cudaEventRecord(s->ev1, s->stream));
     return GWASDEV_OK;
@@ -226,26 +288,21 @@ int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     uint32_t *d_counts = nullptr;
     gwasdev_marginal_information *d_mi = nullptr;
     gwasdev_snp_stats *d_stats = nullptr;
-    bool own_mi = false;
-    if (counts) GW_CUDA(cudaMalloc(&d_counts, n * 8 * sizeof(uint32_t)));
-    if (stats) GW_CUDA(cudaMalloc(&d_stats, n * sizeof(gwasdev_snp_stats)));
+    if (counts) { GW_CUDA(reserve(s->sc_out_counts, n * 8 * sizeof(uint32_t))); d_counts = (uint32_t *)s->sc_out_counts.p; }
+    if (stats) { GW_CUDA(reserve(s->sc_out_stats, n * sizeof(gwasdev_snp_stats))); d_stats = (gwasdev_snp_stats *)s->sc_out_stats.p; }
     if (mi) {
         if (full) {   // keep the full-table margins resident for the pairwise screen
-            if (!s->d_mi) GW_CUDA(cudaMalloc(&s->d_mi, s->M * sizeof(gwasdev_marginal_information)));
+            GW_CUDA(reserve_raw(s->d_mi, s->cap_mi, s->M * sizeof(gwasdev_marginal_information)));
             d_mi = s->d_mi;
-        } else { GW_CUDA(cudaMalloc(&d_mi, n * sizeof(gwasdev_marginal_information))); own_mi = true; }
+        } else { GW_CUDA(reserve(s->sc_out_mi, n * sizeof(gwasdev_marginal_information))); d_mi = (gwasdev_marginal_information *)s->sc_out_mi.p; }
     }
     int rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, d_mi, d_stats);
-    cudaError_t e = cudaSuccess;
-    if (rc == GWASDEV_OK) {
-        if (counts) e = cudaMemcpyAsync(counts, d_counts, n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
-        if (e == cudaSuccess && stats) e = cudaMemcpyAsync(stats, d_stats, n * sizeof(gwasdev_snp_stats), cudaMemcpyDeviceToHost, s->stream);
-        if (e == cudaSuccess && mi) e = cudaMemcpyAsync(mi, d_mi, n * sizeof(gwasdev_marginal_information), cudaMemcpyDeviceToHost, s->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    }
-    cudaFree(d_counts); cudaFree(d_stats);
-    if (own_mi) cudaFree(d_mi);
     if (rc != GWASDEV_OK) return rc;
+    cudaError_t e = cudaSuccess;
+    if (counts) e = cudaMemcpyAsync(counts, d_counts, n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && stats) e = cudaMemcpyAsync(stats, d_stats, n * sizeof(gwasdev_snp_stats), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && mi) e = cudaMemcpyAsync(mi, d_mi, n * sizeof(gwasdev_marginal_information), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) { set_error("gwasdev_marginal_scan: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     if (mi && full) { s->mi_valid = true; s->side_valid = false; }
     return GWASDEV_OK;
@@ -269,8 +326,8 @@ int gwasdev_counts(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, int m
     GW_CUDA(cudaSetDevice(s->device));
     const uint64_t n = snp_end - snp_begin;
     const int per = mode == 0 ? 4 : 8;
-    uint32_t *d_out = nullptr;
-    GW_CUDA(cudaMalloc(&d_out, n * per * sizeof(uint32_t)));
+    GW_CUDA(reserve(s->sc_out_counts, n * per * sizeof(uint32_t)));
+    uint32_t *d_out = (uint32_t *)s->sc_out_counts.p;
     int rc = GWASDEV_OK;
     cudaError_t e = cudaSuccess;
     if (mode == 2) rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_out, nullptr, nullptr);
@@ -284,7 +341,6 @@ int gwasdev_counts(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, int m
     }
     if (rc == GWASDEV_OK && e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * per * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
     if (rc == GWASDEV_OK && e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_out);
     if (rc != GWASDEV_OK) return rc;
     if (e != cudaSuccess) { set_error("gwasdev_counts: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     return GWASDEV_OK;

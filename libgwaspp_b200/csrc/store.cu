@@ -54,25 +54,70 @@ __global__ void pack_rows_kernel(const uint16_t *__restrict__ hdr, const uint32_
     }
 }
 
-// K0. One thread builds one 32-bit output word of both planes of one class by gathering the bits of
-// the class members (idx[k] = sample index of the k-th member, ascending), i.e. the dense streams of
-// selectCaseControl (compressed_genotype_table5.cpp:520-572) without its bit-serial walk.
-__global__ void select_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, const uint32_t *__restrict__ idx,
-                              uint32_t n_class, uint32_t Wout, uint32_t *__restrict__ sel,
-                              uint32_t sel_stride, uint32_t class_off) {
-    const uint64_t snp = blockIdx.x;
-    const uint32_t *p1 = raw + snp * 2ull * Wr, *p2 = p1 + Wr;
-    uint32_t *o1 = sel + snp * (uint64_t)sel_stride + class_off, *o2 = o1 + Wout;
-    for (uint32_t w = threadIdx.x; w < Wout; w += blockDim.x) {
-        uint32_t a = 0, b = 0;
-        const uint32_t k0 = w * 32;
-        for (uint32_t t = 0; t < 32 && k0 + t < n_class; ++t) {
-            const uint32_t s = idx[k0 + t];
-            a |= ((p1[s >> 5] >> (s & 31)) & 1u) << t;
-            b |= ((p2[s >> 5] >> (s & 31)) & 1u) << t;
+// K0: case/control compaction (selectCaseControl, compressed_genotype_table5.cpp:520-572) without the
+// reference's bit-serial walk. The class mask is fixed for all SNPs, so everything that depends only on
+// it is precomputed once on the host: per source word sw the member mask m[sw], the five "move" masks of
+// a parallel-suffix bit compress (Hacker's Delight 7-4) and the exclusive rank R[sw] of its first
+// member; per output word the first source word that feeds it. One thread then builds one output word
+// of both planes with ~15 logic ops per source word instead of 32 single-bit gathers.
+struct SelectTables {
+    const uint32_t *m;      // [Wr]      member mask per source word
+    const uint32_t *mv;     // [Wr][5]   compress move masks
+    const uint32_t *rank;   // [Wr + 1]  members before source word sw
+    const uint32_t *first;  // [Kout]    first source word contributing to output word o
+    uint32_t n_class, Kout;
+};
+
+__device__ __forceinline__ uint32_t compress_bits(uint32_t x, const uint32_t *mv) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint32_t t = x & mv[i];
+        x = (x ^ t) | (t >> (1 << i));
+    }
+    return x;
+}
+
+template <bool TABLES_IN_SMEM>
+__global__ void __launch_bounds__(256)
+select_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, SelectTables ca, SelectTables co,
+              uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Wt, uint64_t M) {
+    extern __shared__ uint32_t tab[];   // per class: m[Wr], mv[5*Wr], rank[Wr+1] (contiguous in global memory too)
+    const uint32_t per = 7 * Wr + 1;
+    if (TABLES_IN_SMEM) {
+        for (uint32_t q = threadIdx.x; q < 2 * per; q += blockDim.x) tab[q] = q < per ? ca.m[q] : co.m[q - per];
+        __syncthreads();
+    }
+    const uint32_t n_out = ca.Kout + co.Kout;
+    for (uint64_t snp = blockIdx.x; snp < M; snp += gridDim.x) {
+        const uint32_t *p1 = raw + snp * 2ull * Wr, *p2 = p1 + Wr;
+        uint32_t *row = sel + snp * (uint64_t)sel_stride;
+        for (uint32_t q = threadIdx.x; q < n_out; q += blockDim.x) {
+            const bool is_ca = q < ca.Kout;
+            const SelectTables &t = is_ca ? ca : co;
+            const uint32_t *tm = TABLES_IN_SMEM ? tab + (is_ca ? 0 : per) : t.m, *tmv = tm + Wr, *trk = tm + 6 * Wr;
+            const uint32_t o = is_ca ? q : q - ca.Kout;
+            const uint32_t lo = 32 * o, hi = min(lo + 32, t.n_class);
+            uint32_t a = 0, b = 0;
+            for (uint32_t sw = t.first[o]; sw < Wr && trk[sw] < hi; ++sw) {
+                const uint32_t m = tm[sw];
+                if (m == 0) continue;
+                const uint32_t x = compress_bits(p1[sw] & m, tmv + 5 * sw), y = compress_bits(p2[sw] & m, tmv + 5 * sw);
+                const int pos = (int)trk[sw] - (int)lo;        // where this word's first member lands
+                if (pos >= 0) { a |= x << pos; b |= y << pos; }
+                else { a |= x >> (-pos); b |= y >> (-pos); }
+            }
+            const uint32_t off = is_ca ? 0 : 2 * Wc;
+            row[sel_word(off, 0, o)] = a;
+            row[sel_word(off, 1, o)] = b;
         }
-        o1[w] = a;
-        o2[w] = b;
+        // zero the padding words of both classes (Kout..W)
+        for (uint32_t q = threadIdx.x; q < (Wc - ca.Kout) + (Wt - co.Kout); q += blockDim.x) {
+            const bool is_ca = q < Wc - ca.Kout;
+            const uint32_t w = is_ca ? ca.Kout + q : co.Kout + (q - (Wc - ca.Kout));
+            const uint32_t off = is_ca ? 0 : 2 * Wc;
+            row[sel_word(off, 0, w)] = 0;
+            row[sel_word(off, 1, w)] = 0;
+        }
     }
 }
 
@@ -87,8 +132,8 @@ __global__ void build_pairwise_kernel(const uint32_t *__restrict__ sel, uint32_t
     uint32_t p1 = 0, p2 = 0;
     if (snp < M) {
         const uint32_t *row = sel + snp * (uint64_t)sel_stride;
-        if (k < Kc) { p1 = row[k]; p2 = row[Wc + k]; }
-        else { p1 = row[2 * Wc + (k - Kc)]; p2 = row[2 * Wc + Wt + (k - Kc)]; }
+        if (k < Kc) { p1 = row[sel_word(0, 0, k)]; p2 = row[sel_word(0, 1, k)]; }
+        else { p1 = row[sel_word(2 * Wc, 0, k - Kc)]; p2 = row[sel_word(2 * Wc, 1, k - Kc)]; }
     }
     const uint32_t bb = p1 & p2;
     pw[(0ull * K + k) * Mpad + snp] = p1 ^ bb;
@@ -96,7 +141,8 @@ __global__ void build_pairwise_kernel(const uint32_t *__restrict__ sel, uint32_t
     pw[(2ull * K + k) * Mpad + snp] = bb;
 }
 
-// compacted rows back in the reference's 16-bit block layout (layout-parity probe)
+// compacted rows back in the reference's 16-bit block layout [case p1][case p2][ctrl p1][ctrl p2]
+// (layout-parity probe)
 __global__ void export_selected_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc,
                                        uint32_t Wt, uint32_t Pca, uint32_t Pco, uint16_t *__restrict__ out,
                                        uint64_t first_row) {
@@ -105,13 +151,12 @@ __global__ void export_selected_kernel(const uint32_t *__restrict__ sel, uint32_
     const uint32_t S = 2 * (Pca + Pco);
     uint16_t *dst = out + r * (uint64_t)S;
     for (uint32_t b = threadIdx.x; b < S; b += blockDim.x) {
-        uint32_t off, k;
-        if (b < Pca) { off = 0; k = b; }
-        else if (b < 2 * Pca) { off = Wc; k = b - Pca; }
-        else if (b < 2 * Pca + Pco) { off = 2 * Wc; k = b - 2 * Pca; }
-        else { off = 2 * Wc + Wt; k = b - 2 * Pca - Pco; }
-        const uint32_t W = (b < 2 * Pca) ? Wc : Wt;
-        const uint32_t word = (k >> 1) < W ? row[off + (k >> 1)] : 0u;
+        uint32_t off, plane, k, W;
+        if (b < Pca) { off = 0; plane = 0; k = b; W = Wc; }
+        else if (b < 2 * Pca) { off = 0; plane = 1; k = b - Pca; W = Wc; }
+        else if (b < 2 * Pca + Pco) { off = 2 * Wc; plane = 0; k = b - 2 * Pca; W = Wt; }
+        else { off = 2 * Wc; plane = 1; k = b - 2 * Pca - Pco; W = Wt; }
+        const uint32_t word = (k >> 1) < W ? row[sel_word(off, plane, k >> 1)] : 0u;
         dst[b] = (uint16_t)(word >> ((k & 1) * 16));
     }
 }
@@ -211,6 +256,7 @@ int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_stor
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_cnt, 4 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         set_error("gwasdev_create: %s", cudaGetErrorString(e));
         gwasdev_destroy(s);
@@ -220,19 +266,23 @@ int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_stor
     return GWASDEV_OK;
 }
 
-static void free_selection(gwasdev_store *s) {
-    cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
-    cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
-    s->d_case_mask = s->d_ctrl_mask = s->d_case_idx = s->d_ctrl_idx = s->d_sel = s->d_pw = nullptr;
-    s->d_mi = nullptr; s->d_side = nullptr; s->d_tile_missing = nullptr;
-    free(s->tmap); s->tmap = nullptr;
+static void free_scratch(gwasdev_store::Scratch &sc) { if (sc.p) cudaFree(sc.p); sc.p = nullptr; sc.cap = 0; }
+
+static void invalidate_selection(gwasdev_store *s) {
     s->selected = s->pw_built = s->mi_valid = s->side_valid = false;
 }
 
 void gwasdev_destroy(gwasdev_store *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    free_selection(s);
+    cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
+    cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
+    free(s->tmap);
+    for (gwasdev_store::Scratch *sc : {&s->sc_out_counts, &s->sc_out_stats, &s->sc_out_mi, &s->sc_cnt, &s->sc_cand, &s->sc_keys,
+                                      &s->sc_keys2, &s->sc_vals, &s->sc_vals2, &s->sc_sort, &s->sc_hits, &s->sc_pi, &s->sc_pj,
+                                      &s->sc_a, &s->sc_b, &s->sc_stage})
+        free_scratch(*sc);
+    if (s->h_cnt) cudaFreeHost(s->h_cnt);
     cudaFree(s->d_hdr); cudaFree(s->d_raw);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -299,8 +349,8 @@ int gwasdev_put_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, cons
     GW_CUDA(cudaSetDevice(s->device));
     const uint64_t row_bytes = (2ull * s->P + 1) * sizeof(uint16_t);
     const uint64_t chunk = std::max<uint64_t>(1, STAGE_BYTES / row_bytes);
-    uint16_t *d_stage = nullptr;
-    GW_CUDA(cudaMalloc(&d_stage, std::min(chunk, n_rows) * row_bytes));
+    GW_CUDA(reserve(s->sc_stage, std::min(chunk, n_rows) * row_bytes));
+    uint16_t *d_stage = (uint16_t *)s->sc_stage.p;
     for (uint64_t r = 0; r < n_rows; r += chunk) {
         const uint64_t n = std::min(chunk, n_rows - r);
         cudaError_t e = cudaMemcpyAsync(d_stage, (const char *)rows + r * row_bytes, n * row_bytes,
@@ -311,10 +361,9 @@ int gwasdev_put_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, cons
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-        if (e != cudaSuccess) { cudaFree(d_stage); set_error("gwasdev_put_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+        if (e != cudaSuccess) { set_error("gwasdev_put_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     }
-    cudaFree(d_stage);
-    s->selected = false; s->mi_valid = false; s->side_valid = false; s->pw_built = false;
+    invalidate_selection(s);
     return GWASDEV_OK;
 }
 
@@ -325,8 +374,8 @@ int gwasdev_get_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint
     GW_CUDA(cudaSetDevice(s->device));
     const uint64_t row_bytes = (2ull * s->P + 1) * sizeof(uint16_t);
     const uint64_t chunk = std::max<uint64_t>(1, STAGE_BYTES / row_bytes);
-    uint16_t *d_stage = nullptr;
-    GW_CUDA(cudaMalloc(&d_stage, std::min(chunk, n_rows) * row_bytes));
+    GW_CUDA(reserve(s->sc_stage, std::min(chunk, n_rows) * row_bytes));
+    uint16_t *d_stage = (uint16_t *)s->sc_stage.p;
     for (uint64_t r = 0; r < n_rows; r += chunk) {
         const uint64_t n = std::min(chunk, n_rows - r);
         pack_rows_kernel<<<(unsigned)n, 128, 0, s->stream>>>(s->d_hdr, s->d_raw, s->P, s->Wr, d_stage, first_row + r);
@@ -334,9 +383,8 @@ int gwasdev_get_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaMemcpyAsync((char *)rows + r * row_bytes, d_stage, n * row_bytes, cudaMemcpyDeviceToHost, s->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-        if (e != cudaSuccess) { cudaFree(d_stage); set_error("gwasdev_get_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+        if (e != cudaSuccess) { set_error("gwasdev_get_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     }
-    cudaFree(d_stage);
     return GWASDEV_OK;
 }
 
@@ -377,7 +425,7 @@ int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     cudaFree(d_cum);
     if (e != cudaSuccess) { set_error("gwasdev_simulate: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
-    s->selected = false; s->mi_valid = false; s->side_valid = false; s->pw_built = false;
+    invalidate_selection(s);
     return GWASDEV_OK;
 }
 
@@ -391,40 +439,88 @@ int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, uint32_t n_cas
     return GWASDEV_OK;
 }
 
+// host-side precomputation of the compress tables for one class
+static void build_select_tables(const std::vector<uint32_t> &mask, uint32_t n_class, uint32_t Kout,
+                                std::vector<uint32_t> &blob /* m | mv | rank | first */) {
+    const uint32_t Wr = (uint32_t)mask.size();
+    blob.assign(7ull * Wr + 1 + std::max(Kout, 1u), 0);
+    uint32_t *m = blob.data(), *mv = m + Wr, *rank = m + 6ull * Wr, *first = rank + Wr + 1;
+    uint32_t r = 0;
+    for (uint32_t sw = 0; sw < Wr; ++sw) {
+        uint32_t mm = mask[sw];
+        m[sw] = mm;
+        rank[sw] = r;
+        r += (uint32_t)__builtin_popcount(mm);
+        uint32_t mk = ~mm << 1;
+        for (int i = 0; i < 5; ++i) {
+            uint32_t mp = mk ^ (mk << 1);
+            mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+            const uint32_t v = mp & mm;
+            mv[5 * sw + i] = v;
+            mm = (mm ^ v) | (v >> (1 << i));
+            mk &= ~mp;
+        }
+    }
+    rank[Wr] = r;
+    (void)n_class;
+    uint32_t sw = 0;
+    for (uint32_t o = 0; o < Kout; ++o) {
+        while (sw < Wr && rank[sw + 1] <= 32 * o) ++sw;   // first source word holding member 32*o
+        first[o] = sw;
+    }
+}
+
 int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask) {
     GW_REQUIRE(s && case_mask && ctrl_mask, "gwasdev_select_case_control: NULL argument");
     GW_CUDA(cudaSetDevice(s->device));
-    // member lists; a sample flagged in both masks is a case (compressed_genotype_table5.cpp:541-561)
-    std::vector<uint32_t> ca, co, mca(s->Wr, 0), mco(s->Wr, 0);
+    // member masks as 32-bit words; a sample flagged in both masks is a case for the compaction
+    // (compressed_genotype_table5.cpp:541-561) but stays in both masks for the mask-on-the-fly overloads
+    std::vector<uint32_t> mca(s->Wr, 0), mco(s->Wr, 0), mco_sel(s->Wr, 0);
+    uint32_t nca = 0, nco = 0;
     for (uint32_t c = 0; c < s->N; ++c) {
         const bool is_ca = (case_mask[c >> 4] >> (c & 15)) & 1, is_co = (ctrl_mask[c >> 4] >> (c & 15)) & 1;
-        if (is_ca) { ca.push_back(c); mca[c >> 5] |= 1u << (c & 31); }
-        else if (is_co) { co.push_back(c); }
+        if (is_ca) { mca[c >> 5] |= 1u << (c & 31); ++nca; }
+        else if (is_co) { mco_sel[c >> 5] |= 1u << (c & 31); ++nco; }
         if (is_co) mco[c >> 5] |= 1u << (c & 31);
     }
-    GW_REQUIRE(!ca.empty() || !co.empty(), "gwasdev_select_case_control: both masks are empty");
-    free_selection(s);
-    s->n_case = (uint32_t)ca.size();
-    s->n_ctrl = (uint32_t)co.size();
-    s->Pca = plane_blocks(s->n_case);
-    s->Pco = plane_blocks(s->n_ctrl);
-    s->Kc = (s->n_case + 31) / 32;
-    s->Kt = (s->n_ctrl + 31) / 32;
+    GW_REQUIRE(nca + nco > 0, "gwasdev_select_case_control: both masks are empty");
+    invalidate_selection(s);
+    s->n_case = nca;
+    s->n_ctrl = nco;
+    s->Pca = plane_blocks(nca);
+    s->Pco = plane_blocks(nco);
+    s->Kc = (nca + 31) / 32;
+    s->Kt = (nco + 31) / 32;
     s->Wc = round_up(std::max(s->Kc, 1u), 4);
     s->Wt = round_up(std::max(s->Kt, 1u), 4);
     const uint32_t stride = 2 * (s->Wc + s->Wt);
-    GW_CUDA(cudaMalloc(&s->d_case_mask, s->Wr * 4ull));
-    GW_CUDA(cudaMalloc(&s->d_ctrl_mask, s->Wr * 4ull));
-    GW_CUDA(cudaMalloc(&s->d_case_idx, std::max<size_t>(1, ca.size()) * 4));
-    GW_CUDA(cudaMalloc(&s->d_ctrl_idx, std::max<size_t>(1, co.size()) * 4));
-    GW_CUDA(cudaMalloc(&s->d_sel, s->M * (uint64_t)stride * 4));
+    std::vector<uint32_t> bca, bco;
+    build_select_tables(mca, nca, s->Kc, bca);
+    build_select_tables(mco_sel, nco, s->Kt, bco);
+    GW_CUDA(reserve_raw(s->d_case_mask, s->cap_mask, s->Wr * 4ull));
+    { size_t cap2 = s->d_ctrl_mask ? s->cap_mask : 0; GW_CUDA(reserve_raw(s->d_ctrl_mask, cap2, s->Wr * 4ull)); }
+    GW_CUDA(reserve_raw(s->d_case_idx, s->cap_case_idx, bca.size() * 4));
+    GW_CUDA(reserve_raw(s->d_ctrl_idx, s->cap_ctrl_idx, bco.size() * 4));
+    GW_CUDA(reserve_raw(s->d_sel, s->cap_sel, s->M * (uint64_t)stride * 4));
     GW_CUDA(cudaMemcpyAsync(s->d_case_mask, mca.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->d_ctrl_mask, mco.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
-    if (!ca.empty()) GW_CUDA(cudaMemcpyAsync(s->d_case_idx, ca.data(), ca.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    if (!co.empty()) GW_CUDA(cudaMemcpyAsync(s->d_ctrl_idx, co.data(), co.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    select_kernel<<<(unsigned)s->M, 128, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_idx, s->n_case, s->Wc, s->d_sel, stride, 0);
-    GW_LAUNCHED();
-    select_kernel<<<(unsigned)s->M, 128, 0, s->stream>>>(s->d_raw, s->Wr, s->d_ctrl_idx, s->n_ctrl, s->Wt, s->d_sel, stride, 2 * s->Wc);
+    GW_CUDA(cudaMemcpyAsync(s->d_case_idx, bca.data(), bca.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    GW_CUDA(cudaMemcpyAsync(s->d_ctrl_idx, bco.data(), bco.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    SelectTables ta, to;
+    ta.m = s->d_case_idx; ta.mv = ta.m + s->Wr; ta.rank = ta.m + 6ull * s->Wr; ta.first = ta.rank + s->Wr + 1; ta.n_class = nca; ta.Kout = s->Kc;
+    to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.n_class = nco; to.Kout = s->Kt;
+    int sms = 0;
+    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const size_t smem = 2 * (7ull * s->Wr + 1) * sizeof(uint32_t);
+    if (smem <= 100 * 1024) {   // tables staged in shared memory (up to ~58 000 samples), else read through L1/L2
+        GW_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+        const unsigned grid = (unsigned)std::min<uint64_t>(s->M, (uint64_t)sms * per_sm);
+        select_kernel<true><<<grid, 256, smem, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
+    } else {
+        const unsigned grid = (unsigned)std::min<uint64_t>(s->M, (uint64_t)sms * 8);
+        select_kernel<false><<<grid, 256, 0, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
+    }
     GW_LAUNCHED();
     GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
     s->selected = true;
@@ -445,14 +541,13 @@ int gwasdev_get_selected_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_r
     if (n_rows == 0) return GWASDEV_OK;
     GW_CUDA(cudaSetDevice(s->device));
     const uint64_t S = 2ull * (s->Pca + s->Pco);
-    uint16_t *d_out = nullptr;
-    GW_CUDA(cudaMalloc(&d_out, n_rows * S * 2));
+    GW_CUDA(reserve(s->sc_stage, n_rows * S * 2));
+    uint16_t *d_out = (uint16_t *)s->sc_stage.p;
     export_selected_kernel<<<(unsigned)n_rows, 128, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, s->Pca, s->Pco, d_out, first_row);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(rows, d_out, n_rows * S * 2, cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_out);
     if (e != cudaSuccess) { set_error("gwasdev_get_selected_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     return GWASDEV_OK;
 }
@@ -464,7 +559,7 @@ int gwasdev_internal_build_pairwise(gwasdev_store *s) {
     if (s->pw_built) return GWASDEV_OK;
     GW_REQUIRE(s->selected, "pairwise layout: call gwasdev_select_case_control first");
     const uint32_t K = s->Kc + s->Kt;
-    GW_CUDA(cudaMalloc(&s->d_pw, 3ull * K * s->Mpad * 4));
+    GW_CUDA(reserve_raw(s->d_pw, s->cap_pw, 3ull * K * s->Mpad * 4));
     dim3 block(32, 8), grid((unsigned)((s->Mpad + 31) / 32), (K + 7) / 8);
     build_pairwise_kernel<<<grid, block, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, s->Kc, s->Kt, s->M, s->Mpad, s->d_pw);
     GW_LAUNCHED();
