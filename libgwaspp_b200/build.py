@@ -9,6 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgwasdev.so")
+HOST_LIB = os.path.join(HERE, "libgwaspp_host.so")
+HOST_CLI = os.path.join(HERE, "gwas_b200")
 SOURCES = ["store.cu", "marginal.cu", "pairwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
@@ -25,7 +27,12 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "gwasdev.h")]
+    if not os.path.exists(HOST_LIB) or not os.path.exists(HOST_CLI):
+        return True
+    t = min(t, os.path.getmtime(HOST_LIB), os.path.getmtime(HOST_CLI))
+    host = os.path.join(HERE, "host")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(host, f) for f in os.listdir(host)] \
+        + [os.path.join(ROOT, "include", "gwasdev.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -50,7 +57,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [nvcc(), "-shared", "-ccbin", "g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
     subprocess.check_call(link)
+    build_host()
     return LIB
+
+
+def build_host() -> str:
+    """C++ host mirror of the reference's GenoTable / test-class API (libgwaspp_host.so) and the small
+    harness executable (gwas_b200), both above the C-ABI."""
+    host = os.path.join(HERE, "host")
+    inc = ["-I", os.path.join(ROOT, "include"), "-I", host]
+    common = ["g++", "-std=c++17", "-O2", "-Wall", *inc]
+    subprocess.check_call([*common, "-fPIC", "-shared", "-o", HOST_LIB, os.path.join(host, "device_geno_table.cpp"),
+                           os.path.join(host, "test_functions.cpp"), "-L", HERE, "-lgwasdev", "-Wl,-rpath,$ORIGIN"])
+    subprocess.check_call([*common, "-o", HOST_CLI, os.path.join(host, "gwas_b200.cpp"), "-L", HERE, "-lgwaspp_host",
+                           "-lgwasdev", "-Wl,-rpath,$ORIGIN"])
+    return HOST_LIB
 
 
 if __name__ == "__main__":

@@ -55,25 +55,6 @@ __device__ __forceinline__ void accumulate_pair(const ChunkPair &c, HS &h1, HS &
     hs_add4(hb, c.x.x & c.y.x, c.x.y & c.y.y, c.x.z & c.y.z, c.x.w & c.y.w);
 }
 
-// one class of one row: lane l of its G-lane group takes chunk pairs l, l+G, ... of Q
-template <int G>
-__device__ __forceinline__ void scan_class(const uint4 *__restrict__ base, uint32_t Q, uint32_t l, bool row_valid,
-                                           uint32_t &s1, uint32_t &s2, uint32_t &sb) {
-    HS h1 = {0, 0, 0}, h2 = {0, 0, 0}, hb = {0, 0, 0};
-    for (uint32_t q0 = l; q0 < Q; q0 += 4 * G) {
-        ChunkPair c[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t q = q0 + u * G;
-            c[u] = ld_pair(base + 2 * q, row_valid && q < Q);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (q0 + u * G < Q) accumulate_pair(c[u], h1, h2, hb);
-    }
-    s1 = hs_total(h1); s2 = hs_total(h2); sb = hs_total(hb);
-}
-
 // chi-square upper tail for df in {1, 2}: pchisq(x, df, lower=0) == gsl_cdf_chisq_Q(x, df)
 __device__ __forceinline__ double chisq_upper(double x, int df) {
     if (!(x > 0.0)) return x != x ? x : 1.0;
@@ -156,39 +137,85 @@ __device__ __forceinline__ void fill_stats(const uint32_t ca[4], const uint32_t 
     else { o.chi2_genotypic = x; o.p_genotypic = chisq_upper(x, df); }
 }
 
-// grid: persistent, 3 CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows.
+// Position of a warp in its stream of load rounds. A round = up to four chunk pairs per lane of one
+// class of one row pass; the sequence (batch of 32 rows) > (pass it) > (class) > (round t0) is identical
+// for all lanes of the warp, so every branch on it is warp-uniform.
+struct Cursor {
+    uint64_t base;      // first row of the current batch of <= 32 rows
+    uint32_t in_batch;  // rows in the batch
+    uint32_t it;        // pass: group g works on batch row g*G + it
+    uint32_t cls;       // 0 cases, 1 controls
+    uint32_t t0;        // first chunk-pair slot of the round (slots advance by G chunk pairs)
+    bool valid;
+};
+
+// grid: persistent, 2 CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows
+// and keeps two rounds of loads in flight (double-buffered, software-pipelined across classes, rows and
+// batches) so that the memory system never sees a bubble between rounds.
 template <int G>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
                      uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
                      uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
                      gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
-    constexpr uint32_t R = 32 / G;                 // rows in flight per warp
     const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
     const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_snps = snp_end - snp_begin;
     const uint64_t r_begin = snp_begin + warp * n_snps / n_warps, r_end = snp_begin + (warp + 1) * n_snps / n_warps;
-    for (uint64_t base = r_begin; base < r_end; base += 32) {
-        const uint32_t in_batch = (uint32_t)min((uint64_t)32, r_end - base);
-        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of row (base + lane)
-        // pass `it`: group g works on batch row g*G + it, so the totals of row L end up in L's own group
-        for (uint32_t it = 0; it < G; ++it) {
-            const uint32_t brow = g * G + it;
-            if (it >= in_batch) break;                                  // warp-uniform: no group has work left
-            const bool valid = brow < in_batch;
-            const uint4 *row = sel + (base + (valid ? brow : 0)) * (uint64_t)stride4;
-            uint32_t s1, s2, sb, t1, t2, tb;
-            scan_class<G>(row, Qc, l, valid, s1, s2, sb);
-            scan_class<G>(row + 2 * Qc, Qt, l, valid, t1, t2, tb);
-            s1 = __reduce_add_sync(group_mask, s1); s2 = __reduce_add_sync(group_mask, s2);
-            sb = __reduce_add_sync(group_mask, sb); t1 = __reduce_add_sync(group_mask, t1);
-            t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
-            if (l == it) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
+    const uint32_t Tc = (Qc + G - 1) / G, Tt = (Qt + G - 1) / G;      // chunk-pair slots per lane and class
+
+    auto load_round = [&](ChunkPair (&buf)[4], const Cursor &c) {
+        const uint32_t brow = g * G + c.it;
+        const bool row_ok = brow < c.in_batch;
+        const uint32_t Q = c.cls ? Qt : Qc;
+        const uint4 *row = sel + (c.base + (row_ok ? brow : 0)) * (uint64_t)stride4 + (c.cls ? 2 * Qc : 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t q = l + G * (c.t0 + u);
+            buf[u] = ld_pair(row + 2 * q, row_ok && q < Q);
         }
-        if (lane < in_batch) {
-            const uint64_t snp = base + lane, o = snp - out_base;
+    };
+    auto advance = [&](Cursor c) {
+        c.t0 += 4;
+        if (c.t0 >= (c.cls ? Tt : Tc)) {
+            c.t0 = 0;
+            if (++c.cls == 2) {
+                c.cls = 0;
+                if (++c.it >= min((uint32_t)G, c.in_batch)) {
+                    c.it = 0;
+                    c.base += 32;
+                    c.valid = c.base < r_end;
+                    c.in_batch = c.valid ? (uint32_t)min((uint64_t)32, r_end - c.base) : 0;
+                }
+            }
+        }
+        return c;
+    };
+
+    HS h1 = {0, 0, 0}, h2 = {0, 0, 0}, hb = {0, 0, 0};
+    uint32_t s1 = 0, s2 = 0, sb = 0;                                  // case sums of the row in flight
+    uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of batch row `lane`
+
+    auto process_round = [&](const ChunkPair (&buf)[4], const Cursor &c) {
+        // invalid slots were loaded as zeros and add nothing
+#pragma unroll
+        for (int u = 0; u < 4; ++u) accumulate_pair(buf[u], h1, h2, hb);
+        if (c.t0 + 4 < (c.cls ? Tt : Tc)) return;
+        // ---- class finished
+        const uint32_t a = hs_total(h1), b = hs_total(h2), ab = hs_total(hb);
+        h1 = {0, 0, 0}; h2 = {0, 0, 0}; hb = {0, 0, 0};
+        if (c.cls == 0) { s1 = a; s2 = b; sb = ab; return; }
+        // ---- row finished: reduce inside the lane group, park in lane (g*G + it)
+        const uint32_t r1 = __reduce_add_sync(group_mask, s1), r2 = __reduce_add_sync(group_mask, s2);
+        const uint32_t rb = __reduce_add_sync(group_mask, sb), q1 = __reduce_add_sync(group_mask, a);
+        const uint32_t q2 = __reduce_add_sync(group_mask, b), qb = __reduce_add_sync(group_mask, ab);
+        if (l == c.it) { m1c = r1; m2c = r2; mbc = rb; m1t = q1; m2t = q2; mbt = qb; }
+        if (c.it + 1 < min((uint32_t)G, c.in_batch)) return;
+        // ---- batch finished: every lane finishes one SNP
+        if (lane < c.in_batch) {
+            const uint64_t snp = c.base + lane, o = snp - out_base;
             uint32_t ca[4], co[4];
             ca[0] = m1c - mbc; ca[1] = m2c - mbc; ca[2] = mbc; ca[3] = n_case - ca[0] - ca[1] - ca[2];
             co[0] = m1t - mbt; co[1] = m2t - mbt; co[2] = mbt; co[3] = n_ctrl - co[0] - co[1] - co[2];
@@ -208,6 +235,24 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
                 stats[o] = st;
             }
         }
+    };
+
+    Cursor c;
+    c.base = r_begin; c.valid = r_begin < r_end;
+    c.in_batch = c.valid ? (uint32_t)min((uint64_t)32, r_end - r_begin) : 0;
+    c.it = 0; c.cls = 0; c.t0 = 0;
+    if (!c.valid) return;
+    ChunkPair A[4], B[4];
+    load_round(A, c);
+    while (true) {
+        const Cursor n = advance(c);
+        if (n.valid) load_round(B, n);
+        process_round(A, c);
+        if (!n.valid) break;
+        c = advance(n);
+        if (c.valid) load_round(A, c);
+        process_round(B, n);
+        if (!c.valid) break;
     }
 }
 
@@ -255,7 +300,7 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
         if (waste < best - 1e-9) { best = waste; G = cand; }
     }
     const uint64_t n = snp_end - snp_begin;
-    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 3, (n + 255) / 256));
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 2, (n + 255) / 256));
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
     if (G == 8)

@@ -1,0 +1,101 @@
+// Minimal harness in the shape of the reference's GWAS executable (src/test/gwas_basic.cpp:126-244) for
+// the association flags only: loads a transposed-PLINK pair (TPED/TFAM), then runs one test-class
+// function through compute(). File parsing here is the small subset the harness needs: alleles
+// 1/2/3/4 -> A/C/G/T and pair collapse as in genetics/individual/tped_genotype_file.cpp:127-190,
+// phenotype column 6 with '1' = case, '0' = control as in tfam_annotation_file.cpp:68-77.
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "test_functions.h"
+
+using namespace libgwaspp::genetics;
+using namespace libgwaspp::algorithms;
+
+static void usage() {
+    std::cerr << "usage: gwas_b200 -g X.tped -p X.tfam [-o out] [--device N] "
+                 "(--test-inline-maf | --select-cc-maf | --inline-cc-maf | --dist-perform | --test-boost-epi)\n";
+}
+
+int main(int argc, char **argv) {
+    std::string geno, pheno, outfile, test;
+    int device = 0;
+    for (int a = 1; a < argc; ++a) {
+        std::string s = argv[a];
+        if ((s == "-g" || s == "--geno") && a + 1 < argc) geno = argv[++a];
+        else if ((s == "-p" || s == "--pheno") && a + 1 < argc) pheno = argv[++a];
+        else if ((s == "-o" || s == "--output") && a + 1 < argc) outfile = argv[++a];
+        else if (s == "--device" && a + 1 < argc) device = atoi(argv[++a]);
+        else if (s == "--comp-level" && a + 1 < argc) ++a;          // accepted for command-line compatibility
+        else if (s == "--tplink") {}
+        else if (s.rfind("--", 0) == 0) test = s.substr(2);
+    }
+    if (geno.empty() || pheno.empty() || test.empty()) { usage(); return 1; }
+
+    std::set<int> cases, controls;
+    int n_individs = 0;
+    {
+        std::ifstream f(pheno.c_str());
+        if (!f.is_open()) { std::cerr << "cannot open " << pheno << std::endl; return 1; }
+        std::string line;
+        while (std::getline(f, line)) {
+            if (line.empty()) continue;
+            size_t pos = 0;
+            for (int col = 0; col < 5 && pos != std::string::npos; ++col) pos = line.find_first_of("\t ", pos) == std::string::npos ? std::string::npos : line.find_first_of("\t ", pos) + 1;
+            if (pos != std::string::npos && pos < line.size()) {
+                if (line[pos] == '1') cases.insert(n_individs);
+                else if (line[pos] == '0') controls.insert(n_individs);
+            }
+            ++n_individs;
+        }
+    }
+    int n_markers = 0;
+    {
+        std::ifstream f(geno.c_str());
+        if (!f.is_open()) { std::cerr << "cannot open " << geno << std::endl; return 1; }
+        std::string line;
+        while (std::getline(f, line)) if (!line.empty()) ++n_markers;
+    }
+    std::cout << "Found " << n_individs << " individuals." << std::endl;
+    std::cout << "Found " << n_markers << " markers" << std::endl;
+    GeneticData gd(n_markers, n_individs, device);
+    {
+        std::ifstream f(geno.c_str());
+        std::string line, buf;
+        int row = 0;
+        while (std::getline(f, line)) {
+            if (line.empty()) continue;
+            size_t pos = 0;
+            for (int col = 0; col < 4; ++col) pos = line.find_first_of("\t ", pos) + 1;
+            buf.clear();
+            bool second = false;
+            for (size_t q = pos; q < line.size(); q += 2) {
+                char c = line[q];
+                c = c == '1' ? 'A' : c == '2' ? 'C' : c == '3' ? 'G' : c == '4' ? 'T' : c;
+                buf.push_back(c);
+                if (second) buf.push_back('\t');
+                second = !second;
+            }
+            gd.addGenotypeRow(row++, buf.data(), buf.data() + buf.size(), '\t');
+        }
+    }
+    gd.setCaseControlSet(cases, controls);
+    std::cout << "Setting " << cases.size() << " cases." << std::endl;
+    std::cout << "Setting " << controls.size() << " controls." << std::endl;
+
+    std::ofstream of;
+    std::ostream *out = &std::cout;
+    if (!outfile.empty()) { of.open(outfile.c_str()); if (!of.is_open()) { std::cerr << "cannot open " << outfile << std::endl; return 1; } out = &of; }
+
+    if (test == "test-inline-maf") compute(inline_maf_print, &gd, out);
+    else if (test == "select-cc-maf") compute(select_cc_maf, &gd, out);
+    else if (test == "inline-cc-maf") compute(inline_cc_maf, &gd, out);
+    else if (test == "dist-perform") compute(genotype_dist_performance, &gd, out);
+    else if (test == "test-boost-epi") compute(computeBoost, &gd, out);
+    else { usage(); return 1; }
+    std::cout << "DONE" << std::endl;
+    return 0;
+}
