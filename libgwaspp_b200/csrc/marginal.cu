@@ -63,12 +63,12 @@ __device__ __forceinline__ double chisq_upper(double x, int df) {
 
 // fp64 arithmetic below uses the _rn intrinsics so that nvcc cannot contract a*b+c into an FMA: the
 // reference is compiled for x86-64 without FMA and rounds every product and sum separately.
-__device__ __forceinline__ void fill_marginal_information(const uint32_t ca[4], const uint32_t co[4],
+__device__ __noinline__ void fill_marginal_information(const uint32_t ca[4], const uint32_t co[4],
                                                           uint32_t n_individs, gwasdev_marginal_information &m) {
     const uint32_t n_ca = ca[3] + ca[0] + ca[1] + ca[2], n_co = co[3] + co[0] + co[1] + co[2];
     double h = 0.0, hy = 0.0;
     const double n = (double)n_individs;
-#pragma unroll
+#pragma unroll 1
     for (int g = 0; g < 4; ++g) {
         const uint32_t mar = ca[g] + co[g];
         m.margins[g] = mar; m.cases[g] = ca[g]; m.controls[g] = co[g];
@@ -103,7 +103,7 @@ __device__ __forceinline__ double maf_reference(const uint32_t ft[4]) {   // alg
     return maf;
 }
 
-__device__ __forceinline__ void fill_stats(const uint32_t ca[4], const uint32_t co[4], gwasdev_snp_stats &o) {
+__device__ __noinline__ void fill_stats(const uint32_t ca[4], const uint32_t co[4], gwasdev_snp_stats &o) {
     o.maf_ref_case = maf_reference(ca);
     o.maf_ref_ctrl = maf_reference(co);
     const double a_ca = 2.0 * ca[0] + ca[1], b_ca = 2.0 * ca[2] + ca[1];
@@ -122,7 +122,7 @@ __device__ __forceinline__ void fill_stats(const uint32_t ca[4], const uint32_t 
     int cols = 0;
     double x = 0.0;
     if (g1 > 0 && g2 > 0) {
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < 3; ++g) {
             const double c = (double)ca[g] + co[g];
             if (c == 0) continue;
@@ -137,6 +137,22 @@ __device__ __forceinline__ void fill_stats(const uint32_t ca[4], const uint32_t 
     else { o.chi2_genotypic = x; o.p_genotypic = chisq_upper(x, df); }
 }
 
+// One SNP's epilogue, kept out of line so that the streaming loop stays small in the instruction cache.
+__device__ __noinline__ void finish_snp(uint32_t m1c, uint32_t m2c, uint32_t mbc, uint32_t m1t, uint32_t m2t, uint32_t mbt,
+                                        uint32_t n_case, uint32_t n_ctrl, uint64_t o, uint32_t *__restrict__ counts,
+                                        gwasdev_marginal_information *__restrict__ mi, gwasdev_snp_stats *__restrict__ stats) {
+    uint32_t ca[4], co[4];
+    ca[0] = m1c - mbc; ca[1] = m2c - mbc; ca[2] = mbc; ca[3] = n_case - ca[0] - ca[1] - ca[2];
+    co[0] = m1t - mbt; co[1] = m2t - mbt; co[2] = mbt; co[3] = n_ctrl - co[0] - co[1] - co[2];
+    if (counts) {
+        uint4 *dst = reinterpret_cast<uint4 *>(counts + 8 * o);
+        dst[0] = make_uint4(ca[0], ca[1], ca[2], ca[3]);
+        dst[1] = make_uint4(co[0], co[1], co[2], co[3]);
+    }
+    if (mi) fill_marginal_information(ca, co, n_case + n_ctrl, mi[o]);
+    if (stats) fill_stats(ca, co, stats[o]);
+}
+
 // Position of a warp in its stream of load rounds. A round = up to four chunk pairs per lane of one
 // class of one row pass; the sequence (batch of 32 rows) > (pass it) > (class) > (round t0) is identical
 // for all lanes of the warp, so every branch on it is warp-uniform.
@@ -149,34 +165,60 @@ struct Cursor {
     bool valid;
 };
 
-// grid: persistent, 2 CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows
-// and keeps two rounds of loads in flight (double-buffered, software-pipelined across classes, rows and
-// batches) so that the memory system never sees a bubble between rounds.
+// ---- PTX helpers: mbarrier + 1-D bulk copy (TMA without a tensor map) -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int SCAN_WARPS = 8;          // warps per CTA
+constexpr int SCAN_STAGES = 3;         // rounds in flight per warp
+constexpr int SCAN_STAGE_BYTES = 4096; // one round: 32 lanes x 4 chunk pairs x 32 bytes
+
+// grid: persistent, 2 CTAs of 256 threads per SM. Each warp owns one contiguous, balanced range of rows
+// and a private 3-stage shared-memory ring that its group leaders fill with cp.async.bulk (one contiguous
+// copy of <= 4*G chunk pairs per lane group and round, completion on the stage's mbarrier), so bytes in
+// flight cost no registers and the stream never has a bubble between rounds, classes, rows or batches.
 template <int G>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(32 * SCAN_WARPS, 2)
 marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
                      uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
                      uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
                      gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
-    const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5, g = lane / G, l = lane % G;
+    unsigned char *ring = smem + wic * (SCAN_STAGES * SCAN_STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SCAN_WARPS * SCAN_STAGES * SCAN_STAGE_BYTES) + wic * SCAN_STAGES;
+    if (lane == 0) {
+        for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
     const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_snps = snp_end - snp_begin;
     const uint64_t r_begin = snp_begin + warp * n_snps / n_warps, r_end = snp_begin + (warp + 1) * n_snps / n_warps;
+    if (r_begin >= r_end) return;
     const uint32_t Tc = (Qc + G - 1) / G, Tt = (Qt + G - 1) / G;      // chunk-pair slots per lane and class
 
-    auto load_round = [&](ChunkPair (&buf)[4], const Cursor &c) {
-        const uint32_t brow = g * G + c.it;
-        const bool row_ok = brow < c.in_batch;
-        const uint32_t Q = c.cls ? Qt : Qc;
-        const uint4 *row = sel + (c.base + (row_ok ? brow : 0)) * (uint64_t)stride4 + (c.cls ? 2 * Qc : 0);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t q = l + G * (c.t0 + u);
-            buf[u] = ld_pair(row + 2 * q, row_ok && q < Q);
-        }
-    };
     auto advance = [&](Cursor c) {
         c.t0 += 4;
         if (c.t0 >= (c.cls ? Tt : Tc)) {
@@ -193,66 +235,77 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
         }
         return c;
     };
+    // chunk pairs group `grp` copies in round c (0 when its row does not exist)
+    auto group_pairs = [&](const Cursor &c, uint32_t grp) -> uint32_t {
+        if (grp * G + c.it >= c.in_batch) return 0u;
+        const uint32_t Q = c.cls ? Qt : Qc, q0 = G * c.t0;
+        return min(4u * G, Q - q0);
+    };
+    auto issue = [&](const Cursor &c, int stage) {
+        if (lane == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (uint32_t grp = 0; grp < 32 / G; ++grp) total += group_pairs(c, grp);
+            mbar_expect_tx(&full[stage], total * 32u);
+        }
+        const uint32_t mine = group_pairs(c, g);
+        if (l == 0 && mine > 0) {
+            const uint4 *src = sel + (c.base + g * G + c.it) * (uint64_t)stride4 + (c.cls ? 2 * Qc : 0) + 2 * (G * c.t0);
+            bulk_g2s(ring + stage * SCAN_STAGE_BYTES + g * (4 * G * 32), src, mine * 32u, &full[stage]);
+        }
+    };
 
     HS h1 = {0, 0, 0}, h2 = {0, 0, 0}, hb = {0, 0, 0};
     uint32_t s1 = 0, s2 = 0, sb = 0;                                  // case sums of the row in flight
     uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of batch row `lane`
 
-    auto process_round = [&](const ChunkPair (&buf)[4], const Cursor &c) {
-        // invalid slots were loaded as zeros and add nothing
+    Cursor cons;
+    cons.base = r_begin; cons.valid = true;
+    cons.in_batch = (uint32_t)min((uint64_t)32, r_end - r_begin);
+    cons.it = 0; cons.cls = 0; cons.t0 = 0;
+    Cursor prod = cons;
+    for (int s = 0; s < SCAN_STAGES && prod.valid; ++s) { issue(prod, s); prod = advance(prod); }
+
+    int stage = 0;
+    uint32_t parity = 0;
+    while (cons.valid) {
+        mbar_wait(&full[stage], parity);
+        {
+            const uint32_t mine = group_pairs(cons, g);
+            const uint4 *sp = reinterpret_cast<const uint4 *>(ring + stage * SCAN_STAGE_BYTES + g * (4 * G * 32));
 #pragma unroll
-        for (int u = 0; u < 4; ++u) accumulate_pair(buf[u], h1, h2, hb);
-        if (c.t0 + 4 < (c.cls ? Tt : Tc)) return;
-        // ---- class finished
-        const uint32_t a = hs_total(h1), b = hs_total(h2), ab = hs_total(hb);
-        h1 = {0, 0, 0}; h2 = {0, 0, 0}; hb = {0, 0, 0};
-        if (c.cls == 0) { s1 = a; s2 = b; sb = ab; return; }
-        // ---- row finished: reduce inside the lane group, park in lane (g*G + it)
-        const uint32_t r1 = __reduce_add_sync(group_mask, s1), r2 = __reduce_add_sync(group_mask, s2);
-        const uint32_t rb = __reduce_add_sync(group_mask, sb), q1 = __reduce_add_sync(group_mask, a);
-        const uint32_t q2 = __reduce_add_sync(group_mask, b), qb = __reduce_add_sync(group_mask, ab);
-        if (l == c.it) { m1c = r1; m2c = r2; mbc = rb; m1t = q1; m2t = q2; mbt = qb; }
-        if (c.it + 1 < min((uint32_t)G, c.in_batch)) return;
-        // ---- batch finished: every lane finishes one SNP
-        if (lane < c.in_batch) {
-            const uint64_t snp = c.base + lane, o = snp - out_base;
-            uint32_t ca[4], co[4];
-            ca[0] = m1c - mbc; ca[1] = m2c - mbc; ca[2] = mbc; ca[3] = n_case - ca[0] - ca[1] - ca[2];
-            co[0] = m1t - mbt; co[1] = m2t - mbt; co[2] = mbt; co[3] = n_ctrl - co[0] - co[1] - co[2];
-            if (counts) {
-                uint4 *dst = reinterpret_cast<uint4 *>(counts + 8 * o);
-                dst[0] = make_uint4(ca[0], ca[1], ca[2], ca[3]);
-                dst[1] = make_uint4(co[0], co[1], co[2], co[3]);
-            }
-            if (mi) {
-                gwasdev_marginal_information m;
-                fill_marginal_information(ca, co, n_case + n_ctrl, m);
-                mi[o] = m;
-            }
-            if (stats) {
-                gwasdev_snp_stats st;
-                fill_stats(ca, co, st);
-                stats[o] = st;
+            for (uint32_t u = 0; u < 4; ++u) {
+                const uint32_t slot = u * G + l;
+                if (slot < mine) {
+                    ChunkPair cp;
+                    cp.x = sp[2 * slot];
+                    cp.y = sp[2 * slot + 1];
+                    accumulate_pair(cp, h1, h2, hb);
+                }
             }
         }
-    };
+        __syncwarp();                                   // every lane has consumed the stage: refill it
+        if (prod.valid) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order our generic reads before the async refill
+            issue(prod, stage);
+            prod = advance(prod);
+        }
 
-    Cursor c;
-    c.base = r_begin; c.valid = r_begin < r_end;
-    c.in_batch = c.valid ? (uint32_t)min((uint64_t)32, r_end - r_begin) : 0;
-    c.it = 0; c.cls = 0; c.t0 = 0;
-    if (!c.valid) return;
-    ChunkPair A[4], B[4];
-    load_round(A, c);
-    while (true) {
-        const Cursor n = advance(c);
-        if (n.valid) load_round(B, n);
-        process_round(A, c);
-        if (!n.valid) break;
-        c = advance(n);
-        if (c.valid) load_round(A, c);
-        process_round(B, n);
-        if (!c.valid) break;
+        if (cons.t0 + 4 >= (cons.cls ? Tt : Tc)) {      // class finished
+            const uint32_t a = hs_total(h1), b = hs_total(h2), ab = hs_total(hb);
+            h1 = {0, 0, 0}; h2 = {0, 0, 0}; hb = {0, 0, 0};
+            if (cons.cls == 0) { s1 = a; s2 = b; sb = ab; }
+            else {                                      // row finished: reduce in the lane group, park in lane g*G + it
+                const uint32_t r1 = __reduce_add_sync(group_mask, s1), r2 = __reduce_add_sync(group_mask, s2);
+                const uint32_t rb = __reduce_add_sync(group_mask, sb), q1 = __reduce_add_sync(group_mask, a);
+                const uint32_t q2 = __reduce_add_sync(group_mask, b), qb = __reduce_add_sync(group_mask, ab);
+                if (l == cons.it) { m1c = r1; m2c = r2; mbc = rb; m1t = q1; m2t = q2; mbt = qb; }
+                if (cons.it + 1 >= min((uint32_t)G, cons.in_batch) && lane < cons.in_batch)   // batch finished
+                    finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, cons.base + lane - out_base, counts, mi, stats);
+            }
+        }
+        cons = advance(cons);
+        if (++stage == SCAN_STAGES) { stage = 0; parity ^= 1; }
     }
 }
 
@@ -302,13 +355,21 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     const uint64_t n = snp_end - snp_begin;
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 2, (n + 255) / 256));
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
+    const size_t smem = (size_t)SCAN_WARPS * SCAN_STAGES * SCAN_STAGE_BYTES + SCAN_WARPS * SCAN_STAGES * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
     if (G == 8)
-        marginal_scan_kernel<8><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+        marginal_scan_kernel<8><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
     else if (G == 16)
-        marginal_scan_kernel<16><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+        marginal_scan_kernel<16><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
     else
-        marginal_scan_kernel<32><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+        marginal_scan_kernel<32><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
     GW_LAUNCHED();
     GW_CUDA(cudaEventRecord(s->ev1, s->stream));
     return GWASDEV_OK;
