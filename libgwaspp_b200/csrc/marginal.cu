@@ -188,25 +188,26 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 constexpr int SCAN_WARPS = 8;          // warps per CTA
-constexpr int SCAN_STAGES = 3;         // rounds in flight per warp
-constexpr int SCAN_STAGE_BYTES = 4096; // one round: 32 lanes x 4 chunk pairs x 32 bytes
+constexpr int SCAN_MAX_SLOTS = 6;      // chunk pairs per lane and round (a round never crosses a class)
 
-// grid: persistent, 2 CTAs of 256 threads per SM. Each warp owns one contiguous, balanced range of rows
-// and a private 3-stage shared-memory ring that its group leaders fill with cp.async.bulk (one contiguous
-// copy of <= 4*G chunk pairs per lane group and round, completion on the stage's mbarrier), so bytes in
-// flight cost no registers and the stream never has a bubble between rounds, classes, rows or batches.
+// grid: persistent, one CTA of 8 warps per SM. Each warp owns one contiguous, balanced range of rows and a
+// private shared-memory ring of `n_stages` rounds that its lane 0 fills with cp.async.bulk (one contiguous
+// copy of <= S*G chunk pairs per lane group and round, completion counted on the stage's mbarrier). Bytes
+// in flight cost no registers, a round is as long as a class of the row when that fits (S <= 6 chunk pairs
+// per lane), and the stream never has a bubble between rounds, classes, rows or batches.
 template <int G>
-__global__ void __launch_bounds__(32 * SCAN_WARPS, 2)
+__global__ void __launch_bounds__(32 * SCAN_WARPS, 1)
 marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
                      uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
                      uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
-                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
+                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base, uint32_t S, uint32_t n_stages) {
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5, g = lane / G, l = lane % G;
-    unsigned char *ring = smem + wic * (SCAN_STAGES * SCAN_STAGE_BYTES);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SCAN_WARPS * SCAN_STAGES * SCAN_STAGE_BYTES) + wic * SCAN_STAGES;
+    const uint32_t stage_bytes = 32u * S * 32u, group_bytes = G * S * 32u;
+    unsigned char *ring = smem + wic * (n_stages * stage_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SCAN_WARPS * n_stages * stage_bytes) + wic * n_stages;
     if (lane == 0) {
-        for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(&full[s], 1);
+        for (uint32_t s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -220,7 +221,7 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
     const uint32_t Tc = (Qc + G - 1) / G, Tt = (Qt + G - 1) / G;      // chunk-pair slots per lane and class
 
     auto advance = [&](Cursor c) {
-        c.t0 += 4;
+        c.t0 += S;
         if (c.t0 >= (c.cls ? Tt : Tc)) {
             c.t0 = 0;
             if (++c.cls == 2) {
@@ -235,23 +236,22 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
         }
         return c;
     };
-    // chunk pairs group `grp` copies in round c (0 when its row does not exist)
+    // chunk pairs lane group `grp` receives in round c (0 when its row does not exist)
     auto group_pairs = [&](const Cursor &c, uint32_t grp) -> uint32_t {
         if (grp * G + c.it >= c.in_batch) return 0u;
-        const uint32_t Q = c.cls ? Qt : Qc, q0 = G * c.t0;
-        return min(4u * G, Q - q0);
+        return min(S * G, (c.cls ? Qt : Qc) - G * c.t0);
     };
-    auto issue = [&](const Cursor &c, int stage) {
-        if (lane == 0) {
-            uint32_t total = 0;
+    auto issue = [&](const Cursor &c, uint32_t stage) {      // lane 0 only
+        uint32_t total = 0;
 #pragma unroll
-            for (uint32_t grp = 0; grp < 32 / G; ++grp) total += group_pairs(c, grp);
-            mbar_expect_tx(&full[stage], total * 32u);
-        }
-        const uint32_t mine = group_pairs(c, g);
-        if (l == 0 && mine > 0) {
-            const uint4 *src = sel + (c.base + g * G + c.it) * (uint64_t)stride4 + (c.cls ? 2 * Qc : 0) + 2 * (G * c.t0);
-            bulk_g2s(ring + stage * SCAN_STAGE_BYTES + g * (4 * G * 32), src, mine * 32u, &full[stage]);
+        for (uint32_t grp = 0; grp < 32 / G; ++grp) total += group_pairs(c, grp);
+        mbar_expect_tx(&full[stage], total * 32u);
+        const uint4 *src0 = sel + (c.base + c.it) * (uint64_t)stride4 + (c.cls ? 2 * Qc : 0) + 2 * (G * c.t0);
+#pragma unroll
+        for (uint32_t grp = 0; grp < 32 / G; ++grp) {
+            const uint32_t pairs = group_pairs(c, grp);
+            if (pairs > 0)
+                bulk_g2s(ring + stage * stage_bytes + grp * group_bytes, src0 + (uint64_t)(grp * G) * stride4, pairs * 32u, &full[stage]);
         }
     };
 
@@ -264,34 +264,33 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
     cons.in_batch = (uint32_t)min((uint64_t)32, r_end - r_begin);
     cons.it = 0; cons.cls = 0; cons.t0 = 0;
     Cursor prod = cons;
-    for (int s = 0; s < SCAN_STAGES && prod.valid; ++s) { issue(prod, s); prod = advance(prod); }
+    for (uint32_t s = 0; s < n_stages && prod.valid; ++s) {
+        if (lane == 0) issue(prod, s);
+        prod = advance(prod);
+    }
 
-    int stage = 0;
-    uint32_t parity = 0;
+    uint32_t stage = 0, parity = 0;
     while (cons.valid) {
         mbar_wait(&full[stage], parity);
         {
             const uint32_t mine = group_pairs(cons, g);
-            const uint4 *sp = reinterpret_cast<const uint4 *>(ring + stage * SCAN_STAGE_BYTES + g * (4 * G * 32));
+            const uint4 *sp = reinterpret_cast<const uint4 *>(ring + stage * stage_bytes + g * group_bytes) + 2 * l;
 #pragma unroll
-            for (uint32_t u = 0; u < 4; ++u) {
-                const uint32_t slot = u * G + l;
-                if (slot < mine) {
+            for (uint32_t u = 0; u < SCAN_MAX_SLOTS; ++u) {
+                if (u * G + l < mine) {                 // u < S is implied: mine <= S*G
                     ChunkPair cp;
-                    cp.x = sp[2 * slot];
-                    cp.y = sp[2 * slot + 1];
+                    cp.x = sp[2 * u * G];
+                    cp.y = sp[2 * u * G + 1];
                     accumulate_pair(cp, h1, h2, hb);
                 }
             }
         }
         __syncwarp();                                   // every lane has consumed the stage: refill it
         if (prod.valid) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order our generic reads before the async refill
-            issue(prod, stage);
+            if (lane == 0) issue(prod, stage);
             prod = advance(prod);
         }
-
-        if (cons.t0 + 4 >= (cons.cls ? Tt : Tc)) {      // class finished
+        if (cons.t0 + S >= (cons.cls ? Tt : Tc)) {      // class finished
             const uint32_t a = hs_total(h1), b = hs_total(h2), ab = hs_total(hb);
             h1 = {0, 0, 0}; h2 = {0, 0, 0}; hb = {0, 0, 0};
             if (cons.cls == 0) { s1 = a; s2 = b; sb = ab; }
@@ -305,7 +304,7 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
             }
         }
         cons = advance(cons);
-        if (++stage == SCAN_STAGES) { stage = 0; parity ^= 1; }
+        if (++stage == n_stages) { stage = 0; parity ^= 1; }
     }
 }
 
@@ -353,23 +352,29 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
         if (waste < best - 1e-9) { best = waste; G = cand; }
     }
     const uint64_t n = snp_end - snp_begin;
-    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 2, (n + 255) / 256));
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms, (n + 255) / 256));
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
-    const size_t smem = (size_t)SCAN_WARPS * SCAN_STAGES * SCAN_STAGE_BYTES + SCAN_WARPS * SCAN_STAGES * sizeof(uint64_t);
+    // round length: a whole class per round when it fits in SCAN_MAX_SLOTS chunk pairs per lane
+    const uint32_t Tmax = std::max((Qc + G - 1) / G, (Qt + G - 1) / G);
+    const uint32_t S = std::min<uint32_t>(Tmax, SCAN_MAX_SLOTS);
+    const size_t stage_bytes = 32ull * S * 32ull;
+    uint32_t n_stages = (uint32_t)std::min<size_t>(6, (200 * 1024) / (SCAN_WARPS * stage_bytes));
+    if (n_stages < 2) n_stages = 2;
+    const size_t smem = SCAN_WARPS * n_stages * stage_bytes + SCAN_WARPS * n_stages * sizeof(uint64_t);
     static bool attr_set = false;
     if (!attr_set) {
-        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_set = true;
     }
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
     if (G == 8)
-        marginal_scan_kernel<8><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+        marginal_scan_kernel<8><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin, S, n_stages);
     else if (G == 16)
-        marginal_scan_kernel<16><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+        marginal_scan_kernel<16><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin, S, n_stages);
     else
-        marginal_scan_kernel<32><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+        marginal_scan_kernel<32><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin, S, n_stages);
     GW_LAUNCHED();
     GW_CUDA(cudaEventRecord(s->ev1, s->stream));
     return GWASDEV_OK;
