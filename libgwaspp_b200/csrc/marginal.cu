@@ -153,158 +153,58 @@ __device__ __noinline__ void finish_snp(uint32_t m1c, uint32_t m2c, uint32_t mbc
     if (stats) fill_stats(ca, co, stats[o]);
 }
 
-// Position of a warp in its stream of load rounds. A round = up to four chunk pairs per lane of one
-// class of one row pass; the sequence (batch of 32 rows) > (pass it) > (class) > (round t0) is identical
-// for all lanes of the warp, so every branch on it is warp-uniform.
-struct Cursor {
-    uint64_t base;      // first row of the current batch of <= 32 rows
-    uint32_t in_batch;  // rows in the batch
-    uint32_t it;        // pass: group g works on batch row g*G + it
-    uint32_t cls;       // 0 cases, 1 controls
-    uint32_t t0;        // first chunk-pair slot of the round (slots advance by G chunk pairs)
-    bool valid;
-};
+constexpr int SCAN_SLOTS = 6;   // chunk pairs a lane loads back to back (12 x 128-bit loads in flight)
 
-// ---- PTX helpers: mbarrier + 1-D bulk copy (TMA without a tensor map) -------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-constexpr int SCAN_WARPS = 8;          // warps per CTA
-constexpr int SCAN_MAX_SLOTS = 6;      // chunk pairs per lane and round (a round never crosses a class)
-
-// grid: persistent, one CTA of 8 warps per SM. Each warp owns one contiguous, balanced range of rows and a
-// private shared-memory ring of `n_stages` rounds that its lane 0 fills with cp.async.bulk (one contiguous
-// copy of <= S*G chunk pairs per lane group and round, completion counted on the stage's mbarrier). Bytes
-// in flight cost no registers, a round is as long as a class of the row when that fits (S <= 6 chunk pairs
-// per lane), and the stream never has a bubble between rounds, classes, rows or batches.
+// one class of one row: lane l of its G-lane group takes chunk pairs l, l+G, ... of Q, SCAN_SLOTS at a
+// time with all loads of a round issued before the first is consumed
 template <int G>
-__global__ void __launch_bounds__(32 * SCAN_WARPS, 1)
+__device__ __forceinline__ void scan_class(const uint4 *__restrict__ base, uint32_t Q, uint32_t l, bool row_valid,
+                                           uint32_t &s1, uint32_t &s2, uint32_t &sb) {
+    HS h1 = {0, 0, 0}, h2 = {0, 0, 0}, hb = {0, 0, 0};
+    const uint4 *p = base + 2 * l;
+    for (uint32_t q0 = l; q0 < Q; q0 += SCAN_SLOTS * G, p += 2 * SCAN_SLOTS * G) {
+        ChunkPair c[SCAN_SLOTS];
+#pragma unroll
+        for (int u = 0; u < SCAN_SLOTS; ++u) c[u] = ld_pair(p + 2 * u * G, row_valid && q0 + u * G < Q);
+#pragma unroll
+        for (int u = 0; u < SCAN_SLOTS; ++u)
+            if (q0 + u * G < Q) accumulate_pair(c[u], h1, h2, hb);     // uniform over the lane group except at the row tail
+    }
+    s1 = hs_total(h1); s2 = hs_total(h2); sb = hs_total(hb);
+}
+
+// grid: persistent, 3 CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows.
+template <int G>
+__global__ void __launch_bounds__(256, 3)
 marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
                      uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
                      uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
-                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base, uint32_t S, uint32_t n_stages) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5, g = lane / G, l = lane % G;
-    const uint32_t stage_bytes = 32u * S * 32u, group_bytes = G * S * 32u;
-    unsigned char *ring = smem + wic * (n_stages * stage_bytes);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + SCAN_WARPS * n_stages * stage_bytes) + wic * n_stages;
-    if (lane == 0) {
-        for (uint32_t s = 0; s < n_stages; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
+                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
+    const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
     const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_snps = snp_end - snp_begin;
     const uint64_t r_begin = snp_begin + warp * n_snps / n_warps, r_end = snp_begin + (warp + 1) * n_snps / n_warps;
-    if (r_begin >= r_end) return;
-    const uint32_t Tc = (Qc + G - 1) / G, Tt = (Qt + G - 1) / G;      // chunk-pair slots per lane and class
-
-    auto advance = [&](Cursor c) {
-        c.t0 += S;
-        if (c.t0 >= (c.cls ? Tt : Tc)) {
-            c.t0 = 0;
-            if (++c.cls == 2) {
-                c.cls = 0;
-                if (++c.it >= min((uint32_t)G, c.in_batch)) {
-                    c.it = 0;
-                    c.base += 32;
-                    c.valid = c.base < r_end;
-                    c.in_batch = c.valid ? (uint32_t)min((uint64_t)32, r_end - c.base) : 0;
-                }
-            }
+    for (uint64_t base = r_begin; base < r_end; base += 32) {
+        const uint32_t in_batch = (uint32_t)min((uint64_t)32, r_end - base);
+        const uint32_t passes = min((uint32_t)G, in_batch);
+        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of row (base + lane)
+        // pass `it`: group g works on batch row g*G + it, so the totals of row L end up in L's own group
+        for (uint32_t it = 0; it < passes; ++it) {
+            const uint32_t brow = g * G + it;
+            const bool valid = brow < in_batch;
+            const uint4 *row = sel + (base + (valid ? brow : 0)) * (uint64_t)stride4;
+            uint32_t s1, s2, sb, t1, t2, tb;
+            scan_class<G>(row, Qc, l, valid, s1, s2, sb);
+            scan_class<G>(row + 2 * Qc, Qt, l, valid, t1, t2, tb);
+            s1 = __reduce_add_sync(group_mask, s1); s2 = __reduce_add_sync(group_mask, s2);
+            sb = __reduce_add_sync(group_mask, sb); t1 = __reduce_add_sync(group_mask, t1);
+            t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
+            if (l == it) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
         }
-        return c;
-    };
-    // chunk pairs lane group `grp` receives in round c (0 when its row does not exist)
-    auto group_pairs = [&](const Cursor &c, uint32_t grp) -> uint32_t {
-        if (grp * G + c.it >= c.in_batch) return 0u;
-        return min(S * G, (c.cls ? Qt : Qc) - G * c.t0);
-    };
-    auto issue = [&](const Cursor &c, uint32_t stage) {      // lane 0 only
-        uint32_t total = 0;
-#pragma unroll
-        for (uint32_t grp = 0; grp < 32 / G; ++grp) total += group_pairs(c, grp);
-        mbar_expect_tx(&full[stage], total * 32u);
-        const uint4 *src0 = sel + (c.base + c.it) * (uint64_t)stride4 + (c.cls ? 2 * Qc : 0) + 2 * (G * c.t0);
-#pragma unroll
-        for (uint32_t grp = 0; grp < 32 / G; ++grp) {
-            const uint32_t pairs = group_pairs(c, grp);
-            if (pairs > 0)
-                bulk_g2s(ring + stage * stage_bytes + grp * group_bytes, src0 + (uint64_t)(grp * G) * stride4, pairs * 32u, &full[stage]);
-        }
-    };
-
-    HS h1 = {0, 0, 0}, h2 = {0, 0, 0}, hb = {0, 0, 0};
-    uint32_t s1 = 0, s2 = 0, sb = 0;                                  // case sums of the row in flight
-    uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of batch row `lane`
-
-    Cursor cons;
-    cons.base = r_begin; cons.valid = true;
-    cons.in_batch = (uint32_t)min((uint64_t)32, r_end - r_begin);
-    cons.it = 0; cons.cls = 0; cons.t0 = 0;
-    Cursor prod = cons;
-    for (uint32_t s = 0; s < n_stages && prod.valid; ++s) {
-        if (lane == 0) issue(prod, s);
-        prod = advance(prod);
-    }
-
-    uint32_t stage = 0, parity = 0;
-    while (cons.valid) {
-        mbar_wait(&full[stage], parity);
-        {
-            const uint32_t mine = group_pairs(cons, g);
-            const uint4 *sp = reinterpret_cast<const uint4 *>(ring + stage * stage_bytes + g * group_bytes) + 2 * l;
-#pragma unroll
-            for (uint32_t u = 0; u < SCAN_MAX_SLOTS; ++u) {
-                if (u * G + l < mine) {                 // u < S is implied: mine <= S*G
-                    ChunkPair cp;
-                    cp.x = sp[2 * u * G];
-                    cp.y = sp[2 * u * G + 1];
-                    accumulate_pair(cp, h1, h2, hb);
-                }
-            }
-        }
-        __syncwarp();                                   // every lane has consumed the stage: refill it
-        if (prod.valid) {
-            if (lane == 0) issue(prod, stage);
-            prod = advance(prod);
-        }
-        if (cons.t0 + S >= (cons.cls ? Tt : Tc)) {      // class finished
-            const uint32_t a = hs_total(h1), b = hs_total(h2), ab = hs_total(hb);
-            h1 = {0, 0, 0}; h2 = {0, 0, 0}; hb = {0, 0, 0};
-            if (cons.cls == 0) { s1 = a; s2 = b; sb = ab; }
-            else {                                      // row finished: reduce in the lane group, park in lane g*G + it
-                const uint32_t r1 = __reduce_add_sync(group_mask, s1), r2 = __reduce_add_sync(group_mask, s2);
-                const uint32_t rb = __reduce_add_sync(group_mask, sb), q1 = __reduce_add_sync(group_mask, a);
-                const uint32_t q2 = __reduce_add_sync(group_mask, b), qb = __reduce_add_sync(group_mask, ab);
-                if (l == cons.it) { m1c = r1; m2c = r2; mbc = rb; m1t = q1; m2t = q2; mbt = qb; }
-                if (cons.it + 1 >= min((uint32_t)G, cons.in_batch) && lane < cons.in_batch)   // batch finished
-                    finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, cons.base + lane - out_base, counts, mi, stats);
-            }
-        }
-        cons = advance(cons);
-        if (++stage == n_stages) { stage = 0; parity ^= 1; }
+        if (lane < in_batch)
+            finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + lane - out_base, counts, mi, stats);
     }
 }
 
@@ -352,29 +252,15 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
         if (waste < best - 1e-9) { best = waste; G = cand; }
     }
     const uint64_t n = snp_end - snp_begin;
-    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms, (n + 255) / 256));
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 3, (n + 255) / 256));
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
-    // round length: a whole class per round when it fits in SCAN_MAX_SLOTS chunk pairs per lane
-    const uint32_t Tmax = std::max((Qc + G - 1) / G, (Qt + G - 1) / G);
-    const uint32_t S = std::min<uint32_t>(Tmax, SCAN_MAX_SLOTS);
-    const size_t stage_bytes = 32ull * S * 32ull;
-    uint32_t n_stages = (uint32_t)std::min<size_t>(6, (200 * 1024) / (SCAN_WARPS * stage_bytes));
-    if (n_stages < 2) n_stages = 2;
-    const size_t smem = SCAN_WARPS * n_stages * stage_bytes + SCAN_WARPS * n_stages * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        GW_CUDA(cudaFuncSetAttribute(marginal_scan_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
     if (G == 8)
-        marginal_scan_kernel<8><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin, S, n_stages);
+        marginal_scan_kernel<8><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
     else if (G == 16)
-        marginal_scan_kernel<16><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin, S, n_stages);
+        marginal_scan_kernel<16><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
     else
-        marginal_scan_kernel<32><<<blocks, 256, smem, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin, S, n_stages);
+        marginal_scan_kernel<32><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
     GW_LAUNCHED();
     GW_CUDA(cudaEventRecord(s->ev1, s->stream));
     return GWASDEV_OK;
