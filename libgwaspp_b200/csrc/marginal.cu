@@ -13,6 +13,7 @@
 // (algorithms/maf_func.h:46-54) and the allelic / genotypic chi-square tests (no reference
 // counterpart). Bound: HBM bandwidth; algorithmic bytes = n_samples / 4 per SNP.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -153,29 +154,29 @@ __device__ __noinline__ void finish_snp(uint32_t m1c, uint32_t m2c, uint32_t mbc
     if (stats) fill_stats(ca, co, stats[o]);
 }
 
-constexpr int SCAN_SLOTS = 6;   // chunk pairs a lane loads back to back (12 x 128-bit loads in flight)
+// SLOTS = chunk pairs a lane loads back to back (2*SLOTS 128-bit loads in flight per lane)
 
 // one class of one row: lane l of its G-lane group takes chunk pairs l, l+G, ... of Q, SCAN_SLOTS at a
 // time with all loads of a round issued before the first is consumed
-template <int G>
+template <int G, int SLOTS>
 __device__ __forceinline__ void scan_class(const uint4 *__restrict__ base, uint32_t Q, uint32_t l, bool row_valid,
                                            uint32_t &s1, uint32_t &s2, uint32_t &sb) {
     HS h1 = {0, 0, 0}, h2 = {0, 0, 0}, hb = {0, 0, 0};
     const uint4 *p = base + 2 * l;
-    for (uint32_t q0 = l; q0 < Q; q0 += SCAN_SLOTS * G, p += 2 * SCAN_SLOTS * G) {
-        ChunkPair c[SCAN_SLOTS];
+    for (uint32_t q0 = l; q0 < Q; q0 += SLOTS * G, p += 2 * SLOTS * G) {
+        ChunkPair c[SLOTS];
 #pragma unroll
-        for (int u = 0; u < SCAN_SLOTS; ++u) c[u] = ld_pair(p + 2 * u * G, row_valid && q0 + u * G < Q);
+        for (int u = 0; u < SLOTS; ++u) c[u] = ld_pair(p + 2 * u * G, row_valid && q0 + u * G < Q);
 #pragma unroll
-        for (int u = 0; u < SCAN_SLOTS; ++u)
+        for (int u = 0; u < SLOTS; ++u)
             if (q0 + u * G < Q) accumulate_pair(c[u], h1, h2, hb);     // uniform over the lane group except at the row tail
     }
     s1 = hs_total(h1); s2 = hs_total(h2); sb = hs_total(hb);
 }
 
-// grid: persistent, 3 CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows.
-template <int G>
-__global__ void __launch_bounds__(256, 3)
+// grid: persistent, MINB CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows.
+template <int G, int SLOTS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
                      uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
                      uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
@@ -196,8 +197,8 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
             const bool valid = brow < in_batch;
             const uint4 *row = sel + (base + (valid ? brow : 0)) * (uint64_t)stride4;
             uint32_t s1, s2, sb, t1, t2, tb;
-            scan_class<G>(row, Qc, l, valid, s1, s2, sb);
-            scan_class<G>(row + 2 * Qc, Qt, l, valid, t1, t2, tb);
+            scan_class<G, SLOTS>(row, Qc, l, valid, s1, s2, sb);
+            scan_class<G, SLOTS>(row + 2 * Qc, Qt, l, valid, t1, t2, tb);
             s1 = __reduce_add_sync(group_mask, s1); s2 = __reduce_add_sync(group_mask, s2);
             sb = __reduce_add_sync(group_mask, sb); t1 = __reduce_add_sync(group_mask, t1);
             t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
@@ -252,15 +253,31 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
         if (waste < best - 1e-9) { best = waste; G = cand; }
     }
     const uint64_t n = snp_end - snp_begin;
-    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * 3, (n + 255) / 256));
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
+    // tuning knob (loads in flight per lane, resident CTAs per SM); defaults measured on B200, see DESIGN.md
+    int slots = 6, minb = 3;
+    if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d", &slots, &minb);
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * minb, (n + 255) / 256));
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
-    if (G == 8)
-        marginal_scan_kernel<8><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
-    else if (G == 16)
-        marginal_scan_kernel<16><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
-    else
-        marginal_scan_kernel<32><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, d_counts, d_mi, d_stats, snp_begin);
+#define SCAN_LAUNCH(GG, SS, BB)                                                                                          \
+    marginal_scan_kernel<GG, SS, BB><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, \
+                                                                    snp_end, d_counts, d_mi, d_stats, snp_begin)
+#define SCAN_CFG(GG)                                                                                   \
+    do {                                                                                               \
+        if (slots == 6 && minb == 3) SCAN_LAUNCH(GG, 6, 3);                                            \
+        else if (slots == 5 && minb == 3) SCAN_LAUNCH(GG, 5, 3);                                       \
+        else if (slots == 4 && minb == 4) SCAN_LAUNCH(GG, 4, 4);                                       \
+        else if (slots == 3 && minb == 4) SCAN_LAUNCH(GG, 3, 4);                                       \
+        else if (slots == 5 && minb == 4) SCAN_LAUNCH(GG, 5, 4);                                       \
+        else if (slots == 8 && minb == 2) SCAN_LAUNCH(GG, 8, 2);                                       \
+        else if (slots == 2 && minb == 5) SCAN_LAUNCH(GG, 2, 5);                                       \
+        else { set_error("GWASDEV_SCAN_CFG=%d,%d is not an instantiated configuration", slots, minb); return GWASDEV_EINVAL; } \
+    } while (0)
+    if (G == 8) SCAN_CFG(8);
+    else if (G == 16) SCAN_CFG(16);
+    else SCAN_CFG(32);
+#undef SCAN_CFG
+#undef SCAN_LAUNCH
     GW_LAUNCHED();
     GW_CUDA(cudaEventRecord(s->ev1, s->stream));
     return GWASDEV_OK;
