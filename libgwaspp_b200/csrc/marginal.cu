@@ -180,14 +180,17 @@ __global__ void __launch_bounds__(256, MINB)
 marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
                      uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
                      uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
-                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
+                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base, int interleave) {
     const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
     const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_snps = snp_end - snp_begin;
-    const uint64_t r_begin = snp_begin + warp * n_snps / n_warps, r_end = snp_begin + (warp + 1) * n_snps / n_warps;
-    for (uint64_t base = r_begin; base < r_end; base += 32) {
+    // contiguous balanced ranges (default) or batches of 32 rows dealt round-robin over the warps
+    const uint64_t r_begin = interleave ? snp_begin + warp * 32 : snp_begin + warp * n_snps / n_warps;
+    const uint64_t r_end = interleave ? snp_end : snp_begin + (warp + 1) * n_snps / n_warps;
+    const uint64_t r_step = interleave ? n_warps * 32 : 32;
+    for (uint64_t base = r_begin; base < r_end; base += r_step) {
         const uint32_t in_batch = (uint32_t)min((uint64_t)32, r_end - base);
         const uint32_t passes = min((uint32_t)G, in_batch);
         uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of row (base + lane)
@@ -255,13 +258,13 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     const uint64_t n = snp_end - snp_begin;
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
     // tuning knob (loads in flight per lane, resident CTAs per SM); defaults measured on B200, see DESIGN.md
-    int slots = 6, minb = 3;
-    if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d", &slots, &minb);
+    int slots = 5, minb = 3, interleave = 0;
+    if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d,%d,%d", &slots, &minb, &G, &interleave);
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * minb, (n + 255) / 256));
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
 #define SCAN_LAUNCH(GG, SS, BB)                                                                                          \
     marginal_scan_kernel<GG, SS, BB><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, \
-                                                                    snp_end, d_counts, d_mi, d_stats, snp_begin)
+                                                                    snp_end, d_counts, d_mi, d_stats, snp_begin, interleave)
 #define SCAN_CFG(GG)                                                                                   \
     do {                                                                                               \
         if (slots == 6 && minb == 3) SCAN_LAUNCH(GG, 6, 3);                                            \

@@ -1,6 +1,6 @@
 """Tuning sweep of the marginal-scan kernel configuration (GWASDEV_SCAN_CFG=slots,blocks_per_sm) on configs[1]."""
 import os, sys, subprocess, json
-cfgs = ["6,3", "5,3", "4,4", "3,4", "5,4", "8,2", "2,5"]
+cfgs = sys.argv[1:] or ["5,3,8,0", "5,3,8,1", "5,3,16,0", "5,3,16,1", "5,3,32,0", "5,3,32,1", "3,4,32,1", "2,5,32,1", "2,5,8,1"]
 for c in cfgs:
     env = dict(os.environ, GWASDEV_SCAN_CFG=c)
     out = subprocess.run([sys.executable, "bench.py", "--no-pairwise", "--no-cpu-baseline", "--steps", "20"], env=env,
