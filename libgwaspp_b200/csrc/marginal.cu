@@ -50,11 +50,16 @@ __device__ __forceinline__ void hs_add4(HS &h, uint32_t w0, uint32_t w1, uint32_
 }
 __device__ __forceinline__ uint32_t hs_total(const HS &h) { return 4 * h.fours4 + 2 * __popc(h.twos) + __popc(h.ones); }
 
+// |p1| and |p2| go through the carry-save adders (ALU pipe), |p1 & p2| through plain POPC (XU pipe): with
+// ~6 LOP3 + 1 POPC per carry-save stream and 4 POPC per plain stream, two-and-one balances the two pipes
+// (ALU 2 warp-instr/clk/SM, XU 0.5) better than three-and-none or none-and-three (B200 sweep).
 __device__ __forceinline__ void accumulate_pair(const ChunkPair &c, HS &h1, HS &h2, HS &hb) {
     hs_add4(h1, c.x.x, c.x.y, c.x.z, c.x.w);
     hs_add4(h2, c.y.x, c.y.y, c.y.z, c.y.w);
-    hs_add4(hb, c.x.x & c.y.x, c.x.y & c.y.y, c.x.z & c.y.z, c.x.w & c.y.w);
+    hb.ones += __popc(c.x.x & c.y.x) + __popc(c.x.y & c.y.y);
+    hb.twos += __popc(c.x.z & c.y.z) + __popc(c.x.w & c.y.w);
 }
+__device__ __forceinline__ uint32_t plain_total(const HS &h) { return h.ones + h.twos; }
 
 // chi-square upper tail for df in {1, 2}: pchisq(x, df, lower=0) == gsl_cdf_chisq_Q(x, df)
 __device__ __forceinline__ double chisq_upper(double x, int df) {
@@ -171,7 +176,7 @@ __device__ __forceinline__ void scan_class(const uint4 *__restrict__ base, uint3
         for (int u = 0; u < SLOTS; ++u)
             if (q0 + u * G < Q) accumulate_pair(c[u], h1, h2, hb);     // uniform over the lane group except at the row tail
     }
-    s1 = hs_total(h1); s2 = hs_total(h2); sb = hs_total(hb);
+    s1 = hs_total(h1); s2 = hs_total(h2); sb = plain_total(hb);
 }
 
 // grid: persistent, MINB CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows.
@@ -258,7 +263,7 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     const uint64_t n = snp_end - snp_begin;
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
     // tuning knob (loads in flight per lane, resident CTAs per SM); defaults measured on B200, see DESIGN.md
-    int slots = 5, minb = 3, interleave = 0;
+    int slots = 5, minb = 3, interleave = 1;
     if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d,%d,%d", &slots, &minb, &G, &interleave);
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * minb, (n + 255) / 256));
     GW_CUDA(cudaEventRecord(s->ev0, s->stream));
