@@ -174,6 +174,9 @@ GWASDEV_API int gwasdev_pairwise_epi_test(int device, uint64_t n, const int32_t 
 /* Register-only __popc throughput in 32-bit word-cells (AND+POPC) per second on `device`; the
  * integer-pipe roofline denominator of the pairwise screen. */
 GWASDEV_API int gwasdev_popc_peak(int device, double *word_cells_per_s, double *sm_clock_mhz);
+/* Read-only streaming bandwidth (GB/s) of a plain 128-bit-load kernel over `bytes` of HBM on `device`:
+ * context for the marginal scan's roofline next to the driver-measured copy bandwidth. */
+GWASDEV_API int gwasdev_hbm_read_peak(int device, uint64_t bytes, double *gb_per_s);
 
 #ifdef __cplusplus
 }

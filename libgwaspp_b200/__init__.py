@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "gwasdev_select_case_control", "gwasdev_case_control_counts", "gwasdev_get_selected_rows",
     "gwasdev_marginal_scan", "gwasdev_last_scan_ms", "gwasdev_counts", "gwasdev_pair_tables",
     "gwasdev_pairwise_scan", "gwasdev_ksa", "gwasdev_ksa_screen_f32", "gwasdev_gtest", "gwasdev_pairwise_epi_test",
-    "gwasdev_popc_peak",
+    "gwasdev_popc_peak", "gwasdev_hbm_read_peak",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
     L.gwasdev_gtest.argtypes = [vp, u64, vp, vp, vp, vp]
     L.gwasdev_pairwise_epi_test.argtypes = [i32, u64, vp, vp, vp, vp]
     L.gwasdev_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.gwasdev_hbm_read_peak.argtypes = [i32, u64, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -146,6 +147,12 @@ def popc_peak(device: int = 0) -> tuple[float, float]:
     r, mhz = C.c_double(), C.c_double()
     _check(load_library().gwasdev_popc_peak(device, C.byref(r), C.byref(mhz)), "gwasdev_popc_peak")
     return r.value, mhz.value
+
+
+def hbm_read_peak(device: int = 0, nbytes: int = 1 << 31) -> float:
+    r = C.c_double()
+    _check(load_library().gwasdev_hbm_read_peak(device, nbytes, C.byref(r)), "gwasdev_hbm_read_peak")
+    return r.value
 
 
 def pairwise_epi_test(cs, ct, device: int = 0):
