@@ -90,7 +90,37 @@ int main(int argc, char **argv) {
     std::ostream *out = &std::cout;
     if (!outfile.empty()) { of.open(outfile.c_str()); if (!of.is_open()) { std::cerr << "cannot open " << outfile << std::endl; return 1; } out = &of; }
 
-    if (test == "test-inline-maf") compute(inline_maf_print, &gd, out);
+    if (test == "dump-api") {
+        // every per-call virtual of the GenoTable interface, one line each (used by tests/test_gpu_host_layer.py)
+        DeviceGenoTable &gt = *gd.getGenotypeTable();
+        CaseControlSet &ccs = *gd.getCaseControlSet();
+        const int M = gt.row_size(), N = gt.column_size();
+        for (int r = 0; r < M; r += 7)
+            for (int c = 0; c < N; c += 11) *out << "call " << r << " " << c << " " << gt.getCallAt((uint)r, (uint)c) << "\n";
+        auto ft = [&](const char *tag, int r, const frequency_table &a) { *out << tag << " " << r << " " << a.aa << " " << a.ab << " " << a.bb << " " << a.xx << "\n"; };
+        for (int r = 0; r < M; ++r) { GenotypeDistribution d; gt.getGenotypeDistribution((uint)r, d); ft("whole", r, *d.getDistribution()); }
+        for (int r = 0; r < M; ++r) { CaseControlGenotypeDistribution d; gt.getCaseControlGenotypeDistribution((uint)r, ccs, d); ft("mask_ca", r, *d.getCaseDistribution()); ft("mask_co", r, *d.getControlDistribution()); }
+        gt.selectCaseControl(ccs);
+        marginal_information *mar = NULL; int nm = 0;
+        computeMargins(gt, N, mar, nm);
+        for (int r = 0; r < M; ++r) {
+            CaseControlGenotypeDistribution d; gt.getCaseControlGenotypeDistribution((uint)r, d); ft("sel_ca", r, *d.getCaseDistribution()); ft("sel_co", r, *d.getControlDistribution());
+            marginal_information m; CaseControlGenotypeDistribution e; gt.getCaseControlGenotypeDistribution((uint)r, e, m);
+            ft("mar_ca", r, m.cases); ft("mar_co", r, m.controls);
+            if (memcmp(&m, &mar[r], sizeof m) != 0) *out << "MARGIN_MISMATCH " << r << "\n";
+        }
+        auto tab = [&](const char *tag, int i, int j, const CONTIN_TABLE_T &t) { *out << tag << " " << i << " " << j; for (int q = 0; q < 16; ++q) *out << " " << t.contin[q]; *out << "\n"; };
+        for (int i = 0; i < M; i += 5)
+            for (int j = i + 1; j < M; j += 9) {
+                ContingencyTable ct; gt.getContingencyTable((uint)i, (uint)j, ct); tab("t0", i, j, *ct.getContingencyTable());
+                CaseControlContingencyTable a, b, c;
+                gt.getCaseControlContingencyTable((uint)i, (uint)j, ccs, a); tab("t1_ca", i, j, *a.getCaseContingencyTable()); tab("t1_co", i, j, *a.getControlContingencyTable());
+                gt.getCaseControlContingencyTable((uint)i, (uint)j, b); tab("t2_ca", i, j, *b.getCaseContingencyTable()); tab("t2_co", i, j, *b.getControlContingencyTable());
+                gt.getCaseControlContingencyTable((uint)i, (uint)j, mar[i], mar[j], c); tab("t3_ca", i, j, *c.getCaseContingencyTable()); tab("t3_co", i, j, *c.getControlContingencyTable());
+            }
+        delete[] mar;
+    }
+    else if (test == "test-inline-maf") compute(inline_maf_print, &gd, out);
     else if (test == "select-cc-maf") compute(select_cc_maf, &gd, out);
     else if (test == "inline-cc-maf") compute(inline_cc_maf, &gd, out);
     else if (test == "dist-perform") compute(genotype_dist_performance, &gd, out);

@@ -1,0 +1,91 @@
+"""Multi-GPU driver for the pairwise screen: one process per GPU (torch.distributed), the store replicated,
+64x64 SNP tile pairs dealt round-robin over the ranks (no data-path collective), hit lists combined with
+one all_gather at the end -- NCCL over NVLink on GPUs, gloo on CPU for the host-logic tests.
+
+The reference has no counterpart (single process, single thread); the work split follows SURVEY.md 8(e).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+HIT_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("stat", "<f8")])
+
+
+def hits_to_tensor(hits: np.ndarray, capacity: int, device):
+    """Pack a HIT_DTYPE array into a fixed-size (capacity, 2) int64 tensor (16-byte records) for all_gather."""
+    import torch
+    buf = np.zeros((capacity, 2), np.int64)
+    buf.view(np.uint8).reshape(-1)[: hits.nbytes] = hits.view(np.uint8).reshape(-1)
+    return torch.from_numpy(buf).to(device)
+
+
+def tensor_to_hits(t, n: int) -> np.ndarray:
+    raw = t.cpu().numpy().view(np.uint8).reshape(-1)[: n * HIT_DTYPE.itemsize]
+    return np.frombuffer(raw.tobytes(), HIT_DTYPE).copy()
+
+
+def merge_hits(parts) -> np.ndarray:
+    """Union of per-rank hit lists in the reference's (i, j) emission order. Shards are disjoint by
+    construction; duplicates would mean a sharding bug, so they are rejected."""
+    parts = [p for p in parts if len(p)]
+    if not parts:
+        return np.zeros(0, HIT_DTYPE)
+    allh = np.concatenate(parts)
+    order = np.lexsort((allh["j"], allh["i"]))
+    allh = allh[order]
+    key = allh["i"].astype(np.uint64) << np.uint64(32) | allh["j"].astype(np.uint64)
+    if len(key) > 1 and np.any(key[1:] == key[:-1]):
+        raise ValueError("duplicate SNP pair across shards")
+    return allh
+
+
+def top_k(hits: np.ndarray, k: int) -> np.ndarray:
+    """The k strongest interactions (ties broken by (i, j))."""
+    order = np.lexsort((hits["j"], hits["i"], -hits["stat"]))
+    return hits[order[:k]]
+
+
+def gather_hits(local_hits: np.ndarray, group=None, device=None) -> np.ndarray:
+    """all_gather the ranks' hit lists (counts first, then buffers padded to the largest count) and merge."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return merge_hits([local_hits])
+    world = dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    cnt = torch.tensor([len(local_hits)], dtype=torch.int64, device=device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    counts = [int(c.item()) for c in cnts]
+    cap = max(1, max(counts))
+    mine = hits_to_tensor(local_hits, cap, device)
+    bufs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine, group=group)
+    return merge_hits([tensor_to_hits(b, n) for b, n in zip(bufs, counts)])
+
+
+def shard_tiles(n_snps: int, shard: int, n_shards: int, tile: int = 64):
+    """Tile pairs (I <= J) handled by `shard`: linear upper-triangular index t with t % n_shards == shard --
+    the same enumeration the screen kernel uses. Returns (list of (I, J), pairs covered)."""
+    T = (n_snps + tile - 1) // tile
+    out, pairs, t = [], 0, 0
+    for I in range(T):
+        mi = min(tile, n_snps - I * tile)
+        for J in range(I, T):
+            if t % n_shards == shard:
+                mj = min(tile, n_snps - J * tile)
+                out.append((I, J))
+                pairs += mi * (mi - 1) // 2 if I == J else mi * mj
+            t += 1
+    return out, pairs
+
+
+def pairwise_scan_distributed(store, threshold: float = 30.0, group=None):
+    """Run this rank's shard of the exhaustive screen and return the merged, (i, j)-ordered hit list on
+    every rank together with this rank's PairStats."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    hits, stats = store.pairwise_scan(threshold, shard=rank, n_shards=world)
+    return gather_hits(hits, group), stats

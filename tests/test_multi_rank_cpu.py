@@ -1,0 +1,89 @@
+"""N > 1 host logic on CPU: world_size-2 gloo all_gather of hit lists, shard bookkeeping, merge order.
+(The GPU side of the same path is covered by tests/test_gpu_parity.py through the shard arguments.)"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from libgwaspp_b200 import multi_gpu as mg  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_hits(rank, world, n_snps=900):
+    """Deterministic pseudo-hits living in this rank's tile shard."""
+    tiles, _ = mg.shard_tiles(n_snps, rank, world)
+    rng = np.random.default_rng(100 + rank)
+    out = []
+    for I, J in tiles[:: max(1, len(tiles) // 7)]:
+        i = I * 64 + int(rng.integers(0, 32))
+        j = J * 64 + 32 + int(rng.integers(0, 32))
+        if i < j < n_snps:
+            out.append((i, j, 30.0 + float(rng.random()) * 10))
+    return np.array(out, mg.HIT_DTYPE)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    merged = mg.gather_hits(_fake_hits(rank, world))
+    q.put((rank, merged.tobytes()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_gather_of_hits(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = mg.merge_hits([_fake_hits(r, world) for r in range(world)])
+    assert len(want) > 5
+    for r in range(world):
+        assert np.array_equal(np.frombuffer(got[r], mg.HIT_DTYPE), want)     # every rank holds the same merged list
+    key = want["i"].astype(np.int64) * 10_000 + want["j"]
+    assert np.all(np.diff(key) > 0)                                          # the reference's (i, j) emission order
+
+
+@pytest.mark.parametrize("n_snps,world", [(130, 2), (1000, 3), (64, 4), (50_000, 8), (4097, 5)])
+def test_shards_partition_the_pair_space(n_snps, world):
+    seen, total = set(), 0
+    for r in range(world):
+        tiles, pairs = mg.shard_tiles(n_snps, r, world)
+        assert not (seen & set(tiles))
+        seen |= set(tiles)
+        total += pairs
+    T = (n_snps + 63) // 64
+    assert len(seen) == T * (T + 1) // 2
+    assert total == n_snps * (n_snps - 1) // 2
+
+
+def test_merge_rejects_duplicates_and_orders_top_k():
+    a = np.array([(1, 5, 31.0), (0, 9, 40.0)], mg.HIT_DTYPE)
+    b = np.array([(0, 3, 35.0)], mg.HIT_DTYPE)
+    m = mg.merge_hits([a, b])
+    assert [(int(x["i"]), int(x["j"])) for x in m] == [(0, 3), (0, 9), (1, 5)]
+    assert [float(x["stat"]) for x in mg.top_k(m, 2)] == [40.0, 35.0]
+    with pytest.raises(ValueError):
+        mg.merge_hits([a, a])
+    assert len(mg.merge_hits([])) == 0
