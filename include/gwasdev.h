@@ -67,6 +67,8 @@ typedef struct {
     double screen_ms;        /* device time of the tiled screen kernel (CUDA events) */
     double total_ms;         /* device time of the whole call incl. re-scoring */
     uint32_t tiles, tiles_nine_cell;
+    uint32_t engine;         /* engine used for the tiles without missing calls: 1 AND+POPC, 2 tensor cores */
+    uint32_t reserved;
 } gwasdev_pair_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -156,6 +158,17 @@ GWASDEV_API int gwasdev_pair_tables(gwasdev_store *s, uint64_t n, const uint32_t
 GWASDEV_API int gwasdev_pairwise_scan(gwasdev_store *s, double threshold, uint32_t shard, uint32_t n_shards,
                           gwasdev_hit *hits, uint64_t capacity, uint64_t *n_hits,
                           gwasdev_pair_stats *stats, int on_device);
+/* Engine for the tile pairs without missing calls. 0 (default): tensor cores (tcgen05 kind::i8 GEMM over signed
+ * one-hot bytes, pairwise_mma.cu) when n_case < 16384 and n_ctrl < 131072, else AND+POPC tiles; 1: AND+POPC
+ * tiles; 2: tensor cores or GWASDEV_EINVAL. Tile pairs with missing calls always take the 9-cell AND+POPC
+ * kernel (the reference's other branch, compressed_genotype_table5.cpp:1000-1067). Results are identical. */
+GWASDEV_API int gwasdev_set_pair_engine(gwasdev_store *s, int engine);
+/* Parity probe of the tensor-core engine: raw corner counts of one tile pair of its schedule (A-block I of 64
+ * SNPs, B-block J of 128 SNPs, I <= 2J+1): out[(a*128 + b)*8 + {0,1,2,3}] = cases AA_BB, AA_bb, aa_BB, aa_bb
+ * (compressed_genotype_table5.cpp:1069-1083), +4: controls (:1118-1132). out holds 64*128*8 values. */
+GWASDEV_API int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *out);
+/* Diagnostic twin of gwasdev_ksa_screen_f32 for the tensor-core engine's epilogue. */
+GWASDEV_API int gwasdev_ksa_screen_mma_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, float *stat);
 /* KSA statistic in fp64 for given pairs (the re-scoring kernel on its own; parity probe). */
 GWASDEV_API int gwasdev_ksa(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, double *stat);
 /* Diagnostic: the screen kernel's fp32 epilogue evaluated on given pairs, to measure its distance from

@@ -31,7 +31,7 @@ assert MI_DTYPE.itemsize == 192 and STATS_DTYPE.itemsize == 64 and HIT_DTYPE.ite
 class PairStats(C.Structure):
     _fields_ = [("pairs_tested", C.c_uint64), ("candidates", C.c_uint64), ("hits", C.c_uint64),
                 ("word_cells", C.c_uint64), ("screen_ms", C.c_double), ("total_ms", C.c_double),
-                ("tiles", C.c_uint32), ("tiles_nine_cell", C.c_uint32)]
+                ("tiles", C.c_uint32), ("tiles_nine_cell", C.c_uint32), ("engine", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class GwasDevError(RuntimeError):
@@ -48,7 +48,8 @@ ABI_SYMBOLS = [
     "gwasdev_select_case_control", "gwasdev_case_control_counts", "gwasdev_get_selected_rows",
     "gwasdev_marginal_scan", "gwasdev_last_scan_ms", "gwasdev_counts", "gwasdev_pair_tables",
     "gwasdev_pairwise_scan", "gwasdev_ksa", "gwasdev_ksa_screen_f32", "gwasdev_gtest", "gwasdev_pairwise_epi_test",
-    "gwasdev_popc_peak", "gwasdev_hbm_read_peak",
+    "gwasdev_popc_peak", "gwasdev_hbm_read_peak", "gwasdev_set_pair_engine", "gwasdev_mma_tile_counts",
+    "gwasdev_ksa_screen_mma_f32",
 ]
 
 
@@ -89,6 +90,9 @@ def load_library():
     L.gwasdev_ksa.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_ksa_screen_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_gtest.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.gwasdev_set_pair_engine.argtypes = [vp, i32]
+    L.gwasdev_mma_tile_counts.argtypes = [vp, u32, u32, vp]
+    L.gwasdev_ksa_screen_mma_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_pairwise_epi_test.argtypes = [i32, u64, vp, vp, vp, vp]
     L.gwasdev_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gwasdev_hbm_read_peak.argtypes = [i32, u64, C.POINTER(C.c_double)]
@@ -300,6 +304,22 @@ class GenoStore:
         pi, pj = self._pairs(pi, pj)
         out = np.zeros(len(pi), np.float32)
         _check(self.L.gwasdev_ksa_screen_f32(self.h, len(pi), _ptr(pi), _ptr(pj), _ptr(out)), "gwasdev_ksa_screen_f32")
+        return out
+
+    def ksa_screen_mma_f32(self, pi, pj) -> np.ndarray:
+        pi, pj = self._pairs(pi, pj)
+        out = np.zeros(len(pi), np.float32)
+        _check(self.L.gwasdev_ksa_screen_mma_f32(self.h, len(pi), _ptr(pi), _ptr(pj), _ptr(out)), "gwasdev_ksa_screen_mma_f32")
+        return out
+
+    def set_pair_engine(self, engine: int):
+        """0 auto, 1 AND+POPC tiles, 2 tensor cores (tcgen05)."""
+        _check(self.L.gwasdev_set_pair_engine(self.h, engine), "gwasdev_set_pair_engine")
+
+    def mma_tile_counts(self, I: int, J: int) -> np.ndarray:
+        """Raw corner counts of tile pair (A-block I of 64 SNPs, B-block J of 128 SNPs): [64, 128, 2 classes, 4 cells]."""
+        out = np.zeros((64, 128, 2, 4), np.uint32)
+        _check(self.L.gwasdev_mma_tile_counts(self.h, I, J, _ptr(out)), "gwasdev_mma_tile_counts")
         return out
 
     def gtest(self, pi, pj):

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgwasdev.so")
 HOST_LIB = os.path.join(HERE, "libgwaspp_host.so")
 HOST_CLI = os.path.join(HERE, "gwas_b200")
-SOURCES = ["store.cu", "marginal.cu", "pairwise.cu"]
+SOURCES = ["store.cu", "marginal.cu", "pairwise.cu", "pairwise_mma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
 

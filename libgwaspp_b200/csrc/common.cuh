@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "gwasdev.h"
 
@@ -151,6 +152,20 @@ struct gwasdev_store {
     bool side_valid = false;
 
     size_t cap_pw = 0, cap_mi = 0, cap_side = 0, cap_tile = 0;
+
+    // tensor-core pair screen (pairwise_mma.cu): signed-byte one-hot rows, K-major
+    int pair_engine = 0;          // 0 auto, 1 AND+POPC tiles, 2 tcgen05 tiles (gwasdev_set_pair_engine)
+    bool mm_built = false;
+    uint64_t mm_rows = 0;         // 2 rows (planes aa, bb) per SNP, SNP count rounded up to 128
+    uint32_t mm_kbytes = 0;       // bytes per row: cases padded to 128, then controls padded to 128
+    int8_t *d_mm = nullptr;
+    void *tmap_mm = nullptr;      // host copies of the two CUtensorMaps (A box, B box)
+    void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
+    uint64_t *d_band_off = nullptr;
+    uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
+    std::vector<uint8_t> h_tile_missing;   // host copy of d_tile_missing (valid with side_valid)
+    size_t cap_mm = 0, cap_mma_row = 0, cap_mma_col = 0, cap_band = 0;
+    bool mma_side_valid = false;
     bool any_missing = false, any_clean = false;     // over tiles, valid with side_valid
 
     // grow-only scratch, so that steady-state calls never touch cudaMalloc / cudaFree (both cost

@@ -326,7 +326,7 @@ int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     if (e == cudaSuccess && mi) e = cudaMemcpyAsync(mi, d_mi, n * sizeof(gwasdev_marginal_information), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) { set_error("gwasdev_marginal_scan: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
-    if (mi && full) { s->mi_valid = true; s->side_valid = false; }
+    if (mi && full) { s->mi_valid = true; s->side_valid = false; s->mma_side_valid = false; }
     return GWASDEV_OK;
 }
 

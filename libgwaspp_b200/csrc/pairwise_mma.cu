@@ -1,0 +1,649 @@
+// K2+K3 on the 5th-generation tensor cores: the four corner cells of every pair's 3x3x2 table as ONE
+// signed-byte GEMM per SNP tile pair (tcgen05.mma kind::i8, accumulators in TMEM), fused with the fp32 KSA
+// screen. Same results as pair_screen_kernel<false> in pairwise.cu (the AND+POPC engine): the counted
+// cells are integers, and the candidates are re-scored in fp64 by rescore_kernel either way.
+//
+// Reference path replaced: the no-missing shortcut of getCaseControlContingencyTable(i, j, m1, m2, ccct)
+// (genotype/compressed_genotype_table5.cpp:1069-1144: AA_BB, AA_bb, aa_BB, aa_bb counted, the other five
+// cells from the per-SNP class margins) + computeBoost's KSA statistic and threshold
+// (algorithms/epistasis_func.cpp:424-470, :482-484).
+//
+// Formulation. Row 2s+p of the operand matrix is the one-hot plane p (0: genotype aa, 1: genotype bb) of
+// SNP s over the samples, one signed byte per sample: a case sample that has the genotype is +1, a
+// control sample that has it is -128, everything else 0. A sample is either case or control for both
+// SNPs of a pair, so
+//     D[2i+p][2j+q] = sum_samples A*B = n_case(p, q) + 16384 * n_ctrl(p, q)
+// exactly in int32 (n_case < 16384, n_ctrl < 131072): one accumulator tile carries both classes.
+//
+// Kernel. One CTA per SM, persistent over tile pairs (64 A-SNPs = 128 rows) x (128 B-SNPs = 256 rows):
+//   warp 0   TMA producer : cp.async.bulk.tensor.2d, SWIZZLE_128B boxes of 128 sample bytes, 4-stage ring
+//   warp 1   MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=32, 4 per stage, into one of
+//                           two 256-column TMEM accumulators; tcgen05.commit frees the stage / publishes
+//                           the accumulator
+//   warps 2+ epilogue     : tcgen05.ld 32x32b, lane pairs swap the two planes by shuffle, decode the
+//                           counts, margins -> 3x3x2 table, fp32 KSA, candidates above threshold - margin
+// Tile order keeps a band of 16 A-blocks and a sliding window of B-blocks L2-resident.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "pair_common.cuh"
+
+int gwasdev_internal_ensure_side(gwasdev_store *s);   // pairwise.cu: margins, PairSide records, missing-call flags
+
+namespace gwasdev {
+
+constexpr int MMA_A_SNPS = 64, MMA_B_SNPS = 128;
+constexpr int MMA_M = 2 * MMA_A_SNPS, MMA_N = 2 * MMA_B_SNPS;      // operand rows per tile
+constexpr int MMA_KB = 128;                                        // sample bytes per stage (one 128B swizzle row)
+constexpr int UMMA_K = 32;                                         // bytes per tcgen05.mma kind::i8
+constexpr int MMA_STAGES = 4;
+constexpr int A_STAGE_BYTES = MMA_M * MMA_KB, B_STAGE_BYTES = MMA_N * MMA_KB;
+constexpr int STAGE_BYTES_MMA = A_STAGE_BYTES + B_STAGE_BYTES;     // 48 KiB
+constexpr int EPI_WARPS = 16;
+constexpr int MMA_THREADS = (2 + EPI_WARPS) * 32;
+constexpr int BAND = 16;                                           // A-blocks per L2 band
+constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
+constexpr uint32_t CTRL_SHIFT = 14;                                // (-128)^2 = 2^14
+
+// per-SNP epilogue records, log2 units. Row role (SNP "A" of the pair) / column role (SNP "B").
+//   C_row = sum_kg c_k[g] log2 pca_k[g] + N log2 N          C_col = sum_kg c_k[g] (log2 pbc_k[g] - log2 m[g])
+struct __align__(16) MmaRow { float pca[2][3]; uint16_t cnt[2][3]; float C; uint32_t pad[2]; };
+struct __align__(16) MmaCol { float w[2][3];   uint16_t cnt[2][3]; float C; uint32_t pad[2]; };
+static_assert(sizeof(MmaRow) == 48 && sizeof(MmaCol) == 48, "48-byte epilogue records");
+
+struct MmaParams {
+    uint32_t TA, TB;            // A blocks (64 SNPs), B blocks (128 SNPs)
+    uint32_t NKB;               // 128-byte sample blocks per row
+    uint32_t n_bands;
+    uint64_t M;
+    uint64_t n_tiles;
+    uint32_t shard, n_shards;
+    const uint64_t *band_off;   // [n_bands + 1] tiles before band b
+    const MmaRow *row;
+    const MmaCol *col;
+    const uint8_t *tile_missing;   // per 64-SNP block
+    float thr, N;
+    Candidate *cand;
+    unsigned long long *n_cand;
+    uint64_t cap;
+    uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only
+    uint64_t dump_tile;
+};
+
+// ---- PTX: tcgen05 ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// mbarrier wait with a watchdog: a broken pipeline traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address, 16-byte units
+    d |= (uint64_t)0 << 16;                                // leading byte offset: unused (one swizzle atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor kind::i8: D s32, A and B signed 8-bit, both K-major, N >> 3, M >> 4
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+
+// ---- tile order -------------------------------------------------------------------------------------
+// Band b holds A-blocks [16b, 16b+16); inside a band tiles run column-major over B-blocks J >= 8b, and a
+// column holds the A-blocks I of the band with I <= 2J+1 (a B-block at or right of the A-block).
+__host__ __device__ inline uint32_t band_height(uint32_t TA, uint32_t b) { return min((uint32_t)BAND, TA - BAND * b); }
+__host__ __device__ inline uint32_t column_height(uint32_t na, uint32_t c) { return min(na, 2 * c + 2); }
+
+__device__ __forceinline__ void mma_tile_from_index(uint64_t t, const MmaParams &p, uint32_t &I, uint32_t &J) {
+    uint32_t lo = 0, hi = p.n_bands;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (p.band_off[mid] <= t) lo = mid; else hi = mid; }
+    uint64_t r = t - p.band_off[lo];
+    const uint32_t na = band_height(p.TA, lo);
+    uint32_t c = 0;
+    for (;;) {
+        const uint32_t h = column_height(na, c);
+        if (h == na) break;
+        if (r < h) { I = BAND * lo + (uint32_t)r; J = (BAND / 2) * lo + c; return; }
+        r -= h; ++c;
+    }
+    c += (uint32_t)(r / na);
+    I = BAND * lo + (uint32_t)(r % na);
+    J = (BAND / 2) * lo + c;
+}
+
+// ---- fp32 KSA on the four counted corners -----------------------------------------------------------
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float g2(float n) { return n * lg2_approx(fmaxf(n, 1.0f)); }
+
+// c[k] = {AA_BB, AA_bb, aa_BB, aa_bb} of class k. Returns 2 ln2 (sum g2(n_abk) - sum g2(n_ab.) + N log2 tau - C_row - C_col),
+// which equals ksa_screen_f32 of pairwise.cu when neither SNP has a missing call (row/column sums of the
+// table are then the per-SNP class counts).
+__device__ __forceinline__ float ksa_screen_corners(const uint32_t (&c)[2][4], const float (&pca)[2][3], const uint32_t (&ca)[2][3],
+                                                    const float (&w)[2][3], const uint32_t (&cb)[2][3], float Csum, float N) {
+    uint32_t n[2][3][3];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t AB = c[k][0], Ab = c[k][1], aB = c[k][2], ab = c[k][3];
+        n[k][0][0] = AB; n[k][0][2] = Ab; n[k][2][0] = aB; n[k][2][2] = ab;
+        n[k][0][1] = ca[k][0] - AB - Ab;
+        n[k][2][1] = ca[k][2] - ab - aB;
+        n[k][1][0] = cb[k][0] - AB - aB;
+        n[k][1][2] = cb[k][2] - Ab - ab;
+        n[k][1][1] = cb[k][1] - n[k][0][1] - n[k][2][1];
+    }
+    float S = 0.f, tau = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const float c0 = u2f(n[0][a][b]), c1 = u2f(n[1][a][b]), cab = c0 + c1;
+            const float W = fmaf(w[0][b], pca[0][a], w[1][b] * pca[1][a]);
+            tau = fmaf(cab, W, tau);
+            S += g2(c0) + g2(c1) - g2(cab);
+        }
+    return 1.3862943611f * (fmaf(N, lg2_approx(tau), S) - Csum);
+}
+
+// ---- the kernel -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const MmaParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;              // SWIZZLE_128B atoms are 1024-byte aligned
+    unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm + MMA_STAGES * STAGE_BYTES_MMA);
+    uint64_t *empty = full + MMA_STAGES;
+    uint64_t *tfull = empty + MMA_STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // whole warp: allocate all 512 TMEM columns (two accumulators)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint64_t stride = (uint64_t)p.n_shards * gridDim.x;
+    const uint64_t first = p.dump ? p.dump_tile : p.shard + (uint64_t)p.n_shards * blockIdx.x;
+    const uint64_t last = p.dump ? p.dump_tile + 1 : p.n_tiles;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint64_t it = 0;
+            for (uint64_t t = first; t < last; t += stride) {
+                uint32_t I, J;
+                mma_tile_from_index(t, p, I, J);
+                for (uint32_t kb = 0; kb < p.NKB; ++kb, ++it) {
+                    const int st = (int)(it % MMA_STAGES);
+                    mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
+                    unsigned char *dst = sm + st * STAGE_BYTES_MMA;
+                    mbar_expect_tx(&full[st], STAGE_BYTES_MMA);
+                    tma_load_2d(dst, &map_a, (int)(kb * MMA_KB), (int)(I * MMA_M), &full[st]);
+                    tma_load_2d(dst + A_STAGE_BYTES, &map_b, (int)(kb * MMA_KB), (int)(J * MMA_N), &full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint64_t it = 0, tile_it = 0;
+            for (uint64_t t = first; t < last; t += stride, ++tile_it) {
+                const uint32_t buf = (uint32_t)(tile_it & 1);
+                mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + buf * ACC_COLS;
+                for (uint32_t kb = 0; kb < p.NKB; ++kb, ++it) {
+                    const int st = (int)(it % MMA_STAGES);
+                    mbar_wait_wd(&full[st], (uint32_t)((it / MMA_STAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t a_addr = base + st * STAGE_BYTES_MMA, b_addr = a_addr + A_STAGE_BYTES;
+                    const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+#pragma unroll
+                    for (int k = 0; k < MMA_KB / UMMA_K; ++k)
+                        tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb | (uint32_t)k) != 0);
+                    tc_commit(&empty[st]);            // stage reusable once these MMAs have read it
+                }
+                tc_commit(&tfull[buf]);               // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue =====
+        const int ew = warp - 2;
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int g = ew >> 2;                        // column group: 64 accumulator columns = 32 B-SNPs
+        const int a_loc = 16 * q + (lane >> 1);       // A-SNP of this lane inside the tile
+        const int pl = lane & 1;                      // plane held by this lane's TMEM row (0: aa, 1: bb)
+        uint64_t tile_it = 0;
+        for (uint64_t t = first; t < last; t += stride, ++tile_it) {
+            uint32_t I, J;
+            mma_tile_from_index(t, p, I, J);
+            const uint32_t buf = (uint32_t)(tile_it & 1);
+            const uint64_t gi = (uint64_t)I * MMA_A_SNPS + a_loc;
+            // row-role record of this lane's A-SNP
+            float pca[2][3]; uint32_t ca[2][3]; float Crow;
+            {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(p.row + gi);
+                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
+                pca[0][0] = __uint_as_float(r0.x); pca[0][1] = __uint_as_float(r0.y); pca[0][2] = __uint_as_float(r0.z);
+                pca[1][0] = __uint_as_float(r0.w); pca[1][1] = __uint_as_float(r1.x); pca[1][2] = __uint_as_float(r1.y);
+                ca[0][0] = r1.z & 0xffffu; ca[0][1] = r1.z >> 16; ca[0][2] = r1.w & 0xffffu;
+                ca[1][0] = r1.w >> 16; ca[1][1] = r2.x & 0xffffu; ca[1][2] = r2.x >> 16;
+                Crow = __uint_as_float(r2.y);
+            }
+            const bool a_ok = !p.tile_missing[I];
+            mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 64 * g + 32 * h, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    // columns 4s..4s+3 = B-SNPs b0 = 2s (planes aa, bb) and b1 = 2s+1 of this 16-SNP group.
+                    // Even lanes (plane aa of A) finish pair (a, b0), odd lanes (plane bb of A) pair (a, b1).
+                    const uint32_t keep0 = pl ? v[4 * s + 2] : v[4 * s + 0], keep1 = pl ? v[4 * s + 3] : v[4 * s + 1];
+                    const uint32_t send0 = pl ? v[4 * s + 0] : v[4 * s + 2], send1 = pl ? v[4 * s + 1] : v[4 * s + 3];
+                    const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1), got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
+                    // d[0..3] = D(AA,BB), D(AA,bb), D(aa,BB), D(aa,bb); here A's plane 0 is "AA", plane 1 "aa"
+                    const uint32_t d0 = pl ? got0 : keep0, d1 = pl ? got1 : keep1, d2 = pl ? keep0 : got0, d3 = pl ? keep1 : got1;
+                    const int b_loc = 32 * g + 16 * h + 2 * s + pl;
+                    const uint64_t gj = (uint64_t)J * MMA_B_SNPS + b_loc;
+                    if (p.dump) {
+                        uint32_t *o = p.dump + ((uint64_t)a_loc * MMA_B_SNPS + b_loc) * 8;
+                        o[0] = d0 & 0x3fffu; o[1] = d1 & 0x3fffu; o[2] = d2 & 0x3fffu; o[3] = d3 & 0x3fffu;
+                        o[4] = d0 >> CTRL_SHIFT; o[5] = d1 >> CTRL_SHIFT; o[6] = d2 >> CTRL_SHIFT; o[7] = d3 >> CTRL_SHIFT;
+                        continue;
+                    }
+                    if (!(gi < gj && gj < p.M && a_ok)) continue;
+                    if (p.tile_missing[gj >> 6]) continue;
+                    uint32_t c[2][4];
+                    c[0][0] = d0 & 0x3fffu; c[0][1] = d1 & 0x3fffu; c[0][2] = d2 & 0x3fffu; c[0][3] = d3 & 0x3fffu;
+                    c[1][0] = d0 >> CTRL_SHIFT; c[1][1] = d1 >> CTRL_SHIFT; c[1][2] = d2 >> CTRL_SHIFT; c[1][3] = d3 >> CTRL_SHIFT;
+                    float w[2][3]; uint32_t cb[2][3]; float Ccol;
+                    {
+                        const uint4 *cp = reinterpret_cast<const uint4 *>(p.col + gj);
+                        const uint4 r0 = __ldg(cp), r1 = __ldg(cp + 1), r2 = __ldg(cp + 2);
+                        w[0][0] = __uint_as_float(r0.x); w[0][1] = __uint_as_float(r0.y); w[0][2] = __uint_as_float(r0.z);
+                        w[1][0] = __uint_as_float(r0.w); w[1][1] = __uint_as_float(r1.x); w[1][2] = __uint_as_float(r1.y);
+                        cb[0][0] = r1.z & 0xffffu; cb[0][1] = r1.z >> 16; cb[0][2] = r1.w & 0xffffu;
+                        cb[1][0] = r1.w >> 16; cb[1][1] = r2.x & 0xffffu; cb[1][2] = r2.x >> 16;
+                        Ccol = __uint_as_float(r2.y);
+                    }
+                    const float stat = ksa_screen_corners(c, pca, ca, w, cb, Crow + Ccol, p.N);
+                    if (stat > p.thr) {
+                        const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
+                        if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- operand matrix: scan layout -> signed one-hot bytes ---------------------------------------------
+// One thread per (SNP, 32-sample word): 32 bytes of plane aa and 32 bytes of plane bb.
+__device__ __forceinline__ uint32_t spread4(uint32_t nibble) { return (nibble * 0x00204081u) & 0x01010101u; }   // bit i -> byte i
+
+__global__ void expand_mma_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Kc, uint32_t Kt,
+                                  uint32_t case_bytes, uint32_t kbytes, uint64_t M, int8_t *__restrict__ mm) {
+    const uint32_t K = Kc + Kt;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t snp = idx / K;
+    if (snp >= M) return;
+    const uint32_t k = (uint32_t)(idx - snp * K);
+    const uint32_t *row = sel + snp * (uint64_t)sel_stride;
+    uint32_t p1, p2, off, shift;
+    if (k < Kc) { p1 = row[sel_word(0, 0, k)]; p2 = row[sel_word(0, 1, k)]; off = 32 * k; shift = 0; }
+    else { p1 = row[sel_word(2 * Wc, 0, k - Kc)]; p2 = row[sel_word(2 * Wc, 1, k - Kc)]; off = case_bytes + 32 * (k - Kc); shift = 7; }
+    const uint32_t bb = p1 & p2, aa = p1 ^ bb;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+        const uint32_t x = pl ? bb : aa;
+        uint4 *dst = reinterpret_cast<uint4 *>(mm + (2 * snp + pl) * (uint64_t)kbytes + off);
+        uint4 lo, hi;
+        lo.x = spread4(x & 15u) << shift;         lo.y = spread4((x >> 4) & 15u) << shift;
+        lo.z = spread4((x >> 8) & 15u) << shift;  lo.w = spread4((x >> 12) & 15u) << shift;
+        hi.x = spread4((x >> 16) & 15u) << shift; hi.y = spread4((x >> 20) & 15u) << shift;
+        hi.z = spread4((x >> 24) & 15u) << shift; hi.w = spread4((x >> 28) & 15u) << shift;
+        dst[0] = lo; dst[1] = hi;
+    }
+}
+
+__global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__ mi, uint64_t M, uint64_t Mrec, uint32_t n_ind,
+                                MmaRow *__restrict__ row, MmaCol *__restrict__ col) {
+    const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (snp >= Mrec) return;
+    MmaRow r; MmaCol c;
+    r.pad[0] = r.pad[1] = c.pad[0] = c.pad[1] = 0;
+    const float qnan = __int_as_float(0x7fc00000);
+    if (snp < M) {
+        const gwasdev_marginal_information m = mi[snp];
+        double Cr = (double)n_ind * log2((double)n_ind), Cc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t *cnt = k ? m.controls : m.cases;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const double pca = m.dPca[4 * k + g], pbc = m.dPbc[4 * k + g], mar = (double)m.margins[g];
+                r.pca[k][g] = (float)pca;
+                c.w[k][g] = m.margins[g] > 0 ? (float)(pbc / mar) : qnan;
+                r.cnt[k][g] = c.cnt[k][g] = (uint16_t)cnt[g];
+                if (cnt[g] > 0) { Cr += (double)cnt[g] * log2(pca); Cc += (double)cnt[g] * (log2(pbc) - log2(mar)); }
+            }
+        }
+        r.C = (float)Cr; c.C = (float)Cc;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) { r.pca[k][g] = 0.f; c.w[k][g] = qnan; r.cnt[k][g] = c.cnt[k][g] = 0; }
+        r.C = c.C = 0.f;
+    }
+    row[snp] = r; col[snp] = c;
+}
+
+// fp32 value of the tensor-core engine's epilogue for given pairs (diagnostic twin of screen_probe_kernel)
+__global__ void screen_probe_mma_kernel(const uint32_t *__restrict__ sel, uint32_t stride, uint32_t Wc, uint32_t Wt,
+                                        const MmaRow *__restrict__ row, const MmaCol *__restrict__ col,
+                                        const uint32_t *__restrict__ pi, const uint32_t *__restrict__ pj, uint64_t n, float N,
+                                        float *__restrict__ out) {
+    const uint64_t qi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n) return;
+    const uint32_t i = pi[qi], j = pj[qi];
+    const uint32_t *ri = sel + i * (uint64_t)stride, *rj = sel + j * (uint64_t)stride;
+    uint32_t c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int k = 0; k < 2; ++k) {
+        const uint32_t W = k ? Wt : Wc, off = k ? 2 * Wc : 0;
+        for (uint32_t wq = 0; wq < W; ++wq) {
+            const uint32_t x = sel_word(off, 0, wq), y = sel_word(off, 1, wq);
+            const uint32_t a1 = ri[x], a2 = ri[y], b1 = rj[x], b2 = rj[y];
+            const uint32_t abb = a1 & a2, aaa = a1 ^ abb, bbb = b1 & b2, baa = b1 ^ bbb;
+            c[k][0] += __popc(aaa & baa); c[k][1] += __popc(aaa & bbb); c[k][2] += __popc(abb & baa); c[k][3] += __popc(abb & bbb);
+        }
+    }
+    const MmaRow A = row[i]; const MmaCol B = col[j];
+    float pca[2][3], w[2][3]; uint32_t ca[2][3], cb[2][3];
+    for (int k = 0; k < 2; ++k)
+        for (int gq = 0; gq < 3; ++gq) { pca[k][gq] = A.pca[k][gq]; w[k][gq] = B.w[k][gq]; ca[k][gq] = A.cnt[k][gq]; cb[k][gq] = B.cnt[k][gq]; }
+    out[qi] = ksa_screen_corners(c, pca, ca, w, cb, A.C + B.C, N);
+}
+
+}  // namespace gwasdev
+
+using namespace gwasdev;
+
+// ---- host side --------------------------------------------------------------------------------------
+bool gwasdev_internal_mma_eligible(const gwasdev_store *s) {
+    return s->n_case >= 1 && s->n_ctrl >= 1 && s->n_case < (1u << CTRL_SHIFT) && s->n_ctrl < (1u << (31 - CTRL_SHIFT));
+}
+
+static int make_mm_map(gwasdev_store *s, uint32_t box_rows, CUtensorMap *out) {
+    encode_tiled_fn encode = nullptr;
+    { int rc = get_encode_tiled(&encode); if (rc != GWASDEV_OK) return rc; }
+    cuuint64_t gdim[2] = {s->mm_kbytes, s->mm_rows};
+    cuuint64_t gstride[1] = {s->mm_kbytes};
+    cuuint32_t box[2] = {(cuuint32_t)MMA_KB, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s->d_mm, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (tensor-core operand matrix) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
+    return GWASDEV_OK;
+}
+
+// operand matrix + tensor maps + per-SNP epilogue records + band table; margins must be valid
+static int ensure_mma_inputs(gwasdev_store *s) {
+    const uint64_t Msnp = (s->M + MMA_B_SNPS - 1) / MMA_B_SNPS * MMA_B_SNPS;
+    if (!s->mm_built) {
+        const uint32_t case_bytes = round_up(s->n_case, MMA_KB), ctrl_bytes = round_up(s->n_ctrl, MMA_KB);
+        s->mm_kbytes = case_bytes + ctrl_bytes;
+        s->mm_rows = 2 * Msnp;
+        const size_t bytes = (size_t)s->mm_rows * s->mm_kbytes;
+        GW_CUDA(reserve_raw(s->d_mm, s->cap_mm, bytes));
+        GW_CUDA(cudaMemsetAsync(s->d_mm, 0, bytes, s->stream));
+        const uint32_t K = s->Kc + s->Kt;
+        const uint64_t work = s->M * K;
+        expand_mma_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt,
+                                                                                 case_bytes, s->mm_kbytes, s->M, s->d_mm);
+        GW_LAUNCHED();
+        if (!s->tmap_mm && posix_memalign(&s->tmap_mm, 64, 2 * sizeof(CUtensorMap)) != 0) { s->tmap_mm = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
+        int rc;
+        if ((rc = make_mm_map(s, MMA_M, (CUtensorMap *)s->tmap_mm)) != GWASDEV_OK) return rc;
+        if ((rc = make_mm_map(s, MMA_N, (CUtensorMap *)s->tmap_mm + 1)) != GWASDEV_OK) return rc;
+        // band table
+        const uint32_t TA = (uint32_t)((s->M + MMA_A_SNPS - 1) / MMA_A_SNPS), TB = (uint32_t)(Msnp / MMA_B_SNPS);
+        const uint32_t n_bands = (TA + BAND - 1) / BAND;
+        std::vector<uint64_t> off(n_bands + 1, 0);
+        for (uint32_t b = 0; b < n_bands; ++b) {
+            const uint32_t na = band_height(TA, b);
+            uint64_t tiles = 0;
+            for (uint32_t J = (BAND / 2) * b; J < TB; ++J) tiles += column_height(na, J - (BAND / 2) * b);
+            off[b + 1] = off[b] + tiles;
+        }
+        GW_CUDA(reserve_raw(s->d_band_off, s->cap_band, off.size() * sizeof(uint64_t)));
+        GW_CUDA(cudaMemcpyAsync(s->d_band_off, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+        GW_CUDA(cudaStreamSynchronize(s->stream));   // `off` is a stack-owned source
+        s->mm_tiles = off[n_bands];
+        s->mm_built = true;
+    }
+    if (!s->mma_side_valid) {
+        MmaRow *row = (MmaRow *)s->d_mma_row; MmaCol *col = (MmaCol *)s->d_mma_col;
+        GW_CUDA(reserve_raw(row, s->cap_mma_row, Msnp * sizeof(MmaRow)));
+        GW_CUDA(reserve_raw(col, s->cap_mma_col, Msnp * sizeof(MmaCol)));
+        s->d_mma_row = row; s->d_mma_col = col;
+        mma_side_kernel<<<(unsigned)((Msnp + 127) / 128), 128, 0, s->stream>>>(s->d_mi, s->M, Msnp, s->n_case + s->n_ctrl, row, col);
+        GW_LAUNCHED();
+        s->mma_side_valid = true;
+    }
+    return GWASDEV_OK;
+}
+
+static uint64_t rect_pairs(uint64_t M, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1) {   // pairs i<j, i in [i0,i1), j in [j0,j1), < M
+    i1 = std::min(i1, M); j1 = std::min(j1, M);
+    uint64_t n = 0;
+    for (uint64_t i = i0; i < i1; ++i) { const uint64_t lo = std::max(j0, i + 1); if (j1 > lo) n += j1 - lo; }
+    return n;
+}
+
+// Pairs the tensor-core engine covers for this shard: pairs i<j of the tiles t with t % n_shards == shard whose
+// two 64-SNP blocks are free of missing calls (flags == nullptr: no block has any).
+uint64_t gwasdev_internal_mma_shard_pairs(const gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags,
+                                          uint64_t *tiles_out) {
+    const uint64_t M = s->M;
+    const uint64_t Msnp = (M + MMA_B_SNPS - 1) / MMA_B_SNPS * MMA_B_SNPS;
+    const uint32_t TA = (uint32_t)((M + MMA_A_SNPS - 1) / MMA_A_SNPS), TB = (uint32_t)(Msnp / MMA_B_SNPS);
+    const uint32_t n_bands = (TA + BAND - 1) / BAND;
+    uint64_t pairs = 0, tiles = 0, t = 0;
+    for (uint32_t b = 0; b < n_bands; ++b) {
+        const uint32_t na = band_height(TA, b);
+        for (uint32_t J = (BAND / 2) * b; J < TB; ++J) {
+            const uint32_t h = column_height(na, J - (BAND / 2) * b);
+            const uint64_t j0 = (uint64_t)J * MMA_B_SNPS, j1 = std::min<uint64_t>(j0 + MMA_B_SNPS, M);
+            // tiles t .. t+h-1 are A-blocks I = 16b + ii of this column; those of the shard: (t + ii) % n_shards == shard
+            const bool simple = !flags && (uint64_t)(BAND * b + h) * MMA_A_SNPS <= j0 && (uint64_t)(BAND * b + h) * MMA_A_SNPS <= M;
+            uint32_t ii = (uint32_t)((shard + n_shards - t % n_shards) % n_shards);
+            if (simple) {          // every tile of the column is a full rectangle left of the B-block
+                if (ii < h) { const uint64_t cnt = (h - 1 - ii) / n_shards + 1; tiles += cnt; pairs += cnt * MMA_A_SNPS * (j1 - j0); }
+            } else {
+                for (; ii < h; ii += n_shards) {
+                    const uint32_t I = BAND * b + ii;
+                    ++tiles;
+                    if (!flags) pairs += rect_pairs(M, (uint64_t)I * MMA_A_SNPS, (uint64_t)(I + 1) * MMA_A_SNPS, j0, j0 + MMA_B_SNPS);
+                    else if (!flags[I])
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const uint64_t jb = 2ull * J + sub;
+                            if (jb * TILE < M && !flags[jb]) pairs += rect_pairs(M, (uint64_t)I * MMA_A_SNPS, (uint64_t)(I + 1) * MMA_A_SNPS, jb * TILE, (jb + 1) * TILE);
+                        }
+                }
+            }
+            t += h;
+        }
+    }
+    if (tiles_out) *tiles_out = tiles;
+    return pairs;
+}
+
+static size_t mma_smem_bytes() { return 1024 + (size_t)MMA_STAGES * STAGE_BYTES_MMA + (2 * MMA_STAGES + 4) * sizeof(uint64_t) + 16; }
+
+static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
+    int sms = 0;
+    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const size_t smem = mma_smem_bytes();
+    GW_CUDA(cudaFuncSetAttribute(pair_screen_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms, my_tiles));
+    const CUtensorMap *maps = (const CUtensorMap *)s->tmap_mm;
+    pair_screen_mma_kernel<<<grid, MMA_THREADS, smem, s->stream>>>(maps[0], maps[1], p);
+    GW_LAUNCHED();
+    return GWASDEV_OK;
+}
+
+static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t n_shards) {
+    const uint64_t Msnp = (s->M + MMA_B_SNPS - 1) / MMA_B_SNPS * MMA_B_SNPS;
+    p.TA = (uint32_t)((s->M + MMA_A_SNPS - 1) / MMA_A_SNPS); p.TB = (uint32_t)(Msnp / MMA_B_SNPS);
+    p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TA + BAND - 1) / BAND; p.M = s->M;
+    p.shard = shard; p.n_shards = n_shards; p.band_off = s->d_band_off;
+    p.row = (const MmaRow *)s->d_mma_row; p.col = (const MmaCol *)s->d_mma_col; p.tile_missing = s->d_tile_missing;
+    p.N = (float)(s->n_case + s->n_ctrl);
+    p.dump = nullptr; p.dump_tile = 0;
+}
+
+// Launches the tensor-core screen for this shard's clean tiles. thr already carries the fp32 margin.
+int gwasdev_internal_screen_mma(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, void *cand,
+                                unsigned long long *n_cand, uint64_t cap) {
+    int rc = ensure_mma_inputs(s);
+    if (rc != GWASDEV_OK) return rc;
+    MmaParams p;
+    fill_params(s, p, shard, n_shards);
+    const uint64_t n_tiles = s->mm_tiles;
+    p.n_tiles = n_tiles;
+    p.thr = thr; p.cand = (Candidate *)cand; p.n_cand = n_cand; p.cap = cap;
+    const uint64_t my_tiles = n_tiles > shard ? (n_tiles - shard + n_shards - 1) / n_shards : 0;
+    if (my_tiles == 0) return GWASDEV_OK;
+    return launch_mma(s, p, my_tiles);
+}
+
+extern "C" {
+
+int gwasdev_set_pair_engine(gwasdev_store *s, int engine) {
+    GW_REQUIRE(s != nullptr, "gwasdev_set_pair_engine: NULL store");
+    GW_REQUIRE(engine >= 0 && engine <= 2, "gwasdev_set_pair_engine: engine %d (0 auto, 1 popcount, 2 tensor core)", engine);
+    s->pair_engine = engine;
+    return GWASDEV_OK;
+}
+
+// Debug / parity probe: the raw corner counts the tensor-core engine accumulates for one tile pair
+// (A-block I of 64 SNPs, B-block J of 128 SNPs): out[(a*128 + b)*8 + {0..3}] = case AA_BB, AA_bb, aa_BB, aa_bb,
+// +4.. the same for controls.
+int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *out) {
+    GW_REQUIRE(s && out, "gwasdev_mma_tile_counts: NULL argument");
+    GW_REQUIRE(s->selected, "gwasdev_mma_tile_counts: call gwasdev_select_case_control first");
+    GW_REQUIRE(gwasdev_internal_mma_eligible(s), "gwasdev_mma_tile_counts: class sizes outside the tensor-core engine's range");
+    GW_CUDA(cudaSetDevice(s->device));
+    int rc = gwasdev_internal_ensure_side(s);
+    if (rc != GWASDEV_OK) return rc;
+    if ((rc = ensure_mma_inputs(s)) != GWASDEV_OK) return rc;
+    MmaParams p;
+    fill_params(s, p, 0, 1);
+    GW_REQUIRE(I < p.TA && J < p.TB && I <= 2 * J + 1, "gwasdev_mma_tile_counts: tile (%u, %u) is not in the schedule", I, J);
+    // linear index of (I, J)
+    std::vector<uint64_t> off(p.n_bands + 1);
+    GW_CUDA(cudaMemcpyAsync(off.data(), s->d_band_off, off.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    GW_CUDA(cudaStreamSynchronize(s->stream));
+    const uint32_t b = I / BAND, na = band_height(p.TA, b);
+    uint64_t t = off[b];
+    for (uint32_t c = 0; c < J - (BAND / 2) * b; ++c) t += column_height(na, c);
+    t += I - BAND * b;
+    p.n_tiles = off[p.n_bands];
+    const size_t bytes = (size_t)MMA_A_SNPS * MMA_B_SNPS * 8 * sizeof(uint32_t);
+    GW_CUDA(reserve(s->sc_a, bytes));
+    GW_CUDA(cudaMemsetAsync(s->sc_a.p, 0xff, bytes, s->stream));
+    p.dump = (uint32_t *)s->sc_a.p; p.dump_tile = t;
+    p.thr = 0.f; p.cand = nullptr; p.n_cand = nullptr; p.cap = 0;
+    if ((rc = launch_mma(s, p, 1)) != GWASDEV_OK) return rc;
+    GW_CUDA(cudaMemcpyAsync(out, s->sc_a.p, bytes, cudaMemcpyDeviceToHost, s->stream));
+    GW_CUDA(cudaStreamSynchronize(s->stream));
+    return GWASDEV_OK;
+}
+
+int gwasdev_ksa_screen_mma_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, float *stat) {
+    GW_REQUIRE(s && pi && pj && stat, "gwasdev_ksa_screen_mma_f32: NULL argument");
+    GW_REQUIRE(s->selected, "gwasdev_ksa_screen_mma_f32: call gwasdev_select_case_control first");
+    GW_REQUIRE(gwasdev_internal_mma_eligible(s), "gwasdev_ksa_screen_mma_f32: class sizes outside the tensor-core engine's range");
+    for (uint64_t q = 0; q < n; ++q) GW_REQUIRE(pi[q] < s->M && pj[q] < s->M, "gwasdev_ksa_screen_mma_f32: pair outside the table");
+    if (n == 0) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    int rc = gwasdev_internal_ensure_side(s);
+    if (rc != GWASDEV_OK) return rc;
+    if ((rc = ensure_mma_inputs(s)) != GWASDEV_OK) return rc;
+    GW_CUDA(reserve(s->sc_pi, n * 4)); GW_CUDA(reserve(s->sc_pj, n * 4)); GW_CUDA(reserve(s->sc_a, n * 4));
+    GW_CUDA(cudaMemcpyAsync(s->sc_pi.p, pi, n * 4, cudaMemcpyHostToDevice, s->stream));
+    GW_CUDA(cudaMemcpyAsync(s->sc_pj.p, pj, n * 4, cudaMemcpyHostToDevice, s->stream));
+    screen_probe_mma_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
+        s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, (const MmaRow *)s->d_mma_row, (const MmaCol *)s->d_mma_col,
+        (const uint32_t *)s->sc_pi.p, (const uint32_t *)s->sc_pj.p, n, (float)(s->n_case + s->n_ctrl), (float *)s->sc_a.p);
+    GW_LAUNCHED();
+    GW_CUDA(cudaMemcpyAsync(stat, s->sc_a.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    GW_CUDA(cudaStreamSynchronize(s->stream));
+    return GWASDEV_OK;
+}
+
+}  // extern "C"

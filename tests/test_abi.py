@@ -39,7 +39,7 @@ def test_struct_layouts_match_the_reference_pods():
     assert gw.MI_DTYPE.itemsize == 192
     assert gw.MI_DTYPE.fields["dMarginalEntropy"][1] == 48 and gw.MI_DTYPE.fields["dPca"][1] == 128
     assert gw.HIT_DTYPE.itemsize == 16 and gw.STATS_DTYPE.itemsize == 64
-    assert C.sizeof(gw.PairStats) == 56
+    assert C.sizeof(gw.PairStats) == 64
 
 
 def test_geometry_matches_reference(lib, orc):
