@@ -167,7 +167,9 @@ GWASDEV_API int gwasdev_set_pair_engine(gwasdev_store *s, int engine);
  * SNPs, B-block J of 128 SNPs, I <= 2J+1): out[(a*128 + b)*8 + {0,1,2,3}] = cases AA_BB, AA_bb, aa_BB, aa_bb
  * (compressed_genotype_table5.cpp:1069-1083), +4: controls (:1118-1132). out holds 64*128*8 values. */
 GWASDEV_API int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *out);
-/* Diagnostic twin of gwasdev_ksa_screen_f32 for the tensor-core engine's epilogue. */
+/* Diagnostic twin of gwasdev_ksa_screen_f32 for the tensor-core engine's epilogue: stat[2k] = its fp32 value of
+ * the statistic, stat[2k+1] = its cheap upper bound (pairs whose bound is below threshold - margin are dropped
+ * without evaluating the logarithms; the bound must never fall below the statistic). */
 GWASDEV_API int gwasdev_ksa_screen_mma_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, float *stat);
 /* KSA statistic in fp64 for given pairs (the re-scoring kernel on its own; parity probe). */
 GWASDEV_API int gwasdev_ksa(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, double *stat);

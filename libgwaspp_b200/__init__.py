@@ -307,8 +307,9 @@ class GenoStore:
         return out
 
     def ksa_screen_mma_f32(self, pi, pj) -> np.ndarray:
+        """[n, 2]: fp32 statistic of the tensor-core epilogue and its upper-bound pre-filter value."""
         pi, pj = self._pairs(pi, pj)
-        out = np.zeros(len(pi), np.float32)
+        out = np.zeros((len(pi), 2), np.float32)
         _check(self.L.gwasdev_ksa_screen_mma_f32(self.h, len(pi), _ptr(pi), _ptr(pj), _ptr(out)), "gwasdev_ksa_screen_mma_f32")
         return out
 

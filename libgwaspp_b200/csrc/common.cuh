@@ -163,6 +163,7 @@ struct gwasdev_store {
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
     uint64_t *d_band_off = nullptr;
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
+    float mma_qc = 0.f, mma_q0 = 0.f;   // constants of the upper-bound pre-filter (pairwise_mma.cu)
     std::vector<uint8_t> h_tile_missing;   // host copy of d_tile_missing (valid with side_valid)
     size_t cap_mm = 0, cap_mma_row = 0, cap_mma_col = 0, cap_band = 0;
     bool mma_side_valid = false;

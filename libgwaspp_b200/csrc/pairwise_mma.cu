@@ -47,11 +47,13 @@ constexpr int BAND = 16;                                           // A-blocks p
 constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
 constexpr uint32_t CTRL_SHIFT = 14;                                // (-128)^2 = 2^14
 
-// per-SNP epilogue records, log2 units. Row role (SNP "A" of the pair) / column role (SNP "B").
+// per-SNP epilogue records, log2 units, class-interleaved so that (case, control) pairs are float2 operands of
+// the packed fp32 instructions. Row role (SNP "A" of the pair) / column role (SNP "B"), g = aa, ab, bb:
+//   pca[g] = (c_0[g], c_1[g]) / m[g]           w[g] = (c_0[g]/n_0, c_1[g]/n_1) / m[g]  (NaN when m[g] == 0)
 //   C_row = sum_kg c_k[g] log2 pca_k[g] + N log2 N          C_col = sum_kg c_k[g] (log2 pbc_k[g] - log2 m[g])
-struct __align__(16) MmaRow { float pca[2][3]; uint16_t cnt[2][3]; float C; uint32_t pad[2]; };
-struct __align__(16) MmaCol { float w[2][3];   uint16_t cnt[2][3]; float C; uint32_t pad[2]; };
-static_assert(sizeof(MmaRow) == 48 && sizeof(MmaCol) == 48, "48-byte epilogue records");
+struct __align__(16) MmaRow { float2 pca[3]; float2 cnt[3]; float C; float pad[3]; };
+struct __align__(16) MmaCol { float2 w[3];   float2 cnt[3]; float C; float pad[3]; };
+static_assert(sizeof(MmaRow) == 64 && sizeof(MmaCol) == 64, "64-byte epilogue records");
 
 struct MmaParams {
     uint32_t TA, TB;            // A blocks (64 SNPs), B blocks (128 SNPs)
@@ -65,6 +67,7 @@ struct MmaParams {
     const MmaCol *col;
     const uint8_t *tile_missing;   // per 64-SNP block
     float thr, N;
+    float qc, q0;               // upper-bound pre-filter: S <= qc * sum_ab c0^2/cab - q0 (see ksa_upper_bound)
     Candidate *cand;
     unsigned long long *n_cand;
     uint64_t cap;
@@ -152,35 +155,81 @@ __device__ __forceinline__ void mma_tile_from_index(uint64_t t, const MmaParams 
 
 // ---- fp32 KSA on the four counted corners -----------------------------------------------------------
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float g2(float n) { return n * lg2_approx(fmaxf(n, 1.0f)); }
 
-// c[k] = {AA_BB, AA_bb, aa_BB, aa_bb} of class k. Returns 2 ln2 (sum g2(n_abk) - sum g2(n_ab.) + N log2 tau - C_row - C_col),
-// which equals ksa_screen_f32 of pairwise.cu when neither SNP has a missing call (row/column sums of the
-// table are then the per-SNP class counts).
-__device__ __forceinline__ float ksa_screen_corners(const uint32_t (&c)[2][4], const float (&pca)[2][3], const uint32_t (&ca)[2][3],
-                                                    const float (&w)[2][3], const uint32_t (&cb)[2][3], float Csum, float N) {
-    uint32_t n[2][3][3];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const uint32_t AB = c[k][0], Ab = c[k][1], aB = c[k][2], ab = c[k][3];
-        n[k][0][0] = AB; n[k][0][2] = Ab; n[k][2][0] = aB; n[k][2][2] = ab;
-        n[k][0][1] = ca[k][0] - AB - Ab;
-        n[k][2][1] = ca[k][2] - ab - aB;
-        n[k][1][0] = cb[k][0] - AB - aB;
-        n[k][1][2] = cb[k][2] - Ab - ab;
-        n[k][1][1] = cb[k][1] - n[k][0][1] - n[k][2][1];
-    }
-    float S = 0.f, tau = 0.f;
+// The nine cells of both classes as float2 (x: cases, y: controls) from the four counted corners and the
+// per-SNP class counts -- the reference's shortcut (compressed_genotype_table5.cpp:1084-1092, :1133-1141).
+struct Cells { float2 n[3][3]; };
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ Cells derive_cells(float2 AB, float2 Ab, float2 aB, float2 ab, const float2 (&ca)[3], const float2 (&cb)[3]) {
+    Cells t;
+    t.n[0][0] = AB; t.n[0][2] = Ab; t.n[2][0] = aB; t.n[2][2] = ab;
+    t.n[0][1] = sub2(sub2(ca[0], AB), Ab);
+    t.n[2][1] = sub2(sub2(ca[2], ab), aB);
+    t.n[1][0] = sub2(sub2(cb[0], AB), aB);
+    t.n[1][2] = sub2(sub2(cb[2], Ab), ab);
+    t.n[1][1] = sub2(sub2(cb[1], t.n[0][1]), t.n[2][1]);
+    return t;
+}
+
+// Cheap rigorous upper bound of the screen statistic. With x = c0/cab, the cell term g2(c0)+g2(c1)-g2(cab) is
+// -cab H2(x) (binary entropy, bits), and H2(x) >= H2(x0) + H2'(x0)(x-x0) - qc (x-x0)^2 on [0,1] for the
+// cohort's case fraction x0 = n_case/N and the constant qc found on the host. Summed over the table (whose
+// cells add up to N samples and n_case cases when no call is missing) the linear part is constant:
+//     S <= qc * sum_ab c0^2/cab - q0,      q0 = qc x0 n_case + N H2(x0)
+// so stat <= 2 ln2 (N log2 tau + qc Q - q0 - C): nine reciprocals and one logarithm instead of 28 logarithms.
+// tau is accumulated on the way and returned for the exact evaluation.
+__device__ __forceinline__ float ksa_upper_bound(const Cells &t, const float2 (&pca)[3], const float2 (&w)[3], float Csum,
+                                                 float N, float qc, float q0, float &tau_out) {
+    float tau = 0.f, Q = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
-            const float c0 = u2f(n[0][a][b]), c1 = u2f(n[1][a][b]), cab = c0 + c1;
-            const float W = fmaf(w[0][b], pca[0][a], w[1][b] * pca[1][a]);
-            tau = fmaf(cab, W, tau);
-            S += g2(c0) + g2(c1) - g2(cab);
+            const float2 n = t.n[a][b];
+            const float cab = n.x + n.y;
+            const float2 wp = __fmul2_rn(w[b], pca[a]);
+            tau = fmaf(cab, wp.x + wp.y, tau);
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(cab + 1.17549435e-38f));
+            Q = fmaf(n.x, n.x * r, Q);
         }
-    return 1.3862943611f * (fmaf(N, lg2_approx(tau), S) - Csum);
+    tau_out = tau;
+    return 1.3862943611f * (fmaf(N, lg2_approx(tau), fmaf(qc, Q, -q0)) - Csum);
+}
+
+// Exact-formula fp32 value: 2 ln2 (sum g2(n_abk) - sum g2(n_ab.) + N log2 tau - C_row - C_col), equal to
+// ksa_screen_f32 of pairwise.cu when neither SNP has a missing call (row/column sums of the table are then the
+// per-SNP class counts). g2(n) = n log2 n with g2(0) = 0: n + 2^-126 == n for n >= 1, and 0 * log2(2^-126) = -0.
+__device__ __forceinline__ float ksa_screen_cells(const Cells &t, float tau, float Csum, float N) {
+    const float2 tiny = make_float2(1.17549435e-38f, 1.17549435e-38f);
+    float2 S2 = make_float2(0.f, 0.f);
+    float S1 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const float2 n = t.n[a][b];
+            const float cab = n.x + n.y;
+            const float2 na = __fadd2_rn(n, tiny);
+            S2 = __ffma2_rn(n, make_float2(lg2_approx(na.x), lg2_approx(na.y)), S2);
+            S1 = fmaf(-cab, lg2_approx(cab + tiny.x), S1);
+        }
+    return 1.3862943611f * (fmaf(N, lg2_approx(tau), S2.x + S2.y + S1) - Csum);
+}
+
+// D = n_case + 2^14 n_ctrl  ->  (n_case, n_ctrl) as floats, through the 2^23 magic number
+__device__ __forceinline__ float2 decode2(uint32_t d) {
+    const float2 m = make_float2(__uint_as_float((d & 0x3fffu) | 0x4B000000u), __uint_as_float((d >> CTRL_SHIFT) | 0x4B000000u));
+    return __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
+}
+
+__device__ __forceinline__ void load_record(const void *rec, float2 (&p)[3], float2 (&c)[3], float &C) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(rec);
+    const uint4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3);
+    p[0] = make_float2(__uint_as_float(r0.x), __uint_as_float(r0.y)); p[1] = make_float2(__uint_as_float(r0.z), __uint_as_float(r0.w));
+    p[2] = make_float2(__uint_as_float(r1.x), __uint_as_float(r1.y)); c[0] = make_float2(__uint_as_float(r1.z), __uint_as_float(r1.w));
+    c[1] = make_float2(__uint_as_float(r2.x), __uint_as_float(r2.y)); c[2] = make_float2(__uint_as_float(r2.z), __uint_as_float(r2.w));
+    C = __uint_as_float(r3.x);
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------
@@ -268,17 +317,15 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             mma_tile_from_index(t, p, I, J);
             const uint32_t buf = (uint32_t)(tile_it & 1);
             const uint64_t gi = (uint64_t)I * MMA_A_SNPS + a_loc;
-            // row-role record of this lane's A-SNP
-            float pca[2][3]; uint32_t ca[2][3]; float Crow;
-            {
-                const uint4 *rp = reinterpret_cast<const uint4 *>(p.row + gi);
-                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2);
-                pca[0][0] = __uint_as_float(r0.x); pca[0][1] = __uint_as_float(r0.y); pca[0][2] = __uint_as_float(r0.z);
-                pca[1][0] = __uint_as_float(r0.w); pca[1][1] = __uint_as_float(r1.x); pca[1][2] = __uint_as_float(r1.y);
-                ca[0][0] = r1.z & 0xffffu; ca[0][1] = r1.z >> 16; ca[0][2] = r1.w & 0xffffu;
-                ca[1][0] = r1.w >> 16; ca[1][1] = r2.x & 0xffffu; ca[1][2] = r2.x >> 16;
-                Crow = __uint_as_float(r2.y);
-            }
+            // row-role record of this lane's A-SNP. Odd lanes own plane "bb" of A: they see the table with A's
+            // genotype labels aa <-> bb exchanged, which the statistic does not depend on, so their record is
+            // loaded with the two swapped instead of re-ordering four counts per pair.
+            float2 pca[3], ca[3]; float Crow;
+            load_record(p.row + gi, pca, ca, Crow);
+            if (pl) { float2 x = pca[0]; pca[0] = pca[2]; pca[2] = x; x = ca[0]; ca[0] = ca[2]; ca[2] = x; }
+            // interior tile: every pair is i < j inside the table and no block has missing calls
+            const bool interior = (uint64_t)(I + 1) * MMA_A_SNPS <= (uint64_t)J * MMA_B_SNPS && (uint64_t)(J + 1) * MMA_B_SNPS <= p.M &&
+                                  !p.tile_missing[I] && !p.tile_missing[2 * J] && !p.tile_missing[2 * J + 1];
             const bool a_ok = !p.tile_missing[I];
             mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
             tc_fence_after();
@@ -294,35 +341,32 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     const uint32_t keep0 = pl ? v[4 * s + 2] : v[4 * s + 0], keep1 = pl ? v[4 * s + 3] : v[4 * s + 1];
                     const uint32_t send0 = pl ? v[4 * s + 0] : v[4 * s + 2], send1 = pl ? v[4 * s + 1] : v[4 * s + 3];
                     const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1), got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-                    // d[0..3] = D(AA,BB), D(AA,bb), D(aa,BB), D(aa,bb); here A's plane 0 is "AA", plane 1 "aa"
-                    const uint32_t d0 = pl ? got0 : keep0, d1 = pl ? got1 : keep1, d2 = pl ? keep0 : got0, d3 = pl ? keep1 : got1;
                     const int b_loc = 32 * g + 16 * h + 2 * s + pl;
                     const uint64_t gj = (uint64_t)J * MMA_B_SNPS + b_loc;
                     if (p.dump) {
+                        const uint32_t d0 = pl ? got0 : keep0, d1 = pl ? got1 : keep1, d2 = pl ? keep0 : got0, d3 = pl ? keep1 : got1;
                         uint32_t *o = p.dump + ((uint64_t)a_loc * MMA_B_SNPS + b_loc) * 8;
                         o[0] = d0 & 0x3fffu; o[1] = d1 & 0x3fffu; o[2] = d2 & 0x3fffu; o[3] = d3 & 0x3fffu;
                         o[4] = d0 >> CTRL_SHIFT; o[5] = d1 >> CTRL_SHIFT; o[6] = d2 >> CTRL_SHIFT; o[7] = d3 >> CTRL_SHIFT;
                         continue;
                     }
-                    if (!(gi < gj && gj < p.M && a_ok)) continue;
-                    if (p.tile_missing[gj >> 6]) continue;
-                    uint32_t c[2][4];
-                    c[0][0] = d0 & 0x3fffu; c[0][1] = d1 & 0x3fffu; c[0][2] = d2 & 0x3fffu; c[0][3] = d3 & 0x3fffu;
-                    c[1][0] = d0 >> CTRL_SHIFT; c[1][1] = d1 >> CTRL_SHIFT; c[1][2] = d2 >> CTRL_SHIFT; c[1][3] = d3 >> CTRL_SHIFT;
-                    float w[2][3]; uint32_t cb[2][3]; float Ccol;
-                    {
-                        const uint4 *cp = reinterpret_cast<const uint4 *>(p.col + gj);
-                        const uint4 r0 = __ldg(cp), r1 = __ldg(cp + 1), r2 = __ldg(cp + 2);
-                        w[0][0] = __uint_as_float(r0.x); w[0][1] = __uint_as_float(r0.y); w[0][2] = __uint_as_float(r0.z);
-                        w[1][0] = __uint_as_float(r0.w); w[1][1] = __uint_as_float(r1.x); w[1][2] = __uint_as_float(r1.y);
-                        cb[0][0] = r1.z & 0xffffu; cb[0][1] = r1.z >> 16; cb[0][2] = r1.w & 0xffffu;
-                        cb[1][0] = r1.w >> 16; cb[1][1] = r2.x & 0xffffu; cb[1][2] = r2.x >> 16;
-                        Ccol = __uint_as_float(r2.y);
-                    }
-                    const float stat = ksa_screen_corners(c, pca, ca, w, cb, Crow + Ccol, p.N);
-                    if (stat > p.thr) {
-                        const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
-                        if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
+                    bool valid = true;
+                    if (!interior) valid = gi < gj && gj < p.M && a_ok && !p.tile_missing[min(gj, p.M - 1) >> 6];
+                    float2 w[3], cb[3]; float Ccol;
+                    load_record(p.col + gj, w, cb, Ccol);
+                    // own plane of A first ("AA" for even lanes, "aa" for odd lanes with the swapped record)
+                    const Cells t = derive_cells(decode2(keep0), decode2(keep1), decode2(got0), decode2(got1), ca, cb);
+                    float tau;
+                    const float ub = ksa_upper_bound(t, pca, w, Crow + Ccol, p.N, p.qc, p.q0, tau);
+                    const bool hot = valid && ub > p.thr;
+                    if (__any_sync(0xffffffffu, hot)) {
+                        if (hot) {
+                            const float stat = ksa_screen_cells(t, tau, Crow + Ccol, p.N);
+                            if (stat > p.thr) {
+                                const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
+                                if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
+                            }
+                        }
                     }
                 }
             }
@@ -374,8 +418,9 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
     const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (snp >= Mrec) return;
     MmaRow r; MmaCol c;
-    r.pad[0] = r.pad[1] = c.pad[0] = c.pad[1] = 0;
+    r.pad[0] = r.pad[1] = r.pad[2] = c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
     const float qnan = __int_as_float(0x7fc00000);
+    float rp[2][3], cw[2][3], cn[2][3];
     if (snp < M) {
         const gwasdev_marginal_information m = mi[snp];
         double Cr = (double)n_ind * log2((double)n_ind), Cc = 0.0;
@@ -385,9 +430,9 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
                 const double pca = m.dPca[4 * k + g], pbc = m.dPbc[4 * k + g], mar = (double)m.margins[g];
-                r.pca[k][g] = (float)pca;
-                c.w[k][g] = m.margins[g] > 0 ? (float)(pbc / mar) : qnan;
-                r.cnt[k][g] = c.cnt[k][g] = (uint16_t)cnt[g];
+                rp[k][g] = (float)pca;
+                cw[k][g] = m.margins[g] > 0 ? (float)(pbc / mar) : qnan;
+                cn[k][g] = (float)cnt[g];
                 if (cnt[g] > 0) { Cr += (double)cnt[g] * log2(pca); Cc += (double)cnt[g] * (log2(pbc) - log2(mar)); }
             }
         }
@@ -396,8 +441,13 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
 #pragma unroll
         for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int g = 0; g < 3; ++g) { r.pca[k][g] = 0.f; c.w[k][g] = qnan; r.cnt[k][g] = c.cnt[k][g] = 0; }
+            for (int g = 0; g < 3; ++g) { rp[k][g] = 0.f; cw[k][g] = qnan; cn[k][g] = 0.f; }
         r.C = c.C = 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        r.pca[g] = make_float2(rp[0][g], rp[1][g]); c.w[g] = make_float2(cw[0][g], cw[1][g]);
+        r.cnt[g] = c.cnt[g] = make_float2(cn[0][g], cn[1][g]);
     }
     row[snp] = r; col[snp] = c;
 }
@@ -406,7 +456,7 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
 __global__ void screen_probe_mma_kernel(const uint32_t *__restrict__ sel, uint32_t stride, uint32_t Wc, uint32_t Wt,
                                         const MmaRow *__restrict__ row, const MmaCol *__restrict__ col,
                                         const uint32_t *__restrict__ pi, const uint32_t *__restrict__ pj, uint64_t n, float N,
-                                        float *__restrict__ out) {
+                                        float qc, float q0, float *__restrict__ out) {
     const uint64_t qi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= n) return;
     const uint32_t i = pi[qi], j = pj[qi];
@@ -421,11 +471,15 @@ __global__ void screen_probe_mma_kernel(const uint32_t *__restrict__ sel, uint32
             c[k][0] += __popc(aaa & baa); c[k][1] += __popc(aaa & bbb); c[k][2] += __popc(abb & baa); c[k][3] += __popc(abb & bbb);
         }
     }
-    const MmaRow A = row[i]; const MmaCol B = col[j];
-    float pca[2][3], w[2][3]; uint32_t ca[2][3], cb[2][3];
-    for (int k = 0; k < 2; ++k)
-        for (int gq = 0; gq < 3; ++gq) { pca[k][gq] = A.pca[k][gq]; w[k][gq] = B.w[k][gq]; ca[k][gq] = A.cnt[k][gq]; cb[k][gq] = B.cnt[k][gq]; }
-    out[qi] = ksa_screen_corners(c, pca, ca, w, cb, A.C + B.C, N);
+    float2 pca[3], ca[3], w[3], cb[3]; float Crow, Ccol;
+    load_record(row + i, pca, ca, Crow);
+    load_record(col + j, w, cb, Ccol);
+    const Cells t = derive_cells(make_float2((float)c[0][0], (float)c[1][0]), make_float2((float)c[0][1], (float)c[1][1]),
+                                 make_float2((float)c[0][2], (float)c[1][2]), make_float2((float)c[0][3], (float)c[1][3]), ca, cb);
+    float tau;
+    const float ub = ksa_upper_bound(t, pca, w, Crow + Ccol, N, qc, q0, tau);
+    out[2 * qi] = ksa_screen_cells(t, tau, Crow + Ccol, N);
+    out[2 * qi + 1] = ub;
 }
 
 }  // namespace gwasdev
@@ -448,6 +502,24 @@ static int make_mm_map(gwasdev_store *s, uint32_t box_rows, CUtensorMap *out) {
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (tensor-core operand matrix) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
     return GWASDEV_OK;
+}
+
+// Constants of ksa_upper_bound for a cohort with n_case cases among n samples: the smallest qc (plus a safety
+// factor) with H2(x) >= H2(x0) + H2'(x0)(x - x0) - qc (x - x0)^2 on [0, 1], and q0 = qc x0 n_case + n H2(x0).
+static void bound_constants(uint32_t n_case, uint32_t n, float *qc_out, float *q0_out) {
+    const double x0 = (double)n_case / (double)n;
+    auto H = [](double x) { return (x <= 0.0 || x >= 1.0) ? 0.0 : -(x * std::log2(x) + (1.0 - x) * std::log2(1.0 - x)); };
+    const double h0 = H(x0), d0 = std::log2((1.0 - x0) / x0);
+    double qc = 1.0 / (2.0 * std::log(2.0) * x0 * (1.0 - x0));          // limit x -> x0: -H2''(x0) / 2
+    const int G = 1 << 18;
+    for (int k = 0; k <= G; ++k) {
+        const double x = (double)k / G, dx = x - x0;
+        if (std::fabs(dx) < 1e-6) continue;
+        qc = std::max(qc, (h0 + d0 * dx - H(x)) / (dx * dx));
+    }
+    qc *= 1.001;
+    *qc_out = (float)qc;
+    *q0_out = (float)(qc * x0 * (double)n_case + (double)n * h0);
 }
 
 // operand matrix + tensor maps + per-SNP epilogue records + band table; margins must be valid
@@ -483,6 +555,7 @@ static int ensure_mma_inputs(gwasdev_store *s) {
         GW_CUDA(cudaMemcpyAsync(s->d_band_off, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
         GW_CUDA(cudaStreamSynchronize(s->stream));   // `off` is a stack-owned source
         s->mm_tiles = off[n_bands];
+        bound_constants(s->n_case, s->n_case + s->n_ctrl, &s->mma_qc, &s->mma_q0);
         s->mm_built = true;
     }
     if (!s->mma_side_valid) {
@@ -563,6 +636,7 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
     p.shard = shard; p.n_shards = n_shards; p.band_off = s->d_band_off;
     p.row = (const MmaRow *)s->d_mma_row; p.col = (const MmaCol *)s->d_mma_col; p.tile_missing = s->d_tile_missing;
     p.N = (float)(s->n_case + s->n_ctrl);
+    p.qc = s->mma_qc; p.q0 = s->mma_q0;
     p.dump = nullptr; p.dump_tile = 0;
 }
 
@@ -634,14 +708,15 @@ int gwasdev_ksa_screen_mma_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi,
     int rc = gwasdev_internal_ensure_side(s);
     if (rc != GWASDEV_OK) return rc;
     if ((rc = ensure_mma_inputs(s)) != GWASDEV_OK) return rc;
-    GW_CUDA(reserve(s->sc_pi, n * 4)); GW_CUDA(reserve(s->sc_pj, n * 4)); GW_CUDA(reserve(s->sc_a, n * 4));
+    GW_CUDA(reserve(s->sc_pi, n * 4)); GW_CUDA(reserve(s->sc_pj, n * 4)); GW_CUDA(reserve(s->sc_a, n * 8));
     GW_CUDA(cudaMemcpyAsync(s->sc_pi.p, pi, n * 4, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->sc_pj.p, pj, n * 4, cudaMemcpyHostToDevice, s->stream));
     screen_probe_mma_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
         s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, (const MmaRow *)s->d_mma_row, (const MmaCol *)s->d_mma_col,
-        (const uint32_t *)s->sc_pi.p, (const uint32_t *)s->sc_pj.p, n, (float)(s->n_case + s->n_ctrl), (float *)s->sc_a.p);
+        (const uint32_t *)s->sc_pi.p, (const uint32_t *)s->sc_pj.p, n, (float)(s->n_case + s->n_ctrl), s->mma_qc, s->mma_q0,
+        (float *)s->sc_a.p);
     GW_LAUNCHED();
-    GW_CUDA(cudaMemcpyAsync(stat, s->sc_a.p, n * 4, cudaMemcpyDeviceToHost, s->stream));
+    GW_CUDA(cudaMemcpyAsync(stat, s->sc_a.p, n * 8, cudaMemcpyDeviceToHost, s->stream));
     GW_CUDA(cudaStreamSynchronize(s->stream));
     return GWASDEV_OK;
 }

@@ -85,10 +85,14 @@ def test_engines_agree_with_each_other_and_the_oracle(orc, seed, M, N, ncase, mi
         # the fp32 epilogue stays inside its safety margin (0.5)
         if miss == 0:
             ii, jj = np.triu_indices(min(M, 200), 1)
-            f32, f64 = st.ksa_screen_mma_f32(ii, jj), st.ksa(ii, jj)
+            both, f64 = st.ksa_screen_mma_f32(ii, jj), st.ksa(ii, jj)
+            f32, ub = both[:, 0], both[:, 1]
             ok = ~np.isnan(f64)
-            assert np.array_equal(np.isnan(f32), np.isnan(f64))
+            assert np.array_equal(np.isnan(f32), np.isnan(f64)) and np.array_equal(np.isnan(ub), np.isnan(f64))
             assert np.max(np.abs(f32[ok] - f64[ok])) < 0.125
+            # the pre-filter is an upper bound of the statistic (up to fp32 rounding, far inside the margin)
+            assert np.min(ub[ok] - f64[ok]) > -0.05
+            assert np.mean(ub[ok] > 29.5) < 0.05            # ... and a useful one
 
 
 def test_engine_selection_errors(orc):
