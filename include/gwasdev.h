@@ -164,7 +164,7 @@ GWASDEV_API int gwasdev_pairwise_scan(gwasdev_store *s, double threshold, uint32
  * kernel (the reference's other branch, compressed_genotype_table5.cpp:1000-1067). Results are identical. */
 GWASDEV_API int gwasdev_set_pair_engine(gwasdev_store *s, int engine);
 /* Parity probe of the tensor-core engine: raw corner counts of one tile pair of its schedule (A-block I of 64
- * SNPs, B-block J of 128 SNPs, I <= 2J+1): out[(a*128 + b)*8 + {0,1,2,3}] = cases AA_BB, AA_bb, aa_BB, aa_bb
+ * SNPs, B-block J of 128 SNPs, I/2 <= J): out[(a*128 + b)*8 + {0,1,2,3}] = cases AA_BB, AA_bb, aa_BB, aa_bb
  * (compressed_genotype_table5.cpp:1069-1083), +4: controls (:1118-1132). out holds 64*128*8 values. */
 GWASDEV_API int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *out);
 /* Diagnostic twin of gwasdev_ksa_screen_f32 for the tensor-core engine's epilogue: stat[2k] = its fp32 value of

@@ -15,14 +15,18 @@
 //     D[2i+p][2j+q] = sum_samples A*B = n_case(p, q) + 16384 * n_ctrl(p, q)
 // exactly in int32 (n_case < 16384, n_ctrl < 131072): one accumulator tile carries both classes.
 //
-// Kernel. One CTA per SM, persistent over tile pairs (64 A-SNPs = 128 rows) x (128 B-SNPs = 256 rows):
-//   warp 0   TMA producer : cp.async.bulk.tensor.2d, SWIZZLE_128B boxes of 128 sample bytes, 4-stage ring
-//   warp 1   MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128 N=256 K=32, 4 per stage, into one of
-//                           two 256-column TMEM accumulators; tcgen05.commit frees the stage / publishes
-//                           the accumulator
-//   warps 2+ epilogue     : tcgen05.ld 32x32b, lane pairs swap the two planes by shuffle, decode the
-//                           counts, margins -> 3x3x2 table, fp32 KSA, candidates above threshold - margin
-// Tile order keeps a band of 16 A-blocks and a sliding window of B-blocks L2-resident.
+// Kernel. Two CTAs on the two SMs of a TPC work as a pair (cluster of 2, tcgen05 cta_group::2), persistent
+// over tile pairs of (128 A-SNPs = 256 rows, 128 per CTA) x (128 B-SNPs = 256 rows, each CTA stages half):
+//   warp 0   TMA producer : cp.async.bulk.tensor.2d.cta_group::2, SWIZZLE_128B boxes of 128 sample bytes, both
+//                           CTAs' loads complete on the leader's mbarrier, 6-stage ring of 32 KiB per CTA
+//   warp 1   MMA issuer   : (leader CTA) tcgen05.mma.cta_group::2.kind::i8, M=256 N=256 K=32, 4 per stage, into
+//                           one of two 256-column TMEM accumulators; tcgen05.commit multicasts "stage free" and
+//                           "accumulator ready" to both CTAs
+//   warps 2+ epilogue     : each CTA reads its 128 accumulator rows (64 A-SNPs) with tcgen05.ld 32x32b, lane
+//                           pairs swap the two planes by shuffle, decode the counts, margins -> 3x3x2 table,
+//                           upper bound of the KSA statistic, exact fp32 KSA for the few that pass it,
+//                           candidates above threshold - margin
+// Tile order keeps a band of 8 A-blocks and a sliding window of B-blocks L2-resident.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -34,18 +38,20 @@ int gwasdev_internal_ensure_side(gwasdev_store *s);   // pairwise.cu: margins, P
 
 namespace gwasdev {
 
-constexpr int MMA_A_SNPS = 64, MMA_B_SNPS = 128;
-constexpr int MMA_M = 2 * MMA_A_SNPS, MMA_N = 2 * MMA_B_SNPS;      // operand rows per tile
+constexpr int MMA_A_SNPS = 64, MMA_B_SNPS = 128;                   // per CTA: A-SNPs whose rows it owns; B-SNPs of the tile
+constexpr int MMA_BLK = 128;                                       // SNPs per schedule block (A-block of the CTA pair = B-block)
+constexpr int MMA_M = 4 * MMA_A_SNPS, MMA_N = 2 * MMA_B_SNPS;      // operand rows of one cta_group::2 instruction
 constexpr int MMA_KB = 128;                                        // sample bytes per stage (one 128B swizzle row)
 constexpr int UMMA_K = 32;                                         // bytes per tcgen05.mma kind::i8
-constexpr int MMA_STAGES = 4;
-constexpr int A_STAGE_BYTES = MMA_M * MMA_KB, B_STAGE_BYTES = MMA_N * MMA_KB;
-constexpr int STAGE_BYTES_MMA = A_STAGE_BYTES + B_STAGE_BYTES;     // 48 KiB
+constexpr int MMA_STAGES = 6;
+constexpr int A_STAGE_BYTES = 2 * MMA_A_SNPS * MMA_KB, B_STAGE_BYTES = MMA_B_SNPS * MMA_KB;   // per CTA: its A rows, its half of B
+constexpr int STAGE_BYTES_MMA = A_STAGE_BYTES + B_STAGE_BYTES;     // 32 KiB per CTA
 constexpr int EPI_WARPS = 16;
 constexpr int MMA_THREADS = (2 + EPI_WARPS) * 32;
-constexpr int BAND = 16;                                           // A-blocks per L2 band
+constexpr int BAND = 8;                                            // A-blocks per L2 band
 constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
 constexpr uint32_t CTRL_SHIFT = 14;                                // (-128)^2 = 2^14
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                        // shared::cluster address of the pair's even CTA
 
 // per-SNP epilogue records, log2 units, class-interleaved so that (case, control) pairs are float2 operands of
 // the packed fp32 instructions. Row role (SNP "A" of the pair) / column role (SNP "B"), g = aa, ab, bb:
@@ -56,7 +62,7 @@ struct __align__(16) MmaCol { float2 w[3];   float2 cnt[3]; float C; float pad[3
 static_assert(sizeof(MmaRow) == 64 && sizeof(MmaCol) == 64, "64-byte epilogue records");
 
 struct MmaParams {
-    uint32_t TA, TB;            // A blocks (64 SNPs), B blocks (128 SNPs)
+    uint32_t TB;                // 128-SNP blocks
     uint32_t NKB;               // 128-byte sample blocks per row
     uint32_t n_bands;
     uint64_t M;
@@ -71,22 +77,44 @@ struct MmaParams {
     Candidate *cand;
     unsigned long long *n_cand;
     uint64_t cap;
-    uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only
+    uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only, rows of CTA `dump_rank`
     uint64_t dump_tile;
+    uint32_t dump_rank;
 };
 
 // ---- PTX: tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// arrive on the barrier at the same offset in the CTAs of cta_mask once all earlier MMAs of this thread are done
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (no transaction bytes) on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// 2-CTA TMA load: data into this CTA's shared memory, completion bytes on the pair leader's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -128,29 +156,29 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return d;
 }
 // instruction descriptor kind::i8: D s32, A and B signed 8-bit, both K-major, N >> 3, M >> 4
-constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);   // M = 256 over the CTA pair
 
 // ---- tile order -------------------------------------------------------------------------------------
-// Band b holds A-blocks [16b, 16b+16); inside a band tiles run column-major over B-blocks J >= 8b, and a
-// column holds the A-blocks I of the band with I <= 2J+1 (a B-block at or right of the A-block).
-__host__ __device__ inline uint32_t band_height(uint32_t TA, uint32_t b) { return min((uint32_t)BAND, TA - BAND * b); }
-__host__ __device__ inline uint32_t column_height(uint32_t na, uint32_t c) { return min(na, 2 * c + 2); }
+// Tiles are pairs of 128-SNP blocks (I2 <= J). Band b holds A-blocks [8b, 8b+8); inside a band tiles run
+// column-major over B-blocks J >= 8b, and column c = J - 8b holds the band's A-blocks I2 <= J.
+__host__ __device__ inline uint32_t band_height(uint32_t TB, uint32_t b) { return min((uint32_t)BAND, TB - BAND * b); }
+__host__ __device__ inline uint32_t column_height(uint32_t na, uint32_t c) { return min(na, c + 1); }
 
-__device__ __forceinline__ void mma_tile_from_index(uint64_t t, const MmaParams &p, uint32_t &I, uint32_t &J) {
+__device__ __forceinline__ void mma_tile_from_index(uint64_t t, const MmaParams &p, uint32_t &I2, uint32_t &J) {
     uint32_t lo = 0, hi = p.n_bands;
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (p.band_off[mid] <= t) lo = mid; else hi = mid; }
     uint64_t r = t - p.band_off[lo];
-    const uint32_t na = band_height(p.TA, lo);
+    const uint32_t na = band_height(p.TB, lo);
     uint32_t c = 0;
     for (;;) {
         const uint32_t h = column_height(na, c);
         if (h == na) break;
-        if (r < h) { I = BAND * lo + (uint32_t)r; J = (BAND / 2) * lo + c; return; }
+        if (r < h) { I2 = BAND * lo + (uint32_t)r; J = BAND * lo + c; return; }
         r -= h; ++c;
     }
     c += (uint32_t)(r / na);
-    I = BAND * lo + (uint32_t)(r % na);
-    J = (BAND / 2) * lo + c;
+    I2 = BAND * lo + (uint32_t)(r % na);
+    J = BAND * lo + c;
 }
 
 // ---- fp32 KSA on the four counted corners -----------------------------------------------------------
@@ -233,8 +261,8 @@ __device__ __forceinline__ void load_record(const void *rec, float2 (&p)[3], flo
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MMA_THREADS, 1)
-pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const MmaParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
+pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaParams p) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;              // SWIZZLE_128B atoms are 1024-byte aligned
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
@@ -245,45 +273,51 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();          // 0: leader of the CTA pair (issues the MMAs, owns full / tempty)
+    const uint32_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
     if (tid == 0) {
-        for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
+        // full: the leader's own arrive.expect_tx + the peer producer's arrive; both CTAs' TMA bytes land on it.
+        // empty / tfull: one multicast tcgen05.commit each. tempty: every epilogue warp of both CTAs.
+        for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // whole warp: allocate all 512 TMEM columns (two accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == 1) {   // whole warp, in both CTAs: all 512 TMEM columns (two accumulators)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                // barriers initialised and TMEM allocated in both CTAs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint64_t stride = (uint64_t)p.n_shards * gridDim.x;
-    const uint64_t first = p.dump ? p.dump_tile : p.shard + (uint64_t)p.n_shards * blockIdx.x;
+    const uint64_t stride = (uint64_t)p.n_shards * n_pairs;
+    const uint64_t first = p.dump ? p.dump_tile : p.shard + (uint64_t)p.n_shards * pair_id;
     const uint64_t last = p.dump ? p.dump_tile + 1 : p.n_tiles;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (both CTAs: own 128 A rows, own half of the 256 B rows) =====
         if (lane == 0) {
             uint64_t it = 0;
             for (uint64_t t = first; t < last; t += stride) {
-                uint32_t I, J;
-                mma_tile_from_index(t, p, I, J);
+                uint32_t I2, J;
+                mma_tile_from_index(t, p, I2, J);
+                const int a_row = (int)((2 * I2 + rank) * (2 * MMA_A_SNPS)), b_row = (int)(J * MMA_N + rank * MMA_B_SNPS);
                 for (uint32_t kb = 0; kb < p.NKB; ++kb, ++it) {
                     const int st = (int)(it % MMA_STAGES);
                     mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
                     unsigned char *dst = sm + st * STAGE_BYTES_MMA;
-                    mbar_expect_tx(&full[st], STAGE_BYTES_MMA);
-                    tma_load_2d(dst, &map_a, (int)(kb * MMA_KB), (int)(I * MMA_M), &full[st]);
-                    tma_load_2d(dst + A_STAGE_BYTES, &map_b, (int)(kb * MMA_KB), (int)(J * MMA_N), &full[st]);
+                    if (rank == 0) mbar_expect_tx(&full[st], 2 * STAGE_BYTES_MMA);
+                    else mbar_arrive_remote(&full[st], 0);
+                    tma_load_2d_pair(dst, &map_ab, (int)(kb * MMA_KB), a_row, &full[st]);
+                    tma_load_2d_pair(dst + A_STAGE_BYTES, &map_ab, (int)(kb * MMA_KB), b_row, &full[st]);
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
             uint64_t it = 0, tile_it = 0;
             for (uint64_t t = first; t < last; t += stride, ++tile_it) {
                 const uint32_t buf = (uint32_t)(tile_it & 1);
@@ -299,22 +333,23 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
                     for (int k = 0; k < MMA_KB / UMMA_K; ++k)
                         tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb | (uint32_t)k) != 0);
-                    tc_commit(&empty[st]);            // stage reusable once these MMAs have read it
+                    tc_commit_mc(&empty[st], 3);      // stage reusable in both CTAs once these MMAs have read it
                 }
-                tc_commit(&tfull[buf]);               // accumulator complete
+                tc_commit_mc(&tfull[buf], 3);         // accumulator complete in both CTAs
             }
         }
     } else {
-        // ===== epilogue =====
+        // ===== epilogue (both CTAs: own 64 A-SNPs x the tile's 128 B-SNPs) =====
         const int ew = warp - 2;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int g = ew >> 2;                        // column group: 64 accumulator columns = 32 B-SNPs
-        const int a_loc = 16 * q + (lane >> 1);       // A-SNP of this lane inside the tile
+        const int a_loc = 16 * q + (lane >> 1);       // A-SNP of this lane inside the CTA's 64
         const int pl = lane & 1;                      // plane held by this lane's TMEM row (0: aa, 1: bb)
         uint64_t tile_it = 0;
         for (uint64_t t = first; t < last; t += stride, ++tile_it) {
-            uint32_t I, J;
-            mma_tile_from_index(t, p, I, J);
+            uint32_t I2, J;
+            mma_tile_from_index(t, p, I2, J);
+            const uint32_t I = 2 * I2 + rank;         // this CTA's 64-SNP A-block
             const uint32_t buf = (uint32_t)(tile_it & 1);
             const uint64_t gi = (uint64_t)I * MMA_A_SNPS + a_loc;
             // row-role record of this lane's A-SNP. Odd lanes own plane "bb" of A: they see the table with A's
@@ -326,7 +361,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             // interior tile: every pair is i < j inside the table and no block has missing calls
             const bool interior = (uint64_t)(I + 1) * MMA_A_SNPS <= (uint64_t)J * MMA_B_SNPS && (uint64_t)(J + 1) * MMA_B_SNPS <= p.M &&
                                   !p.tile_missing[I] && !p.tile_missing[2 * J] && !p.tile_missing[2 * J + 1];
-            const bool a_ok = !p.tile_missing[I];
+            const bool a_ok = (uint64_t)I * MMA_A_SNPS < p.M && !p.tile_missing[I];
             mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
             tc_fence_after();
 #pragma unroll 1
@@ -344,6 +379,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     const int b_loc = 32 * g + 16 * h + 2 * s + pl;
                     const uint64_t gj = (uint64_t)J * MMA_B_SNPS + b_loc;
                     if (p.dump) {
+                        if (rank != p.dump_rank) continue;
                         const uint32_t d0 = pl ? got0 : keep0, d1 = pl ? got1 : keep1, d2 = pl ? keep0 : got0, d3 = pl ? keep1 : got1;
                         uint32_t *o = p.dump + ((uint64_t)a_loc * MMA_B_SNPS + b_loc) * 8;
                         o[0] = d0 & 0x3fffu; o[1] = d1 & 0x3fffu; o[2] = d2 & 0x3fffu; o[3] = d3 & 0x3fffu;
@@ -372,15 +408,15 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (lane == 0) mbar_arrive_remote(&tempty[buf], 0);
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                                // neither CTA leaves while its pair may still touch its SM
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -537,18 +573,17 @@ static int ensure_mma_inputs(gwasdev_store *s) {
         expand_mma_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt,
                                                                                  case_bytes, s->mm_kbytes, s->M, s->d_mm);
         GW_LAUNCHED();
-        if (!s->tmap_mm && posix_memalign(&s->tmap_mm, 64, 2 * sizeof(CUtensorMap)) != 0) { s->tmap_mm = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
+        if (!s->tmap_mm && posix_memalign(&s->tmap_mm, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
         int rc;
-        if ((rc = make_mm_map(s, MMA_M, (CUtensorMap *)s->tmap_mm)) != GWASDEV_OK) return rc;
-        if ((rc = make_mm_map(s, MMA_N, (CUtensorMap *)s->tmap_mm + 1)) != GWASDEV_OK) return rc;
+        if ((rc = make_mm_map(s, 2 * MMA_A_SNPS, (CUtensorMap *)s->tmap_mm)) != GWASDEV_OK) return rc;   // 128-row boxes: a CTA's A rows / its half of B
         // band table
-        const uint32_t TA = (uint32_t)((s->M + MMA_A_SNPS - 1) / MMA_A_SNPS), TB = (uint32_t)(Msnp / MMA_B_SNPS);
-        const uint32_t n_bands = (TA + BAND - 1) / BAND;
+        const uint32_t TB = (uint32_t)(Msnp / MMA_BLK);
+        const uint32_t n_bands = (TB + BAND - 1) / BAND;
         std::vector<uint64_t> off(n_bands + 1, 0);
         for (uint32_t b = 0; b < n_bands; ++b) {
-            const uint32_t na = band_height(TA, b);
+            const uint32_t na = band_height(TB, b);
             uint64_t tiles = 0;
-            for (uint32_t J = (BAND / 2) * b; J < TB; ++J) tiles += column_height(na, J - (BAND / 2) * b);
+            for (uint32_t J = BAND * b; J < TB; ++J) tiles += column_height(na, J - BAND * b);
             off[b + 1] = off[b] + tiles;
         }
         GW_CUDA(reserve_raw(s->d_band_off, s->cap_band, off.size() * sizeof(uint64_t)));
@@ -582,30 +617,31 @@ static uint64_t rect_pairs(uint64_t M, uint64_t i0, uint64_t i1, uint64_t j0, ui
 uint64_t gwasdev_internal_mma_shard_pairs(const gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags,
                                           uint64_t *tiles_out) {
     const uint64_t M = s->M;
-    const uint64_t Msnp = (M + MMA_B_SNPS - 1) / MMA_B_SNPS * MMA_B_SNPS;
-    const uint32_t TA = (uint32_t)((M + MMA_A_SNPS - 1) / MMA_A_SNPS), TB = (uint32_t)(Msnp / MMA_B_SNPS);
-    const uint32_t n_bands = (TA + BAND - 1) / BAND;
+    const uint32_t TB = (uint32_t)((M + MMA_BLK - 1) / MMA_BLK);
+    const uint32_t n_bands = (TB + BAND - 1) / BAND;
     uint64_t pairs = 0, tiles = 0, t = 0;
     for (uint32_t b = 0; b < n_bands; ++b) {
-        const uint32_t na = band_height(TA, b);
-        for (uint32_t J = (BAND / 2) * b; J < TB; ++J) {
-            const uint32_t h = column_height(na, J - (BAND / 2) * b);
-            const uint64_t j0 = (uint64_t)J * MMA_B_SNPS, j1 = std::min<uint64_t>(j0 + MMA_B_SNPS, M);
-            // tiles t .. t+h-1 are A-blocks I = 16b + ii of this column; those of the shard: (t + ii) % n_shards == shard
-            const bool simple = !flags && (uint64_t)(BAND * b + h) * MMA_A_SNPS <= j0 && (uint64_t)(BAND * b + h) * MMA_A_SNPS <= M;
+        const uint32_t na = band_height(TB, b);
+        for (uint32_t J = BAND * b; J < TB; ++J) {
+            const uint32_t h = column_height(na, J - BAND * b);
+            const uint64_t j0 = (uint64_t)J * MMA_BLK, j1 = std::min<uint64_t>(j0 + MMA_BLK, M);
+            // tiles t .. t+h-1 are A-blocks I2 = 8b + ii of this column; those of the shard: (t + ii) % n_shards == shard
+            const bool simple = !flags && (uint64_t)(BAND * b + h) * MMA_BLK <= j0;     // full rectangles left of the B-block
             uint32_t ii = (uint32_t)((shard + n_shards - t % n_shards) % n_shards);
-            if (simple) {          // every tile of the column is a full rectangle left of the B-block
-                if (ii < h) { const uint64_t cnt = (h - 1 - ii) / n_shards + 1; tiles += cnt; pairs += cnt * MMA_A_SNPS * (j1 - j0); }
+            if (simple) {
+                if (ii < h) { const uint64_t cnt = (h - 1 - ii) / n_shards + 1; tiles += cnt; pairs += cnt * MMA_BLK * (j1 - j0); }
             } else {
                 for (; ii < h; ii += n_shards) {
-                    const uint32_t I = BAND * b + ii;
+                    const uint64_t I2 = BAND * b + ii;
                     ++tiles;
-                    if (!flags) pairs += rect_pairs(M, (uint64_t)I * MMA_A_SNPS, (uint64_t)(I + 1) * MMA_A_SNPS, j0, j0 + MMA_B_SNPS);
-                    else if (!flags[I])
-                        for (int sub = 0; sub < 2; ++sub) {
-                            const uint64_t jb = 2ull * J + sub;
-                            if (jb * TILE < M && !flags[jb]) pairs += rect_pairs(M, (uint64_t)I * MMA_A_SNPS, (uint64_t)(I + 1) * MMA_A_SNPS, jb * TILE, (jb + 1) * TILE);
-                        }
+                    if (!flags) pairs += rect_pairs(M, I2 * MMA_BLK, (I2 + 1) * MMA_BLK, j0, j0 + MMA_BLK);
+                    else
+                        for (int sa = 0; sa < 2; ++sa)
+                            for (int sb = 0; sb < 2; ++sb) {
+                                const uint64_t ia = 2 * I2 + sa, jb = 2ull * J + sb;
+                                if (ia * TILE < M && jb * TILE < M && !flags[ia] && !flags[jb])
+                                    pairs += rect_pairs(M, ia * TILE, (ia + 1) * TILE, jb * TILE, (jb + 1) * TILE);
+                            }
                 }
             }
             t += h;
@@ -622,22 +658,20 @@ static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const size_t smem = mma_smem_bytes();
     GW_CUDA(cudaFuncSetAttribute(pair_screen_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms, my_tiles));
-    const CUtensorMap *maps = (const CUtensorMap *)s->tmap_mm;
-    pair_screen_mma_kernel<<<grid, MMA_THREADS, smem, s->stream>>>(maps[0], maps[1], p);
+    const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));   // one CTA pair per TPC
+    pair_screen_mma_kernel<<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm, p);
     GW_LAUNCHED();
     return GWASDEV_OK;
 }
 
 static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t n_shards) {
-    const uint64_t Msnp = (s->M + MMA_B_SNPS - 1) / MMA_B_SNPS * MMA_B_SNPS;
-    p.TA = (uint32_t)((s->M + MMA_A_SNPS - 1) / MMA_A_SNPS); p.TB = (uint32_t)(Msnp / MMA_B_SNPS);
-    p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TA + BAND - 1) / BAND; p.M = s->M;
+    p.TB = (uint32_t)((s->M + MMA_BLK - 1) / MMA_BLK);
+    p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M;
     p.shard = shard; p.n_shards = n_shards; p.band_off = s->d_band_off;
     p.row = (const MmaRow *)s->d_mma_row; p.col = (const MmaCol *)s->d_mma_col; p.tile_missing = s->d_tile_missing;
     p.N = (float)(s->n_case + s->n_ctrl);
     p.qc = s->mma_qc; p.q0 = s->mma_q0;
-    p.dump = nullptr; p.dump_tile = 0;
+    p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0;
 }
 
 // Launches the tensor-core screen for this shard's clean tiles. thr already carries the fp32 margin.
@@ -677,20 +711,20 @@ int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *
     if ((rc = ensure_mma_inputs(s)) != GWASDEV_OK) return rc;
     MmaParams p;
     fill_params(s, p, 0, 1);
-    GW_REQUIRE(I < p.TA && J < p.TB && I <= 2 * J + 1, "gwasdev_mma_tile_counts: tile (%u, %u) is not in the schedule", I, J);
+    GW_REQUIRE(I / 2 < p.TB && J < p.TB && I / 2 <= J, "gwasdev_mma_tile_counts: tile (%u, %u) is not in the schedule", I, J);
     // linear index of (I, J)
     std::vector<uint64_t> off(p.n_bands + 1);
     GW_CUDA(cudaMemcpyAsync(off.data(), s->d_band_off, off.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
     GW_CUDA(cudaStreamSynchronize(s->stream));
-    const uint32_t b = I / BAND, na = band_height(p.TA, b);
+    const uint32_t I2 = I / 2, b = I2 / BAND, na = band_height(p.TB, b);
     uint64_t t = off[b];
-    for (uint32_t c = 0; c < J - (BAND / 2) * b; ++c) t += column_height(na, c);
-    t += I - BAND * b;
+    for (uint32_t c = 0; c < J - BAND * b; ++c) t += column_height(na, c);
+    t += I2 - BAND * b;
     p.n_tiles = off[p.n_bands];
     const size_t bytes = (size_t)MMA_A_SNPS * MMA_B_SNPS * 8 * sizeof(uint32_t);
     GW_CUDA(reserve(s->sc_a, bytes));
     GW_CUDA(cudaMemsetAsync(s->sc_a.p, 0xff, bytes, s->stream));
-    p.dump = (uint32_t *)s->sc_a.p; p.dump_tile = t;
+    p.dump = (uint32_t *)s->sc_a.p; p.dump_tile = t; p.dump_rank = I & 1;
     p.thr = 0.f; p.cand = nullptr; p.n_cand = nullptr; p.cap = 0;
     if ((rc = launch_mma(s, p, 1)) != GWASDEV_OK) return rc;
     GW_CUDA(cudaMemcpyAsync(out, s->sc_a.p, bytes, cudaMemcpyDeviceToHost, s->stream));

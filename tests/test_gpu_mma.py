@@ -43,7 +43,7 @@ def test_mma_tile_counts_match_pair_tables(orc, seed, M, N, ncase):
     codes, pheno = orc.simulate(seed, M, N, ncase)
     with make_store(orc, codes, pheno) as st:
         TA, TB = (M + 63) // 64, (M + 127) // 128
-        tiles = [(I, J) for J in range(TB) for I in range(TA) if I <= 2 * J + 1]
+        tiles = [(I, J) for J in range(TB) for I in range(TA) if I // 2 <= J]
         for I, J in tiles:
             got = st.mma_tile_counts(I, J)
             assert np.array_equal(got, expected_tile(st, M, I, J)), f"tile ({I}, {J})"
