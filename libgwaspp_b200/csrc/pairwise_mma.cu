@@ -48,6 +48,7 @@ constexpr int A_STAGE_BYTES = 2 * MMA_A_SNPS * MMA_KB, B_STAGE_BYTES = MMA_B_SNP
 constexpr int STAGE_BYTES_MMA = A_STAGE_BYTES + B_STAGE_BYTES;     // 32 KiB per CTA
 constexpr int EPI_WARPS = 16;
 constexpr int MMA_THREADS = (2 + EPI_WARPS) * 32;
+constexpr int COL_STAGE_BYTES = 32 * 64;                           // column-role records of one epilogue warp's 32 B-SNPs
 constexpr int BAND = 8;                                            // A-blocks per L2 band
 constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
 constexpr uint32_t CTRL_SHIFT = 14;                                // (-128)^2 = 2^14
@@ -80,6 +81,8 @@ struct MmaParams {
     uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only, rows of CTA `dump_rank`
     uint64_t dump_tile;
     uint32_t dump_rank;
+    uint32_t dbg;               // GWASDEV_MMA_DEBUG (timing diagnostics, results invalid): 1 epilogue only hand-shakes, 2 epilogue loads TMEM
+                                // but skips the math, 4 no MMAs issued, 16 no exact pass, 32 no TMA loads
 };
 
 // ---- PTX: tcgen05 ------------------------------------------------------------------------------------
@@ -251,9 +254,16 @@ __device__ __forceinline__ float2 decode2(uint32_t d) {
     return __fadd2_rn(m, make_float2(-8388608.0f, -8388608.0f));
 }
 
+__device__ __forceinline__ void unpack_record(const uint4 &r0, const uint4 &r1, const uint4 &r2, const uint4 &r3, float2 (&p)[3], float2 (&c)[3], float &C);
+__device__ __forceinline__ void load_record_smem(const unsigned char *rec, float2 (&p)[3], float2 (&c)[3], float &C) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(rec);
+    unpack_record(q[0], q[1], q[2], q[3], p, c, C);
+}
 __device__ __forceinline__ void load_record(const void *rec, float2 (&p)[3], float2 (&c)[3], float &C) {
     const uint4 *q = reinterpret_cast<const uint4 *>(rec);
-    const uint4 r0 = __ldg(q), r1 = __ldg(q + 1), r2 = __ldg(q + 2), r3 = __ldg(q + 3);
+    unpack_record(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3), p, c, C);
+}
+__device__ __forceinline__ void unpack_record(const uint4 &r0, const uint4 &r1, const uint4 &r2, const uint4 &r3, float2 (&p)[3], float2 (&c)[3], float &C) {
     p[0] = make_float2(__uint_as_float(r0.x), __uint_as_float(r0.y)); p[1] = make_float2(__uint_as_float(r0.z), __uint_as_float(r0.w));
     p[2] = make_float2(__uint_as_float(r1.x), __uint_as_float(r1.y)); c[0] = make_float2(__uint_as_float(r1.z), __uint_as_float(r1.w));
     c[1] = make_float2(__uint_as_float(r2.x), __uint_as_float(r2.y)); c[2] = make_float2(__uint_as_float(r2.z), __uint_as_float(r2.w));
@@ -266,7 +276,8 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;              // SWIZZLE_128B atoms are 1024-byte aligned
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
-    uint64_t *full = reinterpret_cast<uint64_t *>(sm + MMA_STAGES * STAGE_BYTES_MMA);
+    unsigned char *col_sm = sm + MMA_STAGES * STAGE_BYTES_MMA;                 // per epilogue warp: 32 column-role records
+    uint64_t *full = reinterpret_cast<uint64_t *>(col_sm + EPI_WARPS * COL_STAGE_BYTES);
     uint64_t *empty = full + MMA_STAGES;
     uint64_t *tfull = empty + MMA_STAGES;
     uint64_t *tempty = tfull + 2;
@@ -308,6 +319,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     const int st = (int)(it % MMA_STAGES);
                     mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
                     unsigned char *dst = sm + st * STAGE_BYTES_MMA;
+                    if (p.dbg & 32) { if (rank == 0) mbar_arrive(&full[st]); else mbar_arrive_remote(&full[st], 0); continue; }
                     if (rank == 0) mbar_expect_tx(&full[st], 2 * STAGE_BYTES_MMA);
                     else mbar_arrive_remote(&full[st], 0);
                     tma_load_2d_pair(dst, &map_ab, (int)(kb * MMA_KB), a_row, &full[st]);
@@ -330,6 +342,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     tc_fence_after();
                     const uint32_t a_addr = base + st * STAGE_BYTES_MMA, b_addr = a_addr + A_STAGE_BYTES;
                     const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+                    if (!(p.dbg & 4))
 #pragma unroll
                     for (int k = 0; k < MMA_KB / UMMA_K; ++k)
                         tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb | (uint32_t)k) != 0);
@@ -362,46 +375,84 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
             const bool interior = (uint64_t)(I + 1) * MMA_A_SNPS <= (uint64_t)J * MMA_B_SNPS && (uint64_t)(J + 1) * MMA_B_SNPS <= p.M &&
                                   !p.tile_missing[I] && !p.tile_missing[2 * J] && !p.tile_missing[2 * J + 1];
             const bool a_ok = (uint64_t)I * MMA_A_SNPS < p.M && !p.tile_missing[I];
+            // missing-call flags of the two 64-SNP halves of the B-block (a half beyond the table counts as flagged)
+            const bool b_bad0 = (uint64_t)(2 * J) * TILE >= p.M || p.tile_missing[2 * J];
+            const bool b_bad1 = (uint64_t)(2 * J + 1) * TILE >= p.M || p.tile_missing[2 * J + 1];
+            const bool b_bad = g < 2 ? b_bad0 : b_bad1;           // this warp's 32 B-SNPs lie in one half
+            // this warp's 32 column-role records: 2 KiB contiguous in global memory -> its private shared-memory slot
+            unsigned char *my_col = col_sm + ew * COL_STAGE_BYTES;
+            {
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.col + ((uint64_t)J * MMA_B_SNPS + 32 * g));
+                uint4 *dst = reinterpret_cast<uint4 *>(my_col);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst[32 * k + lane] = __ldg(src + 32 * k + lane);
+                __syncwarp();
+            }
             mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
+                if (p.dbg & 1) break;
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 64 * g + 32 * h, v);
                 tc_wait_ld();
+                // columns 4s..4s+3 = B-SNPs b0 = 2s (planes aa, bb) and b1 = 2s+1 of this 16-SNP group. Even lanes
+                // (plane aa of A) finish pair (a, b0), odd lanes (plane bb of A) pair (a, b1): each sends the two
+                // counts its partner needs and keeps its own two.
+                if (p.dump) {
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    // columns 4s..4s+3 = B-SNPs b0 = 2s (planes aa, bb) and b1 = 2s+1 of this 16-SNP group.
-                    // Even lanes (plane aa of A) finish pair (a, b0), odd lanes (plane bb of A) pair (a, b1).
-                    const uint32_t keep0 = pl ? v[4 * s + 2] : v[4 * s + 0], keep1 = pl ? v[4 * s + 3] : v[4 * s + 1];
-                    const uint32_t send0 = pl ? v[4 * s + 0] : v[4 * s + 2], send1 = pl ? v[4 * s + 1] : v[4 * s + 3];
-                    const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1), got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-                    const int b_loc = 32 * g + 16 * h + 2 * s + pl;
-                    const uint64_t gj = (uint64_t)J * MMA_B_SNPS + b_loc;
-                    if (p.dump) {
+                    for (int s = 0; s < 8; ++s) {
+                        const uint32_t keep0 = pl ? v[4 * s + 2] : v[4 * s + 0], keep1 = pl ? v[4 * s + 3] : v[4 * s + 1];
+                        const uint32_t send0 = pl ? v[4 * s + 0] : v[4 * s + 2], send1 = pl ? v[4 * s + 1] : v[4 * s + 3];
+                        const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1), got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
                         if (rank != p.dump_rank) continue;
+                        const int b_loc = 32 * g + 16 * h + 2 * s + pl;
                         const uint32_t d0 = pl ? got0 : keep0, d1 = pl ? got1 : keep1, d2 = pl ? keep0 : got0, d3 = pl ? keep1 : got1;
                         uint32_t *o = p.dump + ((uint64_t)a_loc * MMA_B_SNPS + b_loc) * 8;
                         o[0] = d0 & 0x3fffu; o[1] = d1 & 0x3fffu; o[2] = d2 & 0x3fffu; o[3] = d3 & 0x3fffu;
                         o[4] = d0 >> CTRL_SHIFT; o[5] = d1 >> CTRL_SHIFT; o[6] = d2 >> CTRL_SHIFT; o[7] = d3 >> CTRL_SHIFT;
-                        continue;
                     }
-                    bool valid = true;
-                    if (!interior) valid = gi < gj && gj < p.M && a_ok && !p.tile_missing[min(gj, p.M - 1) >> 6];
+                    continue;
+                }
+                if (p.dbg & 2) { if (v[0] + v[13] + v[31] == 0x7fffffffu) p.cand[0].pad = 1; continue; }
+                // pass 1, branch-free so that the eight pairs interleave: upper bound of the statistic
+                const uint64_t gj0 = (uint64_t)J * MMA_B_SNPS + 32 * g + 16 * h + pl;
+                uint32_t hot = 0;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint32_t keep0 = pl ? v[4 * s + 2] : v[4 * s + 0], keep1 = pl ? v[4 * s + 3] : v[4 * s + 1];
+                    const uint32_t send0 = pl ? v[4 * s + 0] : v[4 * s + 2], send1 = pl ? v[4 * s + 1] : v[4 * s + 3];
+                    const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1), got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
+                    v[4 * s + 0] = keep0; v[4 * s + 1] = keep1; v[4 * s + 2] = got0; v[4 * s + 3] = got1;   // own plane of A first
+                    const uint64_t gj = gj0 + 2 * s;
                     float2 w[3], cb[3]; float Ccol;
-                    load_record(p.col + gj, w, cb, Ccol);
-                    // own plane of A first ("AA" for even lanes, "aa" for odd lanes with the swapped record)
+                    load_record_smem(my_col + (16 * h + 2 * s + pl) * 64, w, cb, Ccol);
                     const Cells t = derive_cells(decode2(keep0), decode2(keep1), decode2(got0), decode2(got1), ca, cb);
                     float tau;
                     const float ub = ksa_upper_bound(t, pca, w, Crow + Ccol, p.N, p.qc, p.q0, tau);
-                    const bool hot = valid && ub > p.thr;
-                    if (__any_sync(0xffffffffu, hot)) {
-                        if (hot) {
-                            const float stat = ksa_screen_cells(t, tau, Crow + Ccol, p.N);
-                            if (stat > p.thr) {
-                                const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
-                                if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
-                            }
+                    const bool valid = interior || (gi < gj && gj < p.M && a_ok && !b_bad);
+                    hot |= (valid && ub > p.thr) ? (1u << s) : 0u;
+                }
+                // pass 2, rare: exact fp32 formula for the pairs whose bound passed
+                if (!(p.dbg & 16) && __any_sync(0xffffffffu, hot != 0)) {
+#pragma unroll 1
+                    for (int s = 0; s < 8; ++s) {
+                        if (!((hot >> s) & 1u)) continue;
+                        uint32_t k0, k1, g0, g1;   // dynamic index into v[]: select instead of local memory
+                        k0 = v[0]; k1 = v[1]; g0 = v[2]; g1 = v[3];
+#pragma unroll
+                        for (int q8 = 1; q8 < 8; ++q8)
+                            if (s == q8) { k0 = v[4 * q8]; k1 = v[4 * q8 + 1]; g0 = v[4 * q8 + 2]; g1 = v[4 * q8 + 3]; }
+                        const uint64_t gj = gj0 + 2 * s;
+                        float2 w[3], cb[3]; float Ccol;
+                        load_record_smem(my_col + (16 * h + 2 * s + pl) * 64, w, cb, Ccol);
+                        const Cells t = derive_cells(decode2(k0), decode2(k1), decode2(g0), decode2(g1), ca, cb);
+                        float tau;
+                        (void)ksa_upper_bound(t, pca, w, Crow + Ccol, p.N, p.qc, p.q0, tau);
+                        const float stat = ksa_screen_cells(t, tau, Crow + Ccol, p.N);
+                        if (stat > p.thr) {
+                            const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
+                            if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
                         }
                     }
                 }
@@ -651,7 +702,7 @@ uint64_t gwasdev_internal_mma_shard_pairs(const gwasdev_store *s, uint32_t shard
     return pairs;
 }
 
-static size_t mma_smem_bytes() { return 1024 + (size_t)MMA_STAGES * STAGE_BYTES_MMA + (2 * MMA_STAGES + 4) * sizeof(uint64_t) + 16; }
+static size_t mma_smem_bytes() { return 1024 + (size_t)MMA_STAGES * STAGE_BYTES_MMA + EPI_WARPS * COL_STAGE_BYTES + (2 * MMA_STAGES + 4) * sizeof(uint64_t) + 16; }
 
 static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
     int sms = 0;
@@ -672,6 +723,7 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
     p.N = (float)(s->n_case + s->n_ctrl);
     p.qc = s->mma_qc; p.q0 = s->mma_q0;
     p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0;
+    p.dbg = getenv("GWASDEV_MMA_DEBUG") ? (uint32_t)atoi(getenv("GWASDEV_MMA_DEBUG")) : 0u;
 }
 
 // Launches the tensor-core screen for this shard's clean tiles. thr already carries the fp32 margin.
