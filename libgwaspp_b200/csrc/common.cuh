@@ -161,11 +161,10 @@ struct gwasdev_store {
     int8_t *d_mm = nullptr;
     void *tmap_mm = nullptr;      // host copies of the two CUtensorMaps (A box, B box)
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
-    uint64_t *d_band_off = nullptr;
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
     float mma_qc = 0.f, mma_q0 = 0.f;   // constants of the upper-bound pre-filter (pairwise_mma.cu)
     std::vector<uint8_t> h_tile_missing;   // host copy of d_tile_missing (valid with side_valid)
-    size_t cap_mm = 0, cap_mma_row = 0, cap_mma_col = 0, cap_band = 0;
+    size_t cap_mm = 0, cap_mma_row = 0, cap_mma_col = 0;
     bool mma_side_valid = false;
     bool any_missing = false, any_clean = false;     // over tiles, valid with side_valid
 

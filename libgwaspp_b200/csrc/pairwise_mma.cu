@@ -17,12 +17,12 @@
 //
 // Kernel. Two CTAs on the two SMs of a TPC work as a pair (cluster of 2, tcgen05 cta_group::2), persistent
 // over tile pairs of (128 A-SNPs = 256 rows, 128 per CTA) x (128 B-SNPs = 256 rows, each CTA stages half):
-//   warp 0   TMA producer : cp.async.bulk.tensor.2d.cta_group::2, SWIZZLE_128B boxes of 128 sample bytes, both
+//   warp 16  TMA producer : cp.async.bulk.tensor.2d.cta_group::2, SWIZZLE_128B boxes of 128 sample bytes, both
 //                           CTAs' loads complete on the leader's mbarrier, 6-stage ring of 32 KiB per CTA
-//   warp 1   MMA issuer   : (leader CTA) tcgen05.mma.cta_group::2.kind::i8, M=256 N=256 K=32, 4 per stage, into
+//   warp 17  MMA issuer   : (leader CTA) tcgen05.mma.cta_group::2.kind::i8, M=256 N=256 K=32, 4 per stage, into
 //                           one of two 256-column TMEM accumulators; tcgen05.commit multicasts "stage free" and
 //                           "accumulator ready" to both CTAs
-//   warps 2+ epilogue     : each CTA reads its 128 accumulator rows (64 A-SNPs) with tcgen05.ld 32x32b, lane
+//   warps 0-15 epilogue   : each CTA reads its 128 accumulator rows (64 A-SNPs) with tcgen05.ld 32x32b, lane
 //                           pairs swap the two planes by shuffle, decode the counts, margins -> 3x3x2 table,
 //                           upper bound of the KSA statistic, exact fp32 KSA for the few that pass it,
 //                           candidates above threshold - margin
@@ -43,11 +43,16 @@ constexpr int MMA_BLK = 128;                                       // SNPs per s
 constexpr int MMA_M = 4 * MMA_A_SNPS, MMA_N = 2 * MMA_B_SNPS;      // operand rows of one cta_group::2 instruction
 constexpr int MMA_KB = 128;                                        // sample bytes per stage (one 128B swizzle row)
 constexpr int UMMA_K = 32;                                         // bytes per tcgen05.mma kind::i8
-constexpr int MMA_STAGES = 6;
-constexpr int A_STAGE_BYTES = 2 * MMA_A_SNPS * MMA_KB, B_STAGE_BYTES = MMA_B_SNPS * MMA_KB;   // per CTA: its A rows, its half of B
-constexpr int STAGE_BYTES_MMA = A_STAGE_BYTES + B_STAGE_BYTES;     // 32 KiB per CTA
+constexpr int MMA_STAGES = 3;
+constexpr int KPS = 2;                                             // 128-byte sample blocks per stage (fewer barrier round trips)
+constexpr int A_STAGE_BYTES = 2 * MMA_A_SNPS * MMA_KB, B_STAGE_BYTES = MMA_B_SNPS * MMA_KB;   // per CTA and sample block: its A rows, its half of B
+constexpr int KB_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;            // 32 KiB per CTA and sample block
+constexpr int STAGE_BYTES_MMA = KPS * KB_BYTES;                    // 64 KiB per CTA
 constexpr int EPI_WARPS = 16;
 constexpr int MMA_THREADS = (2 + EPI_WARPS) * 32;
+// The warp scheduler favours the highest warp ids: the two single-thread roles that every stage waits on sit
+// above the sixteen epilogue warps (which also makes warp % 4 the TMEM lane quadrant of epilogue warp `warp`).
+constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int COL_STAGE_BYTES = 32 * 64;                           // column-role records of one epilogue warp's 32 B-SNPs
 constexpr int BAND = 8;                                            // A-blocks per L2 band
 constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
@@ -62,6 +67,16 @@ struct __align__(16) MmaRow { float2 pca[3]; float2 cnt[3]; float C; float pad[3
 struct __align__(16) MmaCol { float2 w[3];   float2 cnt[3]; float C; float pad[3]; };
 static_assert(sizeof(MmaRow) == 64 && sizeof(MmaCol) == 64, "64-byte epilogue records");
 
+// Records of the bound pass (ksa_bound_fast): tau = sum_ab n_ab. W_ab is affine in the four pooled corner counts
+// x = (AB, Ab, aB, ab), so only differences against the heterozygote class and two per-SNP dot products are needed:
+//   tau = sum_k [ w_k[1] RA_k + pca_k[1] RB_k ] + sum_k [ dA0_k (x1 dB0_k + x2 dB2_k) + dA2_k (x3 dB0_k + x4 dB2_k) ]
+//   dA0 = pca[0]-pca[1], dA2 = pca[2]-pca[1], RA_k = pca_k[0] m[0] + pca_k[2] m[2] - pca_k[1] (m[0]+m[2])     (row role)
+//   dB0 = w[0]-w[1],     dB2 = w[2]-w[1],     RB_k = w_k[0] m[0] + w_k[1] m[1] + w_k[2] m[2]                  (column role)
+// with m[g] the pooled genotype counts. cm[g] = (c_0[g], m[g]): case and pooled counts, the two the bound needs.
+struct __align__(16) MmaRowF { float2 dA0, dA2, pca1, RA, cm0, cm2; float C; float pad[3]; };
+struct __align__(16) MmaColF { float2 dB0, dB2, w1, RB, cm0, cm1, cm2; float C; float pad; };
+static_assert(sizeof(MmaRowF) == 64 && sizeof(MmaColF) == 64, "64-byte bound-pass records");
+
 struct MmaParams {
     uint32_t TB;                // 128-SNP blocks
     uint32_t NKB;               // 128-byte sample blocks per row
@@ -69,12 +84,14 @@ struct MmaParams {
     uint64_t M;
     uint64_t n_tiles;
     uint32_t shard, n_shards;
-    const uint64_t *band_off;   // [n_bands + 1] tiles before band b
     const MmaRow *row;
     const MmaCol *col;
+    const MmaRowF *rowf;
+    const MmaColF *colf;
     const uint8_t *tile_missing;   // per 64-SNP block
     float thr, N;
     float qc, q0;               // upper-bound pre-filter: S <= qc * sum_ab c0^2/cab - q0 (see ksa_upper_bound)
+    float thr2;                 // thr / (2 ln 2): the bound pass compares in log2 units
     Candidate *cand;
     unsigned long long *n_cand;
     uint64_t cap;
@@ -167,22 +184,41 @@ constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(M
 __host__ __device__ inline uint32_t band_height(uint32_t TB, uint32_t b) { return min((uint32_t)BAND, TB - BAND * b); }
 __host__ __device__ inline uint32_t column_height(uint32_t na, uint32_t c) { return min(na, c + 1); }
 
-__device__ __forceinline__ void mma_tile_from_index(uint64_t t, const MmaParams &p, uint32_t &I2, uint32_t &J) {
-    uint32_t lo = 0, hi = p.n_bands;
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (p.band_off[mid] <= t) lo = mid; else hi = mid; }
-    uint64_t r = t - p.band_off[lo];
-    const uint32_t na = band_height(p.TB, lo);
-    uint32_t c = 0;
-    for (;;) {
-        const uint32_t h = column_height(na, c);
-        if (h == na) break;
-        if (r < h) { I2 = BAND * lo + (uint32_t)r; J = BAND * lo + c; return; }
-        r -= h; ++c;
-    }
-    c += (uint32_t)(r / na);
-    I2 = BAND * lo + (uint32_t)(r % na);
-    J = BAND * lo + c;
+// Tiles before band b. Every band before the last is full (8 A-blocks, at least 8 columns): 8 (TB - 8b') - 28 tiles.
+__host__ __device__ inline uint64_t band_offset(uint32_t TB, uint64_t b) {
+    return b * ((uint64_t)BAND * TB) - (uint64_t)(BAND * BAND) * (b * (b - 1) / 2) - b * (uint64_t)(BAND * (BAND - 1) / 2);
 }
+
+__host__ __device__ inline uint64_t band_tiles(uint32_t TB, uint32_t b) {      // tiles in band b (the last one may be short)
+    const uint64_t na = band_height(TB, b), cols = TB - BAND * b;              // cols >= na
+    return na * (na - 1) / 2 + na * (cols - (na - 1));
+}
+
+// Position in the schedule: band and index inside the band. Located once with the closed form, then advanced by
+// the CTA pair's stride with a few integer operations per tile (all three roles walk the same sequence).
+struct TileCursor {
+    uint32_t b;
+    uint64_t r, len;
+    __device__ void locate(uint64_t t, uint32_t TB, uint32_t n_bands) {
+        const double Bc = (double)BAND * TB + 0.5 * BAND * BAND - 0.5 * BAND * (BAND - 1);
+        int64_t k = (int64_t)((Bc - sqrt(fmax(Bc * Bc - 2.0 * BAND * BAND * (double)t, 0.0))) / (double)(BAND * BAND));
+        k = max((int64_t)0, min(k, (int64_t)n_bands - 1));
+        while (k > 0 && band_offset(TB, (uint64_t)k) > t) --k;
+        while (k + 1 < (int64_t)n_bands && band_offset(TB, (uint64_t)k + 1) <= t) ++k;
+        b = (uint32_t)k; r = t - band_offset(TB, b); len = band_tiles(TB, b);
+    }
+    __device__ __forceinline__ void advance(uint64_t d, uint32_t TB, uint32_t n_bands) {
+        r += d;
+        while (r >= len && b + 1 < n_bands) { r -= len; ++b; len = band_tiles(TB, b); }
+    }
+    __device__ __forceinline__ void decode(uint32_t TB, uint32_t &I2, uint32_t &J) const {
+        const uint32_t na = band_height(TB, b), tri = na * (na - 1) / 2;      // columns 0..na-2 hold c+1 tiles each
+        uint32_t c, ii;
+        if (r < tri) { c = 0; uint32_t q = (uint32_t)r; while (q > c) { q -= c + 1; ++c; } ii = q; }
+        else { const uint64_t q = r - tri; c = na - 1 + (uint32_t)(q / na); ii = (uint32_t)(q % na); }
+        I2 = BAND * b + ii; J = BAND * b + c;
+    }
+};
 
 // ---- fp32 KSA on the four counted corners -----------------------------------------------------------
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -226,6 +262,35 @@ __device__ __forceinline__ float ksa_upper_bound(const Cells &t, const float2 (&
         }
     tau_out = tau;
     return 1.3862943611f * (fmaf(N, lg2_approx(tau), fmaf(qc, Q, -q0)) - Csum);
+}
+
+// The same bound from the bound-pass records, in log2 units without the 2 ln2 factor and without the constant
+// (returns N log2 tau + qc Q; the caller compares against thr2 + q0 + C_row + C_col). Corner counts arrive as
+// (case, control); cells are carried as (case, pooled). ~95 instructions, 9 MUFU.RCP + 1 MUFU.LG2.
+__device__ __forceinline__ float ksa_bound_fast(float2 AB, float2 Ab, float2 aB, float2 ab, const MmaRowF &A, const float2 (&b)[7],
+                                                float N, float qc) {
+    // b[] = dB0, dB2, w1, RB, cm0, cm1, cm2 of the column-role record
+    AB.y += AB.x; Ab.y += Ab.x; aB.y += aB.x; ab.y += ab.x;                  // (case, pooled)
+    const float2 n01 = sub2(sub2(A.cm0, AB), Ab), n21 = sub2(sub2(A.cm2, ab), aB);
+    const float2 n10 = sub2(sub2(b[4], AB), aB), n12 = sub2(sub2(b[6], Ab), ab);
+    const float2 n11 = sub2(sub2(b[5], n01), n21);
+    // tau
+    const float2 t0 = __ffma2_rn(A.pca1, b[3], __fmul2_rn(b[2], A.RA));
+    const float i1x = fmaf(Ab.y, b[1].x, AB.y * b[0].x), i1y = fmaf(Ab.y, b[1].y, AB.y * b[0].y);
+    const float i2x = fmaf(ab.y, b[1].x, aB.y * b[0].x), i2y = fmaf(ab.y, b[1].y, aB.y * b[0].y);
+    float tau = t0.x + t0.y;
+    tau = fmaf(A.dA0.x, i1x, tau); tau = fmaf(A.dA0.y, i1y, tau);
+    tau = fmaf(A.dA2.x, i2x, tau); tau = fmaf(A.dA2.y, i2y, tau);
+    // Q = sum c0^2 / cab; an empty cell gives 0 * inf = NaN inside fminf, which returns the other operand, times c0 = 0
+    float Q = 0.f;
+    const float2 cell[9] = {AB, n01, Ab, n10, n11, n12, aB, n21, ab};
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(cell[c].y));
+        Q = fmaf(cell[c].x, fminf(cell[c].x * r, 1.0f), Q);
+    }
+    return fmaf(N, lg2_approx(tau), qc * Q);
 }
 
 // Exact-formula fp32 value: 2 ln2 (sum g2(n_abk) - sum g2(n_ab.) + N log2 tau - C_row - C_col), equal to
@@ -294,7 +359,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {   // whole warp, in both CTAs: all 512 TMEM columns (two accumulators)
+    if (warp == MMA_WARP) {   // whole warp, in both CTAs: all 512 TMEM columns (two accumulators)
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
@@ -307,27 +372,31 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
     const uint64_t first = p.dump ? p.dump_tile : p.shard + (uint64_t)p.n_shards * pair_id;
     const uint64_t last = p.dump ? p.dump_tile + 1 : p.n_tiles;
 
-    if (warp == 0) {
+    if (warp == TMA_WARP) {
         // ===== TMA producer (both CTAs: own 128 A rows, own half of the 256 B rows) =====
         if (lane == 0) {
             uint64_t it = 0;
-            for (uint64_t t = first; t < last; t += stride) {
+            TileCursor cur; cur.locate(first, p.TB, p.n_bands);
+            for (uint64_t t = first; t < last; t += stride, cur.advance(stride, p.TB, p.n_bands)) {
                 uint32_t I2, J;
-                mma_tile_from_index(t, p, I2, J);
+                cur.decode(p.TB, I2, J);
                 const int a_row = (int)((2 * I2 + rank) * (2 * MMA_A_SNPS)), b_row = (int)(J * MMA_N + rank * MMA_B_SNPS);
-                for (uint32_t kb = 0; kb < p.NKB; ++kb, ++it) {
+                for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
+                    const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
                     mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
                     unsigned char *dst = sm + st * STAGE_BYTES_MMA;
                     if (p.dbg & 32) { if (rank == 0) mbar_arrive(&full[st]); else mbar_arrive_remote(&full[st], 0); continue; }
-                    if (rank == 0) mbar_expect_tx(&full[st], 2 * STAGE_BYTES_MMA);
+                    if (rank == 0) mbar_expect_tx(&full[st], nk * 2 * KB_BYTES);
                     else mbar_arrive_remote(&full[st], 0);
-                    tma_load_2d_pair(dst, &map_ab, (int)(kb * MMA_KB), a_row, &full[st]);
-                    tma_load_2d_pair(dst + A_STAGE_BYTES, &map_ab, (int)(kb * MMA_KB), b_row, &full[st]);
+                    for (uint32_t k2 = 0; k2 < nk; ++k2) {
+                        tma_load_2d_pair(dst + k2 * KB_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), a_row, &full[st]);
+                        tma_load_2d_pair(dst + k2 * KB_BYTES + A_STAGE_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), b_row, &full[st]);
+                    }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // ===== MMA issuer (leader CTA only) =====
         if (lane == 0 && rank == 0) {
             uint64_t it = 0, tile_it = 0;
@@ -336,16 +405,19 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + buf * ACC_COLS;
-                for (uint32_t kb = 0; kb < p.NKB; ++kb, ++it) {
+                for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
+                    const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
                     mbar_wait_wd(&full[st], (uint32_t)((it / MMA_STAGES) & 1));
                     tc_fence_after();
-                    const uint32_t a_addr = base + st * STAGE_BYTES_MMA, b_addr = a_addr + A_STAGE_BYTES;
-                    const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
                     if (!(p.dbg & 4))
+                    for (uint32_t k2 = 0; k2 < nk; ++k2) {
+                        const uint32_t a_addr = base + st * STAGE_BYTES_MMA + k2 * KB_BYTES, b_addr = a_addr + A_STAGE_BYTES;
+                        const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
 #pragma unroll
-                    for (int k = 0; k < MMA_KB / UMMA_K; ++k)
-                        tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb | (uint32_t)k) != 0);
+                        for (int k = 0; k < MMA_KB / UMMA_K; ++k)
+                            tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb | k2 | (uint32_t)k) != 0);
+                    }
                     tc_commit_mc(&empty[st], 3);      // stage reusable in both CTAs once these MMAs have read it
                 }
                 tc_commit_mc(&tfull[buf], 3);         // accumulator complete in both CTAs
@@ -353,24 +425,33 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         }
     } else {
         // ===== epilogue (both CTAs: own 64 A-SNPs x the tile's 128 B-SNPs) =====
-        const int ew = warp - 2;
+        const int ew = warp;
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int g = ew >> 2;                        // column group: 64 accumulator columns = 32 B-SNPs
         const int a_loc = 16 * q + (lane >> 1);       // A-SNP of this lane inside the CTA's 64
         const int pl = lane & 1;                      // plane held by this lane's TMEM row (0: aa, 1: bb)
         uint64_t tile_it = 0;
-        for (uint64_t t = first; t < last; t += stride, ++tile_it) {
+        TileCursor cur; cur.locate(first, p.TB, p.n_bands);
+        for (uint64_t t = first; t < last; t += stride, ++tile_it, cur.advance(stride, p.TB, p.n_bands)) {
             uint32_t I2, J;
-            mma_tile_from_index(t, p, I2, J);
+            cur.decode(p.TB, I2, J);
             const uint32_t I = 2 * I2 + rank;         // this CTA's 64-SNP A-block
             const uint32_t buf = (uint32_t)(tile_it & 1);
             const uint64_t gi = (uint64_t)I * MMA_A_SNPS + a_loc;
             // row-role record of this lane's A-SNP. Odd lanes own plane "bb" of A: they see the table with A's
             // genotype labels aa <-> bb exchanged, which the statistic does not depend on, so their record is
             // loaded with the two swapped instead of re-ordering four counts per pair.
-            float2 pca[3], ca[3]; float Crow;
-            load_record(p.row + gi, pca, ca, Crow);
-            if (pl) { float2 x = pca[0]; pca[0] = pca[2]; pca[2] = x; x = ca[0]; ca[0] = ca[2]; ca[2] = x; }
+            MmaRowF A;
+            {
+                const uint4 *rq = reinterpret_cast<const uint4 *>(p.rowf + gi);
+                const uint4 r0 = __ldg(rq), r1 = __ldg(rq + 1), r2 = __ldg(rq + 2), r3 = __ldg(rq + 3);
+                A.dA0 = make_float2(__uint_as_float(r0.x), __uint_as_float(r0.y)); A.dA2 = make_float2(__uint_as_float(r0.z), __uint_as_float(r0.w));
+                A.pca1 = make_float2(__uint_as_float(r1.x), __uint_as_float(r1.y)); A.RA = make_float2(__uint_as_float(r1.z), __uint_as_float(r1.w));
+                A.cm0 = make_float2(__uint_as_float(r2.x), __uint_as_float(r2.y)); A.cm2 = make_float2(__uint_as_float(r2.z), __uint_as_float(r2.w));
+                A.C = __uint_as_float(r3.x);
+                if (pl) { float2 x = A.dA0; A.dA0 = A.dA2; A.dA2 = x; x = A.cm0; A.cm0 = A.cm2; A.cm2 = x; }
+            }
+            const float thrA = p.thr2 + p.q0 + A.C;         // bound pass: N log2 tau + qc Q > thr2 + q0 + C_row + C_col
             // interior tile: every pair is i < j inside the table and no block has missing calls
             const bool interior = (uint64_t)(I + 1) * MMA_A_SNPS <= (uint64_t)J * MMA_B_SNPS && (uint64_t)(J + 1) * MMA_B_SNPS <= p.M &&
                                   !p.tile_missing[I] && !p.tile_missing[2 * J] && !p.tile_missing[2 * J + 1];
@@ -382,13 +463,14 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
             // this warp's 32 column-role records: 2 KiB contiguous in global memory -> its private shared-memory slot
             unsigned char *my_col = col_sm + ew * COL_STAGE_BYTES;
             {
-                const uint4 *src = reinterpret_cast<const uint4 *>(p.col + ((uint64_t)J * MMA_B_SNPS + 32 * g));
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.colf + ((uint64_t)J * MMA_B_SNPS + 32 * g));
                 uint4 *dst = reinterpret_cast<uint4 *>(my_col);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) dst[32 * k + lane] = __ldg(src + 32 * k + lane);
                 __syncwarp();
             }
-            mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
+            if (lane == 0) mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
+            __syncwarp();
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -425,13 +507,18 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1), got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
                     v[4 * s + 0] = keep0; v[4 * s + 1] = keep1; v[4 * s + 2] = got0; v[4 * s + 3] = got1;   // own plane of A first
                     const uint64_t gj = gj0 + 2 * s;
-                    float2 w[3], cb[3]; float Ccol;
-                    load_record_smem(my_col + (16 * h + 2 * s + pl) * 64, w, cb, Ccol);
-                    const Cells t = derive_cells(decode2(keep0), decode2(keep1), decode2(got0), decode2(got1), ca, cb);
-                    float tau;
-                    const float ub = ksa_upper_bound(t, pca, w, Crow + Ccol, p.N, p.qc, p.q0, tau);
+                    float2 b[7]; float Ccol;
+                    {
+                        const uint4 *cq = reinterpret_cast<const uint4 *>(my_col + (16 * h + 2 * s + pl) * 64);
+                        const uint4 r0 = cq[0], r1 = cq[1], r2 = cq[2], r3 = cq[3];
+                        b[0] = make_float2(__uint_as_float(r0.x), __uint_as_float(r0.y)); b[1] = make_float2(__uint_as_float(r0.z), __uint_as_float(r0.w));
+                        b[2] = make_float2(__uint_as_float(r1.x), __uint_as_float(r1.y)); b[3] = make_float2(__uint_as_float(r1.z), __uint_as_float(r1.w));
+                        b[4] = make_float2(__uint_as_float(r2.x), __uint_as_float(r2.y)); b[5] = make_float2(__uint_as_float(r2.z), __uint_as_float(r2.w));
+                        b[6] = make_float2(__uint_as_float(r3.x), __uint_as_float(r3.y)); Ccol = __uint_as_float(r3.z);
+                    }
+                    const float ub = ksa_bound_fast(decode2(keep0), decode2(keep1), decode2(got0), decode2(got1), A, b, p.N, p.qc);
                     const bool valid = interior || (gi < gj && gj < p.M && a_ok && !b_bad);
-                    hot |= (valid && ub > p.thr) ? (1u << s) : 0u;
+                    hot |= (valid && ub > thrA + Ccol) ? (1u << s) : 0u;
                 }
                 // pass 2, rare: exact fp32 formula for the pairs whose bound passed
                 if (!(p.dbg & 16) && __any_sync(0xffffffffu, hot != 0)) {
@@ -444,8 +531,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                         for (int q8 = 1; q8 < 8; ++q8)
                             if (s == q8) { k0 = v[4 * q8]; k1 = v[4 * q8 + 1]; g0 = v[4 * q8 + 2]; g1 = v[4 * q8 + 3]; }
                         const uint64_t gj = gj0 + 2 * s;
-                        float2 w[3], cb[3]; float Ccol;
-                        load_record_smem(my_col + (16 * h + 2 * s + pl) * 64, w, cb, Ccol);
+                        float2 pca[3], ca[3], w[3], cb[3]; float Crow, Ccol;
+                        load_record(p.row + gi, pca, ca, Crow);
+                        if (pl) { float2 x = pca[0]; pca[0] = pca[2]; pca[2] = x; x = ca[0]; ca[0] = ca[2]; ca[2] = x; }
+                        load_record(p.col + gj, w, cb, Ccol);
                         const Cells t = derive_cells(decode2(k0), decode2(k1), decode2(g0), decode2(g1), ca, cb);
                         float tau;
                         (void)ksa_upper_bound(t, pca, w, Crow + Ccol, p.N, p.qc, p.q0, tau);
@@ -465,7 +554,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
 
     tc_fence_before();
     cluster_sync_all();                                // neither CTA leaves while its pair may still touch its SM
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
@@ -501,7 +590,7 @@ __global__ void expand_mma_kernel(const uint32_t *__restrict__ sel, uint32_t sel
 }
 
 __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__ mi, uint64_t M, uint64_t Mrec, uint32_t n_ind,
-                                MmaRow *__restrict__ row, MmaCol *__restrict__ col) {
+                                MmaRow *__restrict__ row, MmaCol *__restrict__ col, MmaRowF *__restrict__ rowf, MmaColF *__restrict__ colf) {
     const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (snp >= Mrec) return;
     MmaRow r; MmaCol c;
@@ -537,11 +626,40 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
         r.cnt[g] = c.cnt[g] = make_float2(cn[0][g], cn[1][g]);
     }
     row[snp] = r; col[snp] = c;
+    // bound-pass records (fp64 differences and dot products, rounded once)
+    MmaRowF rf; MmaColF cf;
+    rf.pad[0] = rf.pad[1] = rf.pad[2] = cf.pad = 0.f;
+    rf.C = r.C; cf.C = c.C;
+    double mp[3], pc[2][3], wc[2][3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        mp[g] = (double)cn[0][g] + (double)cn[1][g];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { pc[k][g] = (double)rp[k][g]; wc[k][g] = (double)cw[k][g]; }
+    }
+    float da0[2], da2[2], ra[2], db0[2], db2[2], rb[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        da0[k] = (float)(pc[k][0] - pc[k][1]); da2[k] = (float)(pc[k][2] - pc[k][1]);
+        ra[k] = (float)(pc[k][0] * mp[0] + pc[k][2] * mp[2] - pc[k][1] * (mp[0] + mp[2]));
+        db0[k] = (float)(wc[k][0] - wc[k][1]); db2[k] = (float)(wc[k][2] - wc[k][1]);
+        // a zero pooled count has w = NaN in the reference's sense (0/0) and n_.b = 0: keep the NaN in RB so that
+        // tau, and with it the bound, is NaN and the pair is dropped exactly like in the exact formula
+        rb[k] = (float)(wc[k][0] * mp[0] + wc[k][1] * mp[1] + wc[k][2] * mp[2]);
+    }
+    rf.dA0 = make_float2(da0[0], da0[1]); rf.dA2 = make_float2(da2[0], da2[1]);
+    rf.pca1 = make_float2(rp[0][1], rp[1][1]); rf.RA = make_float2(ra[0], ra[1]);
+    rf.cm0 = make_float2(cn[0][0], (float)mp[0]); rf.cm2 = make_float2(cn[0][2], (float)mp[2]);
+    cf.dB0 = make_float2(db0[0], db0[1]); cf.dB2 = make_float2(db2[0], db2[1]);
+    cf.w1 = make_float2(cw[0][1], cw[1][1]); cf.RB = make_float2(rb[0], rb[1]);
+    cf.cm0 = make_float2(cn[0][0], (float)mp[0]); cf.cm1 = make_float2(cn[0][1], (float)mp[1]); cf.cm2 = make_float2(cn[0][2], (float)mp[2]);
+    rowf[snp] = rf; colf[snp] = cf;
 }
 
 // fp32 value of the tensor-core engine's epilogue for given pairs (diagnostic twin of screen_probe_kernel)
 __global__ void screen_probe_mma_kernel(const uint32_t *__restrict__ sel, uint32_t stride, uint32_t Wc, uint32_t Wt,
                                         const MmaRow *__restrict__ row, const MmaCol *__restrict__ col,
+                                        const MmaRowF *__restrict__ rowf, const MmaColF *__restrict__ colf,
                                         const uint32_t *__restrict__ pi, const uint32_t *__restrict__ pj, uint64_t n, float N,
                                         float qc, float q0, float *__restrict__ out) {
     const uint64_t qi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -564,9 +682,14 @@ __global__ void screen_probe_mma_kernel(const uint32_t *__restrict__ sel, uint32
     const Cells t = derive_cells(make_float2((float)c[0][0], (float)c[1][0]), make_float2((float)c[0][1], (float)c[1][1]),
                                  make_float2((float)c[0][2], (float)c[1][2]), make_float2((float)c[0][3], (float)c[1][3]), ca, cb);
     float tau;
-    const float ub = ksa_upper_bound(t, pca, w, Crow + Ccol, N, qc, q0, tau);
+    (void)ksa_upper_bound(t, pca, w, Crow + Ccol, N, qc, q0, tau);
     out[2 * qi] = ksa_screen_cells(t, tau, Crow + Ccol, N);
-    out[2 * qi + 1] = ub;
+    // the bound exactly as the screen kernel evaluates it
+    const MmaRowF A = rowf[i]; const MmaColF B = colf[j];
+    const float2 b[7] = {B.dB0, B.dB2, B.w1, B.RB, B.cm0, B.cm1, B.cm2};
+    const float ubf = ksa_bound_fast(make_float2((float)c[0][0], (float)c[1][0]), make_float2((float)c[0][1], (float)c[1][1]),
+                                     make_float2((float)c[0][2], (float)c[1][2]), make_float2((float)c[0][3], (float)c[1][3]), A, b, N, qc);
+    out[2 * qi + 1] = 1.3862943611f * (ubf - q0 - A.C - B.C);
 }
 
 }  // namespace gwasdev
@@ -627,29 +750,26 @@ static int ensure_mma_inputs(gwasdev_store *s) {
         if (!s->tmap_mm && posix_memalign(&s->tmap_mm, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
         int rc;
         if ((rc = make_mm_map(s, 2 * MMA_A_SNPS, (CUtensorMap *)s->tmap_mm)) != GWASDEV_OK) return rc;   // 128-row boxes: a CTA's A rows / its half of B
-        // band table
+        // schedule size: bands of 8 A-blocks (band_offset), the last one possibly shorter
         const uint32_t TB = (uint32_t)(Msnp / MMA_BLK);
         const uint32_t n_bands = (TB + BAND - 1) / BAND;
-        std::vector<uint64_t> off(n_bands + 1, 0);
-        for (uint32_t b = 0; b < n_bands; ++b) {
-            const uint32_t na = band_height(TB, b);
-            uint64_t tiles = 0;
-            for (uint32_t J = BAND * b; J < TB; ++J) tiles += column_height(na, J - BAND * b);
-            off[b + 1] = off[b] + tiles;
+        uint64_t tiles = band_offset(TB, n_bands - 1);
+        {
+            const uint32_t na = band_height(TB, n_bands - 1);
+            for (uint32_t J = BAND * (n_bands - 1); J < TB; ++J) tiles += column_height(na, J - BAND * (n_bands - 1));
         }
-        GW_CUDA(reserve_raw(s->d_band_off, s->cap_band, off.size() * sizeof(uint64_t)));
-        GW_CUDA(cudaMemcpyAsync(s->d_band_off, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
-        GW_CUDA(cudaStreamSynchronize(s->stream));   // `off` is a stack-owned source
-        s->mm_tiles = off[n_bands];
+        s->mm_tiles = tiles;
         bound_constants(s->n_case, s->n_case + s->n_ctrl, &s->mma_qc, &s->mma_q0);
         s->mm_built = true;
     }
     if (!s->mma_side_valid) {
         MmaRow *row = (MmaRow *)s->d_mma_row; MmaCol *col = (MmaCol *)s->d_mma_col;
-        GW_CUDA(reserve_raw(row, s->cap_mma_row, Msnp * sizeof(MmaRow)));
-        GW_CUDA(reserve_raw(col, s->cap_mma_col, Msnp * sizeof(MmaCol)));
+        // exact-pass records followed by the bound-pass records
+        GW_CUDA(reserve_raw(row, s->cap_mma_row, Msnp * (sizeof(MmaRow) + sizeof(MmaRowF))));
+        GW_CUDA(reserve_raw(col, s->cap_mma_col, Msnp * (sizeof(MmaCol) + sizeof(MmaColF))));
         s->d_mma_row = row; s->d_mma_col = col;
-        mma_side_kernel<<<(unsigned)((Msnp + 127) / 128), 128, 0, s->stream>>>(s->d_mi, s->M, Msnp, s->n_case + s->n_ctrl, row, col);
+        mma_side_kernel<<<(unsigned)((Msnp + 127) / 128), 128, 0, s->stream>>>(s->d_mi, s->M, Msnp, s->n_case + s->n_ctrl, row, col,
+                                                                             (MmaRowF *)(row + Msnp), (MmaColF *)(col + Msnp));
         GW_LAUNCHED();
         s->mma_side_valid = true;
     }
@@ -718,10 +838,12 @@ static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
 static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t n_shards) {
     p.TB = (uint32_t)((s->M + MMA_BLK - 1) / MMA_BLK);
     p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M;
-    p.shard = shard; p.n_shards = n_shards; p.band_off = s->d_band_off;
+    p.shard = shard; p.n_shards = n_shards;
+    const uint64_t Msnp = (s->M + MMA_BLK - 1) / MMA_BLK * MMA_BLK;
     p.row = (const MmaRow *)s->d_mma_row; p.col = (const MmaCol *)s->d_mma_col; p.tile_missing = s->d_tile_missing;
+    p.rowf = (const MmaRowF *)(p.row + Msnp); p.colf = (const MmaColF *)(p.col + Msnp);
     p.N = (float)(s->n_case + s->n_ctrl);
-    p.qc = s->mma_qc; p.q0 = s->mma_q0;
+    p.qc = s->mma_qc; p.q0 = s->mma_q0; p.thr2 = 0.f;
     p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0;
     p.dbg = getenv("GWASDEV_MMA_DEBUG") ? (uint32_t)atoi(getenv("GWASDEV_MMA_DEBUG")) : 0u;
 }
@@ -735,7 +857,7 @@ int gwasdev_internal_screen_mma(gwasdev_store *s, float thr, uint32_t shard, uin
     fill_params(s, p, shard, n_shards);
     const uint64_t n_tiles = s->mm_tiles;
     p.n_tiles = n_tiles;
-    p.thr = thr; p.cand = (Candidate *)cand; p.n_cand = n_cand; p.cap = cap;
+    p.thr = thr; p.thr2 = thr / 1.3862943611f; p.cand = (Candidate *)cand; p.n_cand = n_cand; p.cap = cap;
     const uint64_t my_tiles = n_tiles > shard ? (n_tiles - shard + n_shards - 1) / n_shards : 0;
     if (my_tiles == 0) return GWASDEV_OK;
     return launch_mma(s, p, my_tiles);
@@ -765,14 +887,11 @@ int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *
     fill_params(s, p, 0, 1);
     GW_REQUIRE(I / 2 < p.TB && J < p.TB && I / 2 <= J, "gwasdev_mma_tile_counts: tile (%u, %u) is not in the schedule", I, J);
     // linear index of (I, J)
-    std::vector<uint64_t> off(p.n_bands + 1);
-    GW_CUDA(cudaMemcpyAsync(off.data(), s->d_band_off, off.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
-    GW_CUDA(cudaStreamSynchronize(s->stream));
     const uint32_t I2 = I / 2, b = I2 / BAND, na = band_height(p.TB, b);
-    uint64_t t = off[b];
+    uint64_t t = band_offset(p.TB, b);
     for (uint32_t c = 0; c < J - BAND * b; ++c) t += column_height(na, c);
     t += I2 - BAND * b;
-    p.n_tiles = off[p.n_bands];
+    p.n_tiles = s->mm_tiles;
     const size_t bytes = (size_t)MMA_A_SNPS * MMA_B_SNPS * 8 * sizeof(uint32_t);
     GW_CUDA(reserve(s->sc_a, bytes));
     GW_CUDA(cudaMemsetAsync(s->sc_a.p, 0xff, bytes, s->stream));
@@ -794,11 +913,13 @@ int gwasdev_ksa_screen_mma_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi,
     int rc = gwasdev_internal_ensure_side(s);
     if (rc != GWASDEV_OK) return rc;
     if ((rc = ensure_mma_inputs(s)) != GWASDEV_OK) return rc;
+    const uint64_t Msnp = (s->M + MMA_BLK - 1) / MMA_BLK * MMA_BLK;
     GW_CUDA(reserve(s->sc_pi, n * 4)); GW_CUDA(reserve(s->sc_pj, n * 4)); GW_CUDA(reserve(s->sc_a, n * 8));
     GW_CUDA(cudaMemcpyAsync(s->sc_pi.p, pi, n * 4, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->sc_pj.p, pj, n * 4, cudaMemcpyHostToDevice, s->stream));
     screen_probe_mma_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
         s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, (const MmaRow *)s->d_mma_row, (const MmaCol *)s->d_mma_col,
+        (const MmaRowF *)((const MmaRow *)s->d_mma_row + Msnp), (const MmaColF *)((const MmaCol *)s->d_mma_col + Msnp),
         (const uint32_t *)s->sc_pi.p, (const uint32_t *)s->sc_pj.p, n, (float)(s->n_case + s->n_ctrl), s->mma_qc, s->mma_q0,
         (float *)s->sc_a.p);
     GW_LAUNCHED();

@@ -278,7 +278,7 @@ void gwasdev_destroy(gwasdev_store *s) {
     cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
     cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
     free(s->tmap); free(s->tmap_mm);
-    cudaFree(s->d_mm); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col); cudaFree(s->d_band_off);
+    cudaFree(s->d_mm); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col);
     for (gwasdev_store::Scratch *sc : {&s->sc_out_counts, &s->sc_out_stats, &s->sc_out_mi, &s->sc_cnt, &s->sc_cand, &s->sc_keys,
                                       &s->sc_keys2, &s->sc_vals, &s->sc_vals2, &s->sc_sort, &s->sc_hits, &s->sc_pi, &s->sc_pj,
                                       &s->sc_a, &s->sc_b, &s->sc_stage})

@@ -15,7 +15,10 @@ ap.add_argument("--samples", type=int, default=4000)
 ap.add_argument("--cases", type=int, default=0)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--shards", type=int, default=1)
+ap.add_argument("--lib", default="", help="alternative libgwasdev.so (A/B timing of kernel variants)")
 a = ap.parse_args()
+if a.lib:
+    gw.LIB_PATH = os.path.abspath(a.lib)
 ncase = a.cases or a.samples // 2
 with gw.GenoStore(a.snps, a.samples) as st:
     st.simulate(20121127)
