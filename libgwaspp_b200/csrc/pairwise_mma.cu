@@ -98,6 +98,8 @@ struct MmaParams {
     uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only, rows of CTA `dump_rank`
     uint64_t dump_tile;
     uint32_t dump_rank;
+    unsigned long long *prof;   // GWASDEV_MMA_PROF: per CTA {mma busy, mma waiting for tempty, mma waiting for full, epilogue busy,
+                                // epilogue waiting for tfull, producer waiting for empty, tiles} in SM clocks (warp 0 / role threads)
     uint32_t dbg;               // GWASDEV_MMA_DEBUG (timing diagnostics, results invalid): 1 epilogue only hand-shakes, 2 epilogue loads TMEM
                                 // but skips the math, 4 no MMAs issued, 16 no exact pass, 32 no TMA loads
 };
@@ -376,6 +378,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         // ===== TMA producer (both CTAs: own 128 A rows, own half of the 256 B rows) =====
         if (lane == 0) {
             uint64_t it = 0;
+            long long prof_pw = 0;
             TileCursor cur; cur.locate(first, p.TB, p.n_bands);
             for (uint64_t t = first; t < last; t += stride, cur.advance(stride, p.TB, p.n_bands)) {
                 uint32_t I2, J;
@@ -384,7 +387,9 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
                     const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
+                    const long long w0 = clock64();
                     mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
+                    prof_pw += clock64() - w0;
                     unsigned char *dst = sm + st * STAGE_BYTES_MMA;
                     if (p.dbg & 32) { if (rank == 0) mbar_arrive(&full[st]); else mbar_arrive_remote(&full[st], 0); continue; }
                     if (rank == 0) mbar_expect_tx(&full[st], nk * 2 * KB_BYTES);
@@ -395,20 +400,27 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     }
                 }
             }
+            if (p.prof) p.prof[blockIdx.x * 8 + 5] = (unsigned long long)prof_pw;
         }
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer (leader CTA only) =====
         if (lane == 0 && rank == 0) {
             uint64_t it = 0, tile_it = 0;
+            long long prof_te = 0, prof_fu = 0;
+            const long long prof_t0 = clock64();
             for (uint64_t t = first; t < last; t += stride, ++tile_it) {
                 const uint32_t buf = (uint32_t)(tile_it & 1);
+                const long long w0 = clock64();
                 mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
+                prof_te += clock64() - w0;
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + buf * ACC_COLS;
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
                     const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
+                    const long long w1 = clock64();
                     mbar_wait_wd(&full[st], (uint32_t)((it / MMA_STAGES) & 1));
+                    prof_fu += clock64() - w1;
                     tc_fence_after();
                     if (!(p.dbg & 4))
                     for (uint32_t k2 = 0; k2 < nk; ++k2) {
@@ -422,6 +434,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 }
                 tc_commit_mc(&tfull[buf], 3);         // accumulator complete in both CTAs
             }
+            if (p.prof) {
+                unsigned long long *o = p.prof + blockIdx.x * 8;
+                o[0] = (unsigned long long)(clock64() - prof_t0); o[1] = (unsigned long long)prof_te; o[2] = (unsigned long long)prof_fu; o[6] = tile_it;
+            }
         }
     } else {
         // ===== epilogue (both CTAs: own 64 A-SNPs x the tile's 128 B-SNPs) =====
@@ -431,6 +447,8 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         const int a_loc = 16 * q + (lane >> 1);       // A-SNP of this lane inside the CTA's 64
         const int pl = lane & 1;                      // plane held by this lane's TMEM row (0: aa, 1: bb)
         uint64_t tile_it = 0;
+        long long prof_tw = 0;
+        const long long prof_e0 = clock64();
         TileCursor cur; cur.locate(first, p.TB, p.n_bands);
         for (uint64_t t = first; t < last; t += stride, ++tile_it, cur.advance(stride, p.TB, p.n_bands)) {
             uint32_t I2, J;
@@ -469,8 +487,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 for (int k = 0; k < 4; ++k) dst[32 * k + lane] = __ldg(src + 32 * k + lane);
                 __syncwarp();
             }
+            const long long w2 = clock64();
             if (lane == 0) mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
             __syncwarp();
+            prof_tw += clock64() - w2;
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -531,10 +551,16 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                         for (int q8 = 1; q8 < 8; ++q8)
                             if (s == q8) { k0 = v[4 * q8]; k1 = v[4 * q8 + 1]; g0 = v[4 * q8 + 2]; g1 = v[4 * q8 + 3]; }
                         const uint64_t gj = gj0 + 2 * s;
-                        float2 pca[3], ca[3], w[3], cb[3]; float Crow, Ccol;
-                        load_record(p.row + gi, pca, ca, Crow);
-                        if (pl) { float2 x = pca[0]; pca[0] = pca[2]; pca[2] = x; x = ca[0]; ca[0] = ca[2]; ca[2] = x; }
-                        load_record(p.col + gj, w, cb, Ccol);
+                        // the exact-pass operands, rebuilt from the bound-pass records already on chip (no global loads):
+                        // pca[g] = dA_g + pca[1], w[g] = dB_g + w[1], control count = pooled - case
+                        const MmaColF &B = *reinterpret_cast<const MmaColF *>(my_col + (16 * h + 2 * s + pl) * 64);
+                        float2 pca[3], ca[3], w[3], cb[3];
+                        pca[1] = A.pca1; pca[0] = __fadd2_rn(A.dA0, A.pca1); pca[2] = __fadd2_rn(A.dA2, A.pca1);
+                        ca[0] = make_float2(A.cm0.x, A.cm0.y - A.cm0.x); ca[2] = make_float2(A.cm2.x, A.cm2.y - A.cm2.x); ca[1] = ca[0];
+                        w[1] = B.w1; w[0] = __fadd2_rn(B.dB0, B.w1); w[2] = __fadd2_rn(B.dB2, B.w1);
+                        cb[0] = make_float2(B.cm0.x, B.cm0.y - B.cm0.x); cb[1] = make_float2(B.cm1.x, B.cm1.y - B.cm1.x);
+                        cb[2] = make_float2(B.cm2.x, B.cm2.y - B.cm2.x);
+                        const float Crow = A.C, Ccol = B.C;
                         const Cells t = derive_cells(decode2(k0), decode2(k1), decode2(g0), decode2(g1), ca, cb);
                         float tau;
                         (void)ksa_upper_bound(t, pca, w, Crow + Ccol, p.N, p.qc, p.q0, tau);
@@ -549,6 +575,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tempty[buf], 0);
+        }
+        if (p.prof && lane == 0 && (warp == 0 || warp == 15)) {
+            unsigned long long *o = p.prof + blockIdx.x * 8;
+            o[warp == 0 ? 3 : 7] = (unsigned long long)(clock64() - prof_e0); if (warp == 0) o[4] = (unsigned long long)prof_tw;
         }
     }
 
@@ -830,8 +860,27 @@ static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
     const size_t smem = mma_smem_bytes();
     GW_CUDA(cudaFuncSetAttribute(pair_screen_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));   // one CTA pair per TPC
+    const bool prof = getenv("GWASDEV_MMA_PROF") != nullptr && !p.dump;
+    unsigned long long *d_prof = nullptr;
+    if (prof) {
+        GW_CUDA(cudaMalloc(&d_prof, (size_t)2 * pairs * 8 * sizeof(unsigned long long)));
+        GW_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)2 * pairs * 8 * sizeof(unsigned long long), s->stream));
+    }
+    p.prof = d_prof;
     pair_screen_mma_kernel<<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm, p);
     GW_LAUNCHED();
+    if (prof) {
+        std::vector<unsigned long long> h((size_t)2 * pairs * 8);
+        GW_CUDA(cudaMemcpyAsync(h.data(), d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        GW_CUDA(cudaStreamSynchronize(s->stream));
+        cudaFree(d_prof);
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (unsigned c = 0; c < 2 * pairs; ++c) for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)c * 8 + k];
+        const double nl = pairs, nc = 2.0 * pairs, tiles = a[6] / nl;
+        fprintf(stderr, "[gwasdev mma prof] per tile (SM clocks): mma thread %.0f (waits tempty %.0f, full %.0f) | epilogue warp0 %.0f warp15 %.0f "
+                        "(waits tfull %.0f) | producer waits empty %.0f | tiles per pair %.0f\n",
+                a[0] / nl / tiles, a[1] / nl / tiles, a[2] / nl / tiles, a[3] / nc / tiles, a[7] / nc / tiles, a[4] / nc / tiles, a[5] / nc / tiles, tiles);
+    }
     return GWASDEV_OK;
 }
 
@@ -844,7 +893,7 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
     p.rowf = (const MmaRowF *)(p.row + Msnp); p.colf = (const MmaColF *)(p.col + Msnp);
     p.N = (float)(s->n_case + s->n_ctrl);
     p.qc = s->mma_qc; p.q0 = s->mma_q0; p.thr2 = 0.f;
-    p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0;
+    p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0; p.prof = nullptr;
     p.dbg = getenv("GWASDEV_MMA_DEBUG") ? (uint32_t)atoi(getenv("GWASDEV_MMA_DEBUG")) : 0u;
 }
 
