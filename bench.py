@@ -8,10 +8,13 @@ allelic + genotypic chi-square -- with the store resident in HBM; roofline = HBM
 the C-ABI with HOST buffers: case/control masks from host memory -> compaction (K0) -> scan (K1) ->
 counts + statistics copied back to pinned host memory, every step.
 `pairwise`: the exhaustive SNP x SNP screen (configs[2], 2 000/2 000 x 50 000 SNPs = 1 249 975 000 pairs)
-in pairs/s with its integer-popcount roofline, its own e2e (computeBoost call surface) and CPU baseline.
+in pairs/s. Its roofline fraction stays defined on the integer-popcount formula (4 AND+POPC
+word-cells per 32 samples per pair) whichever engine runs; since the tensor-core engine (tcgen05 kind::i8) does the
+same counting as a GEMM, that fraction exceeds 1 and a second object, `roofline.tensor`, gives the int8 MAC rate
+against the tensor-core peak. Plus its own e2e (computeBoost call surface) and CPU baseline.
 
 N > 1 (torchrun): weak scaling for the marginal scan (each rank scans its own 500 000-SNP shard, no
-collective on the data path); the pairwise screen shards tile pairs round-robin over the ranks and
+collective on the data path); the pairwise screen shards tile pairs in chunks over the ranks and
 all-gathers the hit lists over NCCL inside the timed region.
 
 --impl reference: the reference's own CPU implementation (oracle/_ref, the unmodified sources) on all
@@ -254,11 +257,11 @@ def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max
     barrier()
     l0, t0 = gw.launch_count(), time.perf_counter()
     ev0.record(stream)
-    screen_ms, pairs, cells, n_hits, cand = [], 0, 0, 0, 0
+    screen_ms, pairs, cells, n_hits, cand, engine = [], 0, 0, 0, 0, 0
     for _ in range(K):
         n_hits, s = step()
         screen_ms.append(s.screen_ms)
-        pairs, cells, cand = s.pairs_tested, s.word_cells, s.candidates
+        pairs, cells, cand, engine = s.pairs_tested, s.word_cells, s.candidates, s.engine
     ev1.record(stream)
     barrier()
     t1, launches = time.perf_counter(), gw.launch_count() - l0
@@ -268,18 +271,29 @@ def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max
     k_ms = float(np.mean(screen_ms))
     peak_cells, clk = gw.popc_peak(local)
     achieved = cells / (k_ms * 1e-3)
+    peaks, peak_src = measured_peaks()
+    # tensor-core view of the same launch: one int8 MAC per (cell, sample), 4 cells per pair
+    macs = float(pairs) * 4.0 * N
+    tensor_peak = 2.0 * float(peaks.get("bf16_tflops", 1590.0))      # int8 runs at twice the bf16 rate on the same datapath
+    tensor = {"bound": "tensor", "achieved": round(2.0 * macs / (k_ms * 1e-3) / 1e12, 1), "peak": round(tensor_peak, 1),
+              "unit": "TOP/s (int8, 2 ops per MAC)", "frac": round(2.0 * macs / (k_ms * 1e-3) / 1e12 / tensor_peak, 4),
+              "peak_source": f"2 x bf16_tflops of {peak_src} (nominal int8 dense 4 500)",
+              "algorithmic_macs_per_launch": int(macs)}
+    kernel = {2: "pair_screen_mma_kernel (tcgen05.mma cta_group::2 kind::i8)", 1: "pair_screen_kernel<false> (AND+POPC)"}.get(engine, "?")
     res = {
         "metric": "pairwise SNP x SNP tests/sec", "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": round(ms_per_step, 3), "scaling": "strong", "hits": int(n_hits), "candidates": int(cand),
         "config": {"workload": f"configs[2]: exhaustive pairwise epistasis {NCASE}/{N - NCASE} samples x {M} SNPs "
                                f"({M * (M - 1) // 2} pairs), 3x3x2 contingency + KSA statistic, threshold 30",
-                   "parallelism": f"64x64 SNP tile pairs dealt round-robin over {world} rank(s); NCCL all_gather of hits"},
+                   "engine": {2: "tensor cores", 1: "AND+POPC"}.get(engine, "?"),
+                   "parallelism": f"128x128 SNP tile pairs dealt in chunks of 64 over {world} rank(s); NCCL all_gather of hits"},
         "roofline": {"bound": "int_popc", "achieved": round(achieved / 1e12, 4), "peak": round(peak_cells / 1e12, 4),
                      "unit": "T word-cells/s (32-bit AND+POPC)", "frac": round(achieved / peak_cells, 4), "traffic": None,
-                     "kernel": "pair_screen_kernel<false>", "kernel_ms": round(k_ms, 3),
+                     "kernel": kernel, "kernel_ms": round(k_ms, 3),
                      "peak_source": f"register-only __popc microbenchmark run in this process (clock attr {clk:.0f} MHz); "
                                     "nominal 148 SMs x 16 POPC/clk x 1.965 GHz = 4.65",
-                     "algorithmic_word_cells_per_launch": int(cells)},
+                     "algorithmic_word_cells_per_launch": int(cells),
+                     "tensor": tensor if engine == 2 else None},
         "gpu_launches": int(launches),
         "clocks": sampler.window(t0, t1) if rank == 0 else None,
     }

@@ -150,9 +150,11 @@ GWASDEV_API int gwasdev_pair_tables(gwasdev_store *s, uint64_t n, const uint32_t
                         uint32_t *out);
 
 /* ---- exhaustive pairwise screen (K2+K3+K5) -------------------------------------------------- */
-/* computeBoost's pre-screening loop (algorithms/epistasis_func.cpp:397-486) over every pair i<j whose
- * 64x64 SNP tile pair belongs to this shard (tile pairs are dealt round-robin: tile t is handled when
- * t % n_shards == shard). Writes the pairs with stat > threshold, sorted by (i, j), into hits[0..*n_hits).
+/* computeBoost's pre-screening loop (algorithms/epistasis_func.cpp:397-486) over every pair i<j whose SNP tile
+ * pair belongs to this shard. The pair space is cut into tile pairs (128x128 SNPs for the tensor-core engine,
+ * 64x64 for the AND+POPC engine) in a fixed linear order; shards own alternating runs of that order (runs of 64
+ * tiles, resp. single tiles), so the n_shards calls with shard = 0..n_shards-1 cover every pair exactly once.
+ * Writes the pairs with stat > threshold, sorted by (i, j), into hits[0..*n_hits).
  * hits / on_device as for the marginal scan. Requires gwasdev_select_case_control; computes the margins
  * itself when gwasdev_marginal_scan has not been run over all SNPs. */
 GWASDEV_API int gwasdev_pairwise_scan(gwasdev_store *s, double threshold, uint32_t shard, uint32_t n_shards,

@@ -186,6 +186,20 @@ constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(M
 __host__ __device__ inline uint32_t band_height(uint32_t TB, uint32_t b) { return min((uint32_t)BAND, TB - BAND * b); }
 __host__ __device__ inline uint32_t column_height(uint32_t na, uint32_t c) { return min(na, c + 1); }
 
+// Schedule index of the u-th tile of a shard: shards take turns in chunks of SHARD_CHUNK consecutive tiles.
+constexpr uint32_t SHARD_CHUNK = 64;
+__host__ __device__ inline uint64_t shard_tile(uint64_t u, uint32_t shard, uint32_t n_shards) {
+    return ((u / SHARD_CHUNK) * n_shards + shard) * SHARD_CHUNK + u % SHARD_CHUNK;
+}
+__host__ __device__ inline bool tile_in_shard(uint64_t t, uint32_t shard, uint32_t n_shards) { return (t / SHARD_CHUNK) % n_shards == shard; }
+// number of tiles of the shard among the first n tiles of the schedule
+__host__ __device__ inline uint64_t shard_tiles_before(uint64_t n, uint32_t shard, uint32_t n_shards) {
+    const uint64_t chunk = n / SHARD_CHUNK, rem = n % SHARD_CHUNK;
+    uint64_t cnt = (chunk / n_shards) * SHARD_CHUNK + (chunk % n_shards > shard ? SHARD_CHUNK : 0);
+    if (chunk % n_shards == shard) cnt += rem;
+    return cnt;
+}
+
 // Tiles before band b. Every band before the last is full (8 A-blocks, at least 8 columns): 8 (TB - 8b') - 28 tiles.
 __host__ __device__ inline uint64_t band_offset(uint32_t TB, uint64_t b) {
     return b * ((uint64_t)BAND * TB) - (uint64_t)(BAND * BAND) * (b * (b - 1) / 2) - b * (uint64_t)(BAND * (BAND - 1) / 2);
@@ -370,8 +384,11 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint64_t stride = (uint64_t)p.n_shards * n_pairs;
-    const uint64_t first = p.dump ? p.dump_tile : p.shard + (uint64_t)p.n_shards * pair_id;
+    // This CTA pair's tiles: local indices u = pair_id, pair_id + n_pairs, ... of the shard; shard_tile(u) is the schedule
+    // index. Shards own alternating chunks of SHARD_CHUNK consecutive tiles, so that the tiles a GPU works on at the
+    // same time share A- and B-blocks in its L2 whatever the number of GPUs.
+    const uint64_t u_first = p.dump ? 0 : pair_id, u_step = p.dump ? 1 : n_pairs;
+    const uint64_t first = p.dump ? p.dump_tile : shard_tile(u_first, p.shard, p.n_shards);
     const uint64_t last = p.dump ? p.dump_tile + 1 : p.n_tiles;
 
     if (warp == TMA_WARP) {
@@ -380,9 +397,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
             uint64_t it = 0;
             long long prof_pw = 0;
             TileCursor cur; cur.locate(first, p.TB, p.n_bands);
-            for (uint64_t t = first; t < last; t += stride, cur.advance(stride, p.TB, p.n_bands)) {
+            for (uint64_t t = first, u = u_first; t < last;) {
                 uint32_t I2, J;
                 cur.decode(p.TB, I2, J);
+                { u += u_step; const uint64_t tn = p.dump ? last : shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
                 const int a_row = (int)((2 * I2 + rank) * (2 * MMA_A_SNPS)), b_row = (int)(J * MMA_N + rank * MMA_B_SNPS);
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
@@ -408,7 +426,8 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
             uint64_t it = 0, tile_it = 0;
             long long prof_te = 0, prof_fu = 0;
             const long long prof_t0 = clock64();
-            for (uint64_t t = first; t < last; t += stride, ++tile_it) {
+            for (uint64_t t = first, u = u_first; t < last; ++tile_it) {
+                { u += u_step; t = p.dump ? last : shard_tile(u, p.shard, p.n_shards); }
                 const uint32_t buf = (uint32_t)(tile_it & 1);
                 const long long w0 = clock64();
                 mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
@@ -450,9 +469,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         long long prof_tw = 0;
         const long long prof_e0 = clock64();
         TileCursor cur; cur.locate(first, p.TB, p.n_bands);
-        for (uint64_t t = first; t < last; t += stride, ++tile_it, cur.advance(stride, p.TB, p.n_bands)) {
+        for (uint64_t t = first, u = u_first; t < last; ++tile_it) {
             uint32_t I2, J;
             cur.decode(p.TB, I2, J);
+            { u += u_step; const uint64_t tn = p.dump ? last : shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
             const uint32_t I = 2 * I2 + rank;         // this CTA's 64-SNP A-block
             const uint32_t buf = (uint32_t)(tile_it & 1);
             const uint64_t gi = (uint64_t)I * MMA_A_SNPS + a_loc;
@@ -826,13 +846,14 @@ uint64_t gwasdev_internal_mma_shard_pairs(const gwasdev_store *s, uint32_t shard
         for (uint32_t J = BAND * b; J < TB; ++J) {
             const uint32_t h = column_height(na, J - BAND * b);
             const uint64_t j0 = (uint64_t)J * MMA_BLK, j1 = std::min<uint64_t>(j0 + MMA_BLK, M);
-            // tiles t .. t+h-1 are A-blocks I2 = 8b + ii of this column; those of the shard: (t + ii) % n_shards == shard
+            // tiles t .. t+h-1 are A-blocks I2 = 8b + ii of this column; those of the shard: tile_in_shard(t + ii)
+            const uint64_t cnt = shard_tiles_before(t + h, shard, n_shards) - shard_tiles_before(t, shard, n_shards);
             const bool simple = !flags && (uint64_t)(BAND * b + h) * MMA_BLK <= j0;     // full rectangles left of the B-block
-            uint32_t ii = (uint32_t)((shard + n_shards - t % n_shards) % n_shards);
-            if (simple) {
-                if (ii < h) { const uint64_t cnt = (h - 1 - ii) / n_shards + 1; tiles += cnt; pairs += cnt * MMA_BLK * (j1 - j0); }
-            } else {
-                for (; ii < h; ii += n_shards) {
+            if (cnt == 0) { t += h; continue; }
+            if (simple) { tiles += cnt; pairs += cnt * MMA_BLK * (j1 - j0); }
+            else {
+                for (uint32_t ii = 0; ii < h; ++ii) {
+                    if (!tile_in_shard(t + ii, shard, n_shards)) continue;
                     const uint64_t I2 = BAND * b + ii;
                     ++tiles;
                     if (!flags) pairs += rect_pairs(M, I2 * MMA_BLK, (I2 + 1) * MMA_BLK, j0, j0 + MMA_BLK);
@@ -907,7 +928,7 @@ int gwasdev_internal_screen_mma(gwasdev_store *s, float thr, uint32_t shard, uin
     const uint64_t n_tiles = s->mm_tiles;
     p.n_tiles = n_tiles;
     p.thr = thr; p.thr2 = thr / 1.3862943611f; p.cand = (Candidate *)cand; p.n_cand = n_cand; p.cap = cap;
-    const uint64_t my_tiles = n_tiles > shard ? (n_tiles - shard + n_shards - 1) / n_shards : 0;
+    const uint64_t my_tiles = shard_tiles_before(n_tiles, shard, n_shards);
     if (my_tiles == 0) return GWASDEV_OK;
     return launch_mma(s, p, my_tiles);
 }

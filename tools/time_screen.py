@@ -27,3 +27,14 @@ with gw.GenoStore(a.snps, a.samples) as st:
         hits, s = st.pairwise_scan(30.0, shard=0, n_shards=a.shards)
         print(f"rep {r}: engine {s.engine} screen {s.screen_ms:.3f} ms total {s.total_ms:.3f} ms pairs {s.pairs_tested} "
               f"-> {s.pairs_tested / s.screen_ms / 1e6:.2f} G pairs/s, candidates {s.candidates}, hits {s.hits}", flush=True)
+    # phases of the computeBoost call surface with host buffers (what bench.py's pairwise e2e times)
+    import time
+    pheno = gw.simulate_phenotype(20121127, a.samples, ncase)
+    cm, tm = gw.stream_masks(pheno)
+    for r in range(3):
+        t0 = time.perf_counter(); st.select_case_control(case_mask=cm, ctrl_mask=tm); st.synchronize()
+        t1 = time.perf_counter(); hits, s = st.pairwise_scan(30.0, shard=0, n_shards=a.shards)
+        t2 = time.perf_counter(); g = st.gtest(hits["i"], hits["j"]) if len(hits) else None
+        t3 = time.perf_counter()
+        print(f"e2e rep {r}: select {1e3 * (t1 - t0):.2f} ms, pairwise_scan {1e3 * (t2 - t1):.2f} ms (screen {s.screen_ms:.2f}), "
+              f"gtest {1e3 * (t3 - t2):.2f} ms", flush=True)
