@@ -498,6 +498,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
             const bool b_bad0 = (uint64_t)(2 * J) * TILE >= p.M || p.tile_missing[2 * J];
             const bool b_bad1 = (uint64_t)(2 * J + 1) * TILE >= p.M || p.tile_missing[2 * J + 1];
             const bool b_bad = g < 2 ? b_bad0 : b_bad1;           // this warp's 32 B-SNPs lie in one half
+            const bool edge_ok = a_ok && !b_bad;
             // this warp's 32 column-role records: 2 KiB contiguous in global memory -> its private shared-memory slot
             unsigned char *my_col = col_sm + ew * COL_STAGE_BYTES;
             {
@@ -557,8 +558,8 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                         b[6] = make_float2(__uint_as_float(r3.x), __uint_as_float(r3.y)); Ccol = __uint_as_float(r3.z);
                     }
                     const float ub = ksa_bound_fast(decode2(keep0), decode2(keep1), decode2(got0), decode2(got1), A, b, p.N, p.qc);
-                    const bool valid = interior || (gi < gj && gj < p.M && a_ok && !b_bad);
-                    hot |= (valid && ub > thrA + Ccol) ? (1u << s) : 0u;
+                    const bool valid = interior | ((gi < gj) & (gj < p.M) & edge_ok);      // no short-circuit: keeps the pass branch-free
+                    hot |= (valid & (ub > thrA + Ccol)) ? (1u << s) : 0u;
                 }
                 // pass 2, rare: exact fp32 formula for the pairs whose bound passed
                 if (!(p.dbg & 16) && __any_sync(0xffffffffu, hot != 0)) {
