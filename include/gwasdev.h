@@ -94,6 +94,11 @@ GWASDEV_API uint32_t gwasdev_plane_blocks(uint32_t n);
  * (common_genotype.h:257-304). row receives [hdr][plane1: P][plane2: P] 16-bit blocks, P =
  * gwasdev_plane_blocks(n_samples). Returns GWASDEV_EINVAL where the reference would abort. */
 GWASDEV_API int gwasdev_pack_row_text(const char *txt, size_t len, uint32_t n_samples, uint16_t *row);
+/* The same for one sample block of a row that is loaded in several blocks (streaming, see
+ * gwasdev_marginal_accumulate): *label_state carries the row's header word from block to block (0 before the
+ * first block), so that genotype labels stay first-seen over the whole row as in the reference. */
+GWASDEV_API int gwasdev_pack_row_text_block(const char *txt, size_t len, uint32_t n_samples, uint16_t *row,
+                                uint16_t *label_state);
 /* Upload / download n_rows rows in that layout (row stride 2P+1 blocks, host memory). */
 GWASDEV_API int gwasdev_put_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, const uint16_t *rows);
 GWASDEV_API int gwasdev_get_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint16_t *rows);
@@ -104,6 +109,10 @@ GWASDEV_API int gwasdev_call_at(gwasdev_store *s, uint64_t row, uint32_t col, ch
  * over one panel of data/maf_spectrum.tab (bin_counts[b] = SNP count at MAF b %). missing_q32/2^32
  * is the per-genotype missing probability. Labels are first-seen, as the text loader would give. */
 GWASDEV_API int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[51], uint32_t missing_q32);
+/* One sample block of that cohort: the store holds samples [first_sample, first_sample + n_samples) of a cohort of
+ * n_total_samples; draws and first-seen labels are those of the whole-cohort table. */
+GWASDEV_API int gwasdev_simulate_block(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[51], uint32_t missing_q32,
+                           uint32_t first_sample, uint32_t n_total_samples);
 /* Host helper: exactly n_case cases (1) among n_samples, the rest controls (0). */
 GWASDEV_API int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, uint32_t n_case, uint8_t *pheno);
 
@@ -128,6 +137,16 @@ GWASDEV_API int gwasdev_get_selected_rows(gwasdev_store *s, uint64_t first_row, 
  * on_device = 0: outputs are host buffers (copied back inside the call); 1: device buffers. */
 GWASDEV_API int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *counts,
                           gwasdev_marginal_information *mi, gwasdev_snp_stats *stats, int on_device);
+/* Streaming in sample blocks (BASELINE configs[4]): genotype counts are additive over disjoint sample blocks, which the
+ * reference cannot exploit (its rows are always whole: compressed_genotype_table5.cpp:703-747 walks one compacted row).
+ * A store holding one block of samples (loaded with label state carried over, or gwasdev_simulate_block) adds its
+ * case/control counts of SNPs [snp_begin, snp_end) into acc (8 per SNP, device buffer when on_device); after the last
+ * block gwasdev_marginal_finalize computes marginal_information (computeMarginalInformation,
+ * genotype/common_genotype_func.cpp:173-219) and the statistics from the summed counts -- bit-identical to one scan
+ * over the whole cohort. */
+GWASDEV_API int gwasdev_marginal_accumulate(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *acc, int on_device);
+GWASDEV_API int gwasdev_marginal_finalize(int device, uint64_t n_snps, const uint32_t *counts, gwasdev_marginal_information *mi,
+                              gwasdev_snp_stats *stats, int on_device);
 /* Device time (ms, CUDA events) of the scan kernel inside the last gwasdev_marginal_scan call. */
 GWASDEV_API double gwasdev_last_scan_ms(gwasdev_store *s);
 

@@ -49,7 +49,8 @@ ABI_SYMBOLS = [
     "gwasdev_marginal_scan", "gwasdev_last_scan_ms", "gwasdev_counts", "gwasdev_pair_tables",
     "gwasdev_pairwise_scan", "gwasdev_ksa", "gwasdev_ksa_screen_f32", "gwasdev_gtest", "gwasdev_pairwise_epi_test",
     "gwasdev_popc_peak", "gwasdev_hbm_read_peak", "gwasdev_set_pair_engine", "gwasdev_mma_tile_counts",
-    "gwasdev_ksa_screen_mma_f32",
+    "gwasdev_ksa_screen_mma_f32", "gwasdev_pack_row_text_block", "gwasdev_simulate_block", "gwasdev_marginal_accumulate",
+    "gwasdev_marginal_finalize",
 ]
 
 
@@ -90,6 +91,10 @@ def load_library():
     L.gwasdev_ksa.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_ksa_screen_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_gtest.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.gwasdev_pack_row_text_block.argtypes = [C.c_char_p, C.c_size_t, u32, vp, C.POINTER(C.c_uint16)]
+    L.gwasdev_simulate_block.argtypes = [vp, u64, vp, u32, u32, u32]
+    L.gwasdev_marginal_accumulate.argtypes = [vp, u64, u64, vp, i32]
+    L.gwasdev_marginal_finalize.argtypes = [i32, u64, vp, vp, vp, i32]
     L.gwasdev_set_pair_engine.argtypes = [vp, i32]
     L.gwasdev_mma_tile_counts.argtypes = [vp, u32, u32, vp]
     L.gwasdev_ksa_screen_mma_f32.argtypes = [vp, u64, vp, vp, vp]
@@ -145,6 +150,24 @@ def simulate_phenotype(seed: int, n_samples: int, n_case: int) -> np.ndarray:
     out = np.zeros(n_samples, np.uint8)
     _check(load_library().gwasdev_simulate_phenotype(seed, n_samples, n_case, _ptr(out)), "gwasdev_simulate_phenotype")
     return out
+
+
+def pack_row_text_block(line: bytes, n_samples: int, label_state: int = 0):
+    """One sample block of a text row; returns (row, new label state) -- see gwasdev_pack_row_text_block."""
+    P = plane_blocks(n_samples)
+    row = np.zeros(2 * P + 1, np.uint16)
+    st = C.c_uint16(label_state)
+    _check(load_library().gwasdev_pack_row_text_block(line, len(line), n_samples, _ptr(row), C.byref(st)), "gwasdev_pack_row_text_block")
+    return row, int(st.value)
+
+
+def marginal_finalize(counts: np.ndarray, device: int = 0):
+    """marginal_information + statistics from summed counts [n, 8] (host arrays)."""
+    counts = np.ascontiguousarray(counts, np.uint32)
+    n = counts.shape[0]
+    mi, stats = np.zeros(n, MI_DTYPE), np.zeros(n, STATS_DTYPE)
+    _check(load_library().gwasdev_marginal_finalize(device, n, _ptr(counts), _ptr(mi), _ptr(stats), 0), "gwasdev_marginal_finalize")
+    return mi, stats
 
 
 def popc_peak(device: int = 0) -> tuple[float, float]:
@@ -232,6 +255,12 @@ class GenoStore:
         q = int(missing_rate * 4294967296.0) & 0xFFFFFFFF
         _check(self.L.gwasdev_simulate(self.h, seed, _ptr(bins), q), "gwasdev_simulate")
 
+    def simulate_block(self, seed: int, first_sample: int, n_total_samples: int, panel: str = "affy6", missing_rate: float = 0.0):
+        """This store = samples [first_sample, first_sample + n_samples) of the whole-cohort table of gwasdev_simulate."""
+        bins = np.asarray(MAF_SPECTRUM[panel], np.uint32)
+        q = int(missing_rate * 4294967296.0) & 0xFFFFFFFF
+        _check(self.L.gwasdev_simulate_block(self.h, seed, _ptr(bins), q, first_sample, n_total_samples), "gwasdev_simulate_block")
+
     # -- case/control
     def select_case_control(self, pheno=None, *, case_mask=None, ctrl_mask=None):
         if pheno is not None:
@@ -271,6 +300,12 @@ class GenoStore:
         """Raw-pointer call: buffers are torch tensors / numpy arrays / int addresses (device when on_device)."""
         _check(self.L.gwasdev_marginal_scan(self.h, snp_begin, snp_end, _ptr(counts), _ptr(mi), _ptr(stats),
                                             1 if on_device else 0), "gwasdev_marginal_scan")
+
+    def marginal_accumulate(self, acc, snp_begin: int = 0, snp_end: int | None = None, on_device: bool = False):
+        """acc[8 per SNP] += this sample block's case/control genotype counts (streaming in sample blocks)."""
+        snp_end = self.n_snps if snp_end is None else snp_end
+        _check(self.L.gwasdev_marginal_accumulate(self.h, snp_begin, snp_end, _ptr(acc), 1 if on_device else 0),
+               "gwasdev_marginal_accumulate")
 
     def last_scan_ms(self) -> float:
         return float(self.L.gwasdev_last_scan_ms(self.h))

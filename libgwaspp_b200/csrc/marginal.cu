@@ -217,6 +217,26 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
     }
 }
 
+// Streaming in sample blocks: counts are additive over disjoint sample blocks of one cohort.
+__global__ void add_counts_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ acc, uint64_t n4) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const uint4 a = acc[i], b = src[i];
+    acc[i] = make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+// marginal_information + statistics from finished counts: the scan kernel's own epilogue on given counts
+__global__ void finalize_counts_kernel(const uint32_t *__restrict__ counts, uint64_t n, gwasdev_marginal_information *__restrict__ mi,
+                                       gwasdev_snp_stats *__restrict__ stats) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t ca[4], co[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { ca[g] = counts[8 * i + g]; co[g] = counts[8 * i + 4 + g]; }
+    const uint32_t n_ind = ca[0] + ca[1] + ca[2] + ca[3] + co[0] + co[1] + co[2] + co[3];
+    if (mi) fill_marginal_information(ca, co, n_ind, mi[i]);
+    if (stats) fill_stats(ca, co, stats[i]);
+}
+
 // Counts on the RAW rows, optionally through the case/control stream masks (mask-on-the-fly overloads
 // compressed_genotype_table5.cpp:577-607 and :609-657). One warp per SNP.
 __global__ void raw_counts_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, const uint32_t *__restrict__ mca,
@@ -327,6 +347,66 @@ int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) { set_error("gwasdev_marginal_scan: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     if (mi && full) { s->mi_valid = true; s->side_valid = false; s->mma_side_valid = false; }
+    return GWASDEV_OK;
+}
+
+int gwasdev_marginal_accumulate(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *acc, int on_device) {
+    GW_REQUIRE(s && acc, "gwasdev_marginal_accumulate: NULL argument");
+    GW_REQUIRE(s->selected, "gwasdev_marginal_accumulate: call gwasdev_select_case_control first");
+    GW_REQUIRE(snp_begin <= snp_end && snp_end <= s->M, "gwasdev_marginal_accumulate: bad SNP range [%llu, %llu)",
+               (unsigned long long)snp_begin, (unsigned long long)snp_end);
+    if (snp_begin == snp_end) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint64_t n = snp_end - snp_begin;
+    GW_CUDA(reserve(s->sc_out_counts, n * 8 * sizeof(uint32_t)));
+    uint32_t *d_counts = (uint32_t *)s->sc_out_counts.p, *d_acc = acc;
+    int rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, nullptr, nullptr);
+    if (rc != GWASDEV_OK) return rc;
+    if (!on_device) {
+        GW_CUDA(reserve(s->sc_stage, n * 8 * sizeof(uint32_t)));
+        d_acc = (uint32_t *)s->sc_stage.p;
+        GW_CUDA(cudaMemcpyAsync(d_acc, acc, n * 8 * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    }
+    add_counts_kernel<<<(unsigned)((2 * n + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<const uint4 *>(d_counts),
+                                                                              reinterpret_cast<uint4 *>(d_acc), 2 * n);
+    GW_LAUNCHED();
+    if (!on_device) {
+        GW_CUDA(cudaMemcpyAsync(acc, d_acc, n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        GW_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    return GWASDEV_OK;
+}
+
+int gwasdev_marginal_finalize(int device, uint64_t n_snps, const uint32_t *counts, gwasdev_marginal_information *mi,
+                              gwasdev_snp_stats *stats, int on_device) {
+    GW_REQUIRE(counts && (mi || stats), "gwasdev_marginal_finalize: NULL argument");
+    if (gwasdev_device_count() <= device || device < 0) { set_error("gwasdev_marginal_finalize: no CUDA device %d", device); return GWASDEV_ENODEVICE; }
+    if (n_snps == 0) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(device));
+    const uint32_t *d_counts = counts;
+    uint32_t *tmp_counts = nullptr;
+    gwasdev_marginal_information *d_mi = mi;
+    gwasdev_snp_stats *d_stats = stats;
+    cudaError_t e = cudaSuccess;
+    if (!on_device) {
+        e = cudaMalloc(&tmp_counts, n_snps * 8 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemcpy(tmp_counts, counts, n_snps * 8 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+        d_counts = tmp_counts; d_mi = nullptr; d_stats = nullptr;
+        if (e == cudaSuccess && mi) e = cudaMalloc(&d_mi, n_snps * sizeof *mi);
+        if (e == cudaSuccess && stats) e = cudaMalloc(&d_stats, n_snps * sizeof *stats);
+    }
+    if (e == cudaSuccess) {
+        finalize_counts_kernel<<<(unsigned)((n_snps + 127) / 128), 128>>>(d_counts, n_snps, d_mi, d_stats);
+        ++g_launches;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (!on_device) {
+        if (e == cudaSuccess && mi) e = cudaMemcpy(mi, d_mi, n_snps * sizeof *mi, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && stats) e = cudaMemcpy(stats, d_stats, n_snps * sizeof *stats, cudaMemcpyDeviceToHost);
+        cudaFree(tmp_counts); if (mi) cudaFree(d_mi); if (stats) cudaFree(d_stats);
+    }
+    if (e != cudaSuccess) { set_error("gwasdev_marginal_finalize: %s", cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? GWASDEV_ENOMEM : GWASDEV_ENODEVICE; }
     return GWASDEV_OK;
 }
 

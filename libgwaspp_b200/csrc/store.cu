@@ -161,9 +161,11 @@ __global__ void export_selected_kernel(const uint32_t *__restrict__ sel, uint32_
     }
 }
 
-// Synthetic cohort, one thread per SNP (sequential selection sampling over the 2N allele slots).
-// Distribution restated from data/simulate_data.cpp:160-207; see DESIGN.md "synthetic cohort".
-__global__ void simulate_kernel(uint64_t seed, const uint32_t *__restrict__ cum_bins, uint32_t N,
+// Synthetic cohort, one thread per SNP (sequential selection sampling over the 2 * n_total allele slots).
+// Distribution restated from data/simulate_data.cpp:160-207; see DESIGN.md "synthetic cohort". The store holds
+// samples [s0, s0 + N) of the cohort; draws and first-seen labels are replayed from sample 0, so that sample blocks
+// generated one at a time are the columns of the one whole-cohort table (labels included).
+__global__ void simulate_kernel(uint64_t seed, const uint32_t *__restrict__ cum_bins, uint32_t N, uint32_t s0, uint32_t n_total,
                                 uint32_t missing_q32, uint16_t *__restrict__ hdr,
                                 uint32_t *__restrict__ raw, uint32_t Wr, uint64_t M) {
     const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -174,40 +176,36 @@ __global__ void simulate_kernel(uint64_t seed, const uint32_t *__restrict__ cum_
     for (int b = 0; b < 51; ++b)
         if (r < cum_bins[b]) { bin = b; break; }
     const uint64_t frac = sim_hash(seed, snp, SIM_STREAM_FREQ) % 1000;
-    const uint64_t slots = 2ull * N;
+    const uint64_t slots = 2ull * n_total;
     const uint64_t want = ((1000ull * bin + frac) * slots) / 100000ull;   // floor(p * 2N)
     uint64_t chosen = 0;
     Labeler lab;
     lab.reset();
     uint32_t *p1 = raw + snp * 2ull * Wr, *p2 = p1 + Wr;
-    const uint32_t words = (N + 31) / 32;
-    for (uint32_t w = 0; w < Wr; ++w) {
-        uint32_t a = 0, b = 0;
-        if (w < words) {
-            for (uint32_t t = 0; t < 32; ++t) {
-                const uint32_t s = w * 32 + t;
-                if (s >= N) break;
-                int minor = 0;
+    uint32_t a = 0, b = 0, w = 0;
+    for (uint32_t s = 0; s < s0 + N; ++s) {
+        int minor = 0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint64_t slot = 2ull * s + h, left = slots - slot;
-                    const uint64_t u = sim_hash(seed, snp, slot) >> 32;
-                    if (((u * left) >> 32) < want - chosen) { ++minor; ++chosen; }
-                }
-                bool missing = false;
-                if (missing_q32)
-                    missing = (uint32_t)(sim_hash(seed, snp, SIM_STREAM_MISS | s) >> 32) < missing_q32;
-                if (!missing) {
-                    const int enc = minor == 0 ? 0 : (minor == 1 ? 1 : 5);   // "AA", "AC", "CC"
-                    const int c = lab.code(enc);
-                    a |= (uint32_t)(c & 1) << t;
-                    b |= (uint32_t)((c >> 1) & 1) << t;
-                }
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t slot = 2ull * s + h, left = slots - slot;
+            const uint64_t u = sim_hash(seed, snp, slot) >> 32;
+            if (((u * left) >> 32) < want - chosen) { ++minor; ++chosen; }
+        }
+        bool missing = false;
+        if (missing_q32)
+            missing = (uint32_t)(sim_hash(seed, snp, SIM_STREAM_MISS | s) >> 32) < missing_q32;
+        if (!missing) {
+            const int enc = minor == 0 ? 0 : (minor == 1 ? 1 : 5);   // "AA", "AC", "CC"
+            const int c = lab.code(enc);
+            if (s >= s0) {
+                const uint32_t t = (s - s0) & 31;
+                a |= (uint32_t)(c & 1) << t;
+                b |= (uint32_t)((c >> 1) & 1) << t;
             }
         }
-        p1[w] = a;
-        p2[w] = b;
+        if (s >= s0 && (((s - s0) & 31) == 31 || s + 1 == s0 + N)) { p1[w] = a; p2[w] = b; ++w; a = 0; b = 0; }
     }
+    for (; w < Wr; ++w) { p1[w] = 0; p2[w] = 0; }
     hdr[snp] = lab.head;
 }
 
@@ -306,6 +304,10 @@ int gwasdev_synchronize(gwasdev_store *s) {
 }
 
 int gwasdev_pack_row_text(const char *txt, size_t len, uint32_t n_samples, uint16_t *row) {
+    return gwasdev_pack_row_text_block(txt, len, n_samples, row, nullptr);
+}
+
+int gwasdev_pack_row_text_block(const char *txt, size_t len, uint32_t n_samples, uint16_t *row, uint16_t *label_state) {
     GW_REQUIRE(txt && row, "gwasdev_pack_row_text: NULL argument");
     const uint32_t P = plane_blocks(n_samples);
     memset(row, 0, sizeof(uint16_t) * (2 * (size_t)P + 1));
@@ -322,6 +324,15 @@ int gwasdev_pack_row_text(const char *txt, size_t len, uint32_t n_samples, uint1
     };
     Labeler lab;
     lab.reset();
+    if (label_state && *label_state) {   // continue the row's first-seen labelling after the earlier sample blocks
+        const uint16_t h = *label_state, st = h & 0xF000;
+        const int e1 = (h >> 8) & 0xF, e2 = (h >> 4) & 0xF, e3 = h & 0xF;
+        GW_REQUIRE(st == 0x1000 || st == 0x2000 || st == 0x3000 || st == 0x4000 || st == 0x7000, "gwasdev_pack_row_text_block: bad label state 0x%04x", h);
+        lab.head = h;
+        if (st == 0x1000 || st == 0x3000 || st == 0x4000 || st == 0x7000) lab.codes |= 1ull << (4 * e1);
+        if (st == 0x2000 || st == 0x4000 || st == 0x7000) lab.codes |= 2ull << (4 * e2);
+        if (st == 0x3000 || st == 0x7000) lab.codes |= 3ull << (4 * e3);
+    }
     size_t pos = 0;
     for (uint32_t col = 0; col < n_samples && pos + 1 < len; ++col, pos += 3) {
         const int a = allele[(unsigned char)txt[pos]], b = allele[(unsigned char)txt[pos + 1]];
@@ -337,6 +348,7 @@ int gwasdev_pack_row_text(const char *txt, size_t len, uint32_t n_samples, uint1
         }
     }
     row[0] = lab.head;
+    if (label_state) *label_state = lab.head;
     return GWASDEV_OK;
 }
 
@@ -409,8 +421,11 @@ int gwasdev_call_at(gwasdev_store *s, uint64_t row, uint32_t col, char out[3]) {
     return GWASDEV_OK;
 }
 
-int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[51], uint32_t missing_q32) {
+int gwasdev_simulate_block(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[51], uint32_t missing_q32,
+                           uint32_t first_sample, uint32_t n_total_samples) {
     GW_REQUIRE(s && bin_counts, "gwasdev_simulate: NULL argument");
+    GW_REQUIRE((uint64_t)first_sample + s->N <= n_total_samples, "gwasdev_simulate_block: samples [%u, %llu) outside the cohort of %u",
+               first_sample, (unsigned long long)first_sample + s->N, n_total_samples);
     GW_CUDA(cudaSetDevice(s->device));
     uint32_t cum[51];
     uint64_t t = 0;
@@ -420,7 +435,8 @@ int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[
     GW_CUDA(cudaMalloc(&d_cum, sizeof cum));
     GW_CUDA(cudaMemcpyAsync(d_cum, cum, sizeof cum, cudaMemcpyHostToDevice, s->stream));
     const unsigned threads = 64, blocks = (unsigned)((s->M + threads - 1) / threads);
-    simulate_kernel<<<blocks, threads, 0, s->stream>>>(seed, d_cum, s->N, missing_q32, s->d_hdr, s->d_raw, s->Wr, s->M);
+    simulate_kernel<<<blocks, threads, 0, s->stream>>>(seed, d_cum, s->N, first_sample, n_total_samples, missing_q32, s->d_hdr, s->d_raw,
+                                                       s->Wr, s->M);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
@@ -428,6 +444,11 @@ int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[
     if (e != cudaSuccess) { set_error("gwasdev_simulate: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     invalidate_selection(s);
     return GWASDEV_OK;
+}
+
+int gwasdev_simulate(gwasdev_store *s, uint64_t seed, const uint32_t bin_counts[51], uint32_t missing_q32) {
+    GW_REQUIRE(s != nullptr, "gwasdev_simulate: NULL argument");
+    return gwasdev_simulate_block(s, seed, bin_counts, missing_q32, 0, s->N);
 }
 
 int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, uint32_t n_case, uint8_t *pheno) {
