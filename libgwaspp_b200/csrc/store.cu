@@ -77,47 +77,53 @@ __device__ __forceinline__ uint32_t compress_bits(uint32_t x, const uint32_t *mv
     return x;
 }
 
-template <bool TABLES_IN_SMEM>
+// One thread per SOURCE word: both planes are compressed once per class and OR-ed into the output row, which is
+// assembled in shared memory (a source word's members land in at most two consecutive output words) and then
+// written out in the scan layout with full-width stores. SNPS rows per block iteration amortise the two barriers.
+template <bool TABLES_IN_SMEM, int SNPS>
 __global__ void __launch_bounds__(256)
 select_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, SelectTables ca, SelectTables co,
               uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Wt, uint64_t M) {
-    extern __shared__ uint32_t tab[];   // per class: m[Wr], mv[5*Wr], rank[Wr+1] (contiguous in global memory too)
+    extern __shared__ uint32_t tab[];   // [SNPS][sel_stride] output rows, then per class: m[Wr], mv[5*Wr], rank[Wr+1]
     const uint32_t per = 7 * Wr + 1;
+    uint32_t *rows = tab, *tables = tab + SNPS * sel_stride;
     if (TABLES_IN_SMEM) {
-        for (uint32_t q = threadIdx.x; q < 2 * per; q += blockDim.x) tab[q] = q < per ? ca.m[q] : co.m[q - per];
-        __syncthreads();
+        for (uint32_t q = threadIdx.x; q < 2 * per; q += blockDim.x) tables[q] = q < per ? ca.m[q] : co.m[q - per];
     }
-    const uint32_t n_out = ca.Kout + co.Kout;
-    for (uint64_t snp = blockIdx.x; snp < M; snp += gridDim.x) {
-        const uint32_t *p1 = raw + snp * 2ull * Wr, *p2 = p1 + Wr;
-        uint32_t *row = sel + snp * (uint64_t)sel_stride;
-        for (uint32_t q = threadIdx.x; q < n_out; q += blockDim.x) {
-            const bool is_ca = q < ca.Kout;
-            const SelectTables &t = is_ca ? ca : co;
-            const uint32_t *tm = TABLES_IN_SMEM ? tab + (is_ca ? 0 : per) : t.m, *tmv = tm + Wr, *trk = tm + 6 * Wr;
-            const uint32_t o = is_ca ? q : q - ca.Kout;
-            const uint32_t lo = 32 * o, hi = min(lo + 32, t.n_class);
-            uint32_t a = 0, b = 0;
-            for (uint32_t sw = t.first[o]; sw < Wr && trk[sw] < hi; ++sw) {
+    for (uint32_t q = threadIdx.x; q < SNPS * sel_stride; q += blockDim.x) rows[q] = 0;
+    __syncthreads();
+    const uint32_t *tm_ca = TABLES_IN_SMEM ? tables : ca.m, *tm_co = TABLES_IN_SMEM ? tables + per : co.m;
+    for (uint64_t snp0 = (uint64_t)blockIdx.x * SNPS; snp0 < M; snp0 += (uint64_t)gridDim.x * SNPS) {
+        const uint32_t n_here = (uint32_t)min((uint64_t)SNPS, M - snp0);
+        for (uint32_t q = threadIdx.x; q < n_here * Wr; q += blockDim.x) {
+            const uint32_t r = q / Wr, sw = q - r * Wr;
+            const uint32_t *p1 = raw + (snp0 + r) * 2ull * Wr;
+            const uint32_t w1 = p1[sw], w2 = p1[Wr + sw];
+            uint32_t *row = rows + r * sel_stride;
+#pragma unroll
+            for (int cls = 0; cls < 2; ++cls) {
+                const uint32_t *tm = cls ? tm_co : tm_ca;
                 const uint32_t m = tm[sw];
                 if (m == 0) continue;
-                const uint32_t x = compress_bits(p1[sw] & m, tmv + 5 * sw), y = compress_bits(p2[sw] & m, tmv + 5 * sw);
-                const int pos = (int)trk[sw] - (int)lo;        // where this word's first member lands
-                if (pos >= 0) { a |= x << pos; b |= y << pos; }
-                else { a |= x >> (-pos); b |= y >> (-pos); }
+                const uint32_t *mv = tm + Wr + 5 * sw;
+                const uint32_t x = compress_bits(w1 & m, mv), y = compress_bits(w2 & m, mv);
+                const uint32_t pos = tm[6 * Wr + sw], o = pos >> 5, sh = pos & 31, off = cls ? 2 * Wc : 0;
+                if (x) {
+                    atomicOr(&row[sel_word(off, 0, o)], x << sh);
+                    if (sh && (x >> (32 - sh))) atomicOr(&row[sel_word(off, 0, o + 1)], x >> (32 - sh));
+                }
+                if (y) {
+                    atomicOr(&row[sel_word(off, 1, o)], y << sh);
+                    if (sh && (y >> (32 - sh))) atomicOr(&row[sel_word(off, 1, o + 1)], y >> (32 - sh));
+                }
             }
-            const uint32_t off = is_ca ? 0 : 2 * Wc;
-            row[sel_word(off, 0, o)] = a;
-            row[sel_word(off, 1, o)] = b;
         }
-        // zero the padding words of both classes (Kout..W)
-        for (uint32_t q = threadIdx.x; q < (Wc - ca.Kout) + (Wt - co.Kout); q += blockDim.x) {
-            const bool is_ca = q < Wc - ca.Kout;
-            const uint32_t w = is_ca ? ca.Kout + q : co.Kout + (q - (Wc - ca.Kout));
-            const uint32_t off = is_ca ? 0 : 2 * Wc;
-            row[sel_word(off, 0, w)] = 0;
-            row[sel_word(off, 1, w)] = 0;
-        }
+        __syncthreads();
+        // rows are contiguous in the scan layout: stream them out 16 bytes per thread and clear the buffer
+        uint4 *dst = reinterpret_cast<uint4 *>(sel + snp0 * (uint64_t)sel_stride);
+        uint4 *src = reinterpret_cast<uint4 *>(rows);
+        for (uint32_t q = threadIdx.x; q < n_here * sel_stride / 4; q += blockDim.x) { dst[q] = src[q]; src[q] = make_uint4(0, 0, 0, 0); }
+        __syncthreads();
     }
 }
 
@@ -533,15 +539,20 @@ int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, con
     to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.n_class = nco; to.Kout = s->Kt;
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    const size_t smem = 2 * (7ull * s->Wr + 1) * sizeof(uint32_t);
-    if (smem <= 100 * 1024) {   // tables staged in shared memory (up to ~58 000 samples), else read through L1/L2
-        GW_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int SNPS = 4;                                     // rows assembled per block iteration
+    const size_t smem_rows = (size_t)SNPS * stride * sizeof(uint32_t);
+    const size_t smem_tab = 2 * (7ull * s->Wr + 1) * sizeof(uint32_t);
+    if (smem_rows + smem_tab <= 160 * 1024) {   // tables staged in shared memory (up to ~80 000 samples), else read through L1/L2
+        const size_t smem = smem_rows + smem_tab;
+        GW_CUDA(cudaFuncSetAttribute(select_kernel<true, SNPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
-        const unsigned grid = (unsigned)std::min<uint64_t>(s->M, (uint64_t)sms * per_sm);
-        select_kernel<true><<<grid, 256, smem, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
+        const unsigned grid = (unsigned)std::min<uint64_t>((s->M + SNPS - 1) / SNPS, (uint64_t)sms * per_sm);
+        select_kernel<true, SNPS><<<grid, 256, smem, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
     } else {
-        const unsigned grid = (unsigned)std::min<uint64_t>(s->M, (uint64_t)sms * 8);
-        select_kernel<false><<<grid, 256, 0, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
+        GW_REQUIRE(smem_rows <= 200 * 1024, "gwasdev_select_case_control: %u samples exceed the compaction kernel's row buffer", s->N);
+        GW_CUDA(cudaFuncSetAttribute(select_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_rows / SNPS)));
+        const unsigned grid = (unsigned)std::min<uint64_t>(s->M, (uint64_t)sms * 4);
+        select_kernel<false, 1><<<grid, 256, smem_rows / SNPS, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
     }
     GW_LAUNCHED();
     GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
