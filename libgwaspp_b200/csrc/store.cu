@@ -539,6 +539,8 @@ int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, con
     to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.n_class = nco; to.Kout = s->Kt;
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const bool trace = getenv("GWASDEV_TRACE") != nullptr;
+    if (trace) cudaEventRecord(s->ev2, s->stream);
     constexpr int SNPS = 4;                                     // rows assembled per block iteration
     const size_t smem_rows = (size_t)SNPS * stride * sizeof(uint32_t);
     const size_t smem_tab = 2 * (7ull * s->Wr + 1) * sizeof(uint32_t);
@@ -549,13 +551,15 @@ int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, con
         const unsigned grid = (unsigned)std::min<uint64_t>((s->M + SNPS - 1) / SNPS, (uint64_t)sms * per_sm);
         select_kernel<true, SNPS><<<grid, 256, smem, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
     } else {
-        GW_REQUIRE(smem_rows <= 200 * 1024, "gwasdev_select_case_control: %u samples exceed the compaction kernel's row buffer", s->N);
+        GW_REQUIRE(smem_rows / SNPS <= 200 * 1024, "gwasdev_select_case_control: %u samples exceed the compaction kernel's row buffer", s->N);
         GW_CUDA(cudaFuncSetAttribute(select_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_rows / SNPS)));
         const unsigned grid = (unsigned)std::min<uint64_t>(s->M, (uint64_t)sms * 4);
         select_kernel<false, 1><<<grid, 256, smem_rows / SNPS, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
     }
     GW_LAUNCHED();
+    if (trace) cudaEventRecord(s->ev3, s->stream);
     GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
+    if (trace) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev2, s->ev3); fprintf(stderr, "[gwasdev trace] select_kernel %.3f ms\n", ms); }
     s->selected = true;
     return GWASDEV_OK;
 }
