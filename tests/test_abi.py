@@ -87,3 +87,34 @@ def test_stream_masks_and_phenotype_helper(lib, orc):
     ca, co = gw.stream_masks(ph)
     oca, oco, nca, nco = orc.masks(ph)
     assert np.array_equal(ca, oca) and np.array_equal(co, oco) and (nca, nco) == (501, 502)
+
+
+def test_block_packer_carries_first_seen_labels_across_sample_blocks(lib, golden_dir):
+    """gwasdev_pack_row_text_block: a row packed in sample blocks, with the label state carried from block to block,
+    has the bit-planes and the header word of the row packed whole (which is pinned to the reference above)."""
+    g = np.load(os.path.join(golden_dir, "cohort_missing.npz"))
+    txt = [b"AA", b"AC", b"CC", b"00"]
+    codes = g["codes"]
+    N = codes.shape[1]
+    P = gw.plane_blocks(N)
+    rng = np.random.default_rng(3)
+    for r in range(0, codes.shape[0], 3):
+        cuts = sorted(set([0, N] + list(rng.integers(1, N, 3))))
+        state, planes = 0, [[], []]
+        for s0, s1 in zip(cuts[:-1], cuts[1:]):
+            nb = s1 - s0
+            row, state = gw.pack_row_text_block(b"\t".join(txt[c] for c in codes[r, s0:s1]), nb, state)
+            Pb = gw.plane_blocks(nb)
+            for pl in range(2):
+                planes[pl].append(np.unpackbits(row[1 + pl * Pb:1 + (pl + 1) * Pb].view(np.uint8), bitorder="little")[:nb])
+        whole = g["raw_rows"][r]
+        assert state == whole[0]
+        for pl in range(2):
+            ref = np.unpackbits(whole[1 + pl * P:1 + (pl + 1) * P].view(np.uint8), bitorder="little")[:N]
+            assert np.array_equal(np.concatenate(planes[pl]), ref)
+    with pytest.raises(gw.GwasDevError, match="bad label state"):
+        gw.pack_row_text_block(b"AA", 1, 0x5000)
+    # a third spelling of one kind is rejected across blocks as well (the reference aborts, compressed_genotype_table5.cpp:325)
+    _, st = gw.pack_row_text_block(b"AC\tAA", 2, 0)
+    with pytest.raises(gw.GwasDevError, match="third genotype spelling"):
+        gw.pack_row_text_block(b"CA", 1, st)
