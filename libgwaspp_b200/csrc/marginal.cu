@@ -191,17 +191,16 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_snps = snp_end - snp_begin;
-    // contiguous balanced ranges (default) or batches of 32 rows dealt round-robin over the warps
-    const uint64_t r_begin = interleave ? snp_begin + warp * 32 : snp_begin + warp * n_snps / n_warps;
-    const uint64_t r_end = interleave ? snp_end : snp_begin + (warp + 1) * n_snps / n_warps;
-    const uint64_t r_step = interleave ? n_warps * 32 : 32;
-    for (uint64_t base = r_begin; base < r_end; base += r_step) {
-        const uint32_t in_batch = (uint32_t)min((uint64_t)32, r_end - base);
-        const uint32_t passes = min((uint32_t)G, in_batch);
-        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of row (base + lane)
-        // pass `it`: group g works on batch row g*G + it, so the totals of row L end up in L's own group
+    // One batch: up to 32 consecutive rows; in pass `it` the 32/G lane groups work on rows it*(32/G) .. +32/G-1 (so a short
+    // batch needs proportionally fewer passes), lane `it` of group g keeps the totals of row it*(32/G) + g, and after the
+    // passes every lane finishes one SNP.
+    constexpr uint32_t NG = 32 / G;
+    const uint32_t my_row = l * NG + g;
+    auto batch = [&](uint64_t base, uint32_t in_batch) {
+        const uint32_t passes = (in_batch + NG - 1) / NG;
+        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of row (base + my_row)
         for (uint32_t it = 0; it < passes; ++it) {
-            const uint32_t brow = g * G + it;
+            const uint32_t brow = it * NG + g;
             const bool valid = brow < in_batch;
             const uint4 *row = sel + (base + (valid ? brow : 0)) * (uint64_t)stride4;
             uint32_t s1, s2, sb, t1, t2, tb;
@@ -212,8 +211,21 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
             t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
             if (l == it) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
         }
-        if (lane < in_batch)
-            finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + lane - out_base, counts, mi, stats);
+        if (my_row < in_batch)
+            finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + my_row - out_base, counts, mi, stats);
+    };
+    if (interleave) {
+        // full rounds of 32-row batches dealt round-robin over the warps (neighbouring warps stream neighbouring rows),
+        // then the rows that do not fill a round split evenly, so that no warp runs a whole batch longer than the rest
+        const uint64_t rounds = n_snps / (n_warps * 32);
+        for (uint64_t r = 0; r < rounds; ++r) batch(snp_begin + (r * n_warps + warp) * 32, 32);
+        const uint64_t rem_begin = snp_begin + rounds * n_warps * 32, rem = snp_end - rem_begin;
+        const uint64_t b0 = rem_begin + warp * rem / n_warps, b1 = rem_begin + (warp + 1) * rem / n_warps;
+        for (uint64_t base = b0; base < b1; base += 32) batch(base, (uint32_t)min((uint64_t)32, b1 - base));
+    } else {
+        // contiguous balanced ranges
+        const uint64_t b0 = snp_begin + warp * n_snps / n_warps, b1 = snp_begin + (warp + 1) * n_snps / n_warps;
+        for (uint64_t base = b0; base < b1; base += 32) batch(base, (uint32_t)min((uint64_t)32, b1 - base));
     }
 }
 
