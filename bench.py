@@ -38,6 +38,8 @@ sys.path.insert(0, ROOT)
 SEED = 20121127
 MARGINAL = dict(n_snps=500_000, n_samples=10_000, n_case=5_000)       # BASELINE.json configs[1]
 PAIRWISE = dict(n_snps=50_000, n_samples=4_000, n_case=2_000)         # BASELINE.json configs[2]
+NCU_TRAFFIC_MARGINAL = 1.2930e9       # dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1k_marginal_scan_full.md)
+NCU_TRAFFIC_PAIRWISE = 1.9517e10      # same for pair_screen_mma_kernel at configs[2] on one GPU (profiles/r1h_pair_screen_mma_full.md)
 CPU_MARGINAL_SAMPLE_SNPS = 2_000
 CPU_PAIRWISE_SAMPLE_SNPS = 1_500
 
@@ -169,8 +171,11 @@ def gpu_arm(args):
         kms.append(st.last_scan_ms())
     k_ms = float(np.mean(kms))
     achieved = bytes_per_step / (k_ms * 1e-3) / 1e9
+    traffic = args.traffic_bytes
+    if traffic is None and (M, N, NCASE) == (MARGINAL["n_snps"], MARGINAL["n_samples"], MARGINAL["n_case"]):
+        traffic = NCU_TRAFFIC_MARGINAL          # ncu --set full capture of this launch shape, profiles/r1k_marginal_scan_full.md
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": args.traffic_bytes,
+                "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
                 "kernel": "marginal_scan_kernel", "kernel_ms": round(k_ms, 4), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_step}
 
@@ -348,12 +353,13 @@ def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max
     res = {
         "metric": "pairwise SNP x SNP tests/sec", "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": round(ms_per_step, 3), "scaling": "strong", "hits": int(n_hits), "candidates": int(cand),
-        "config": {"workload": f"configs[2]: exhaustive pairwise epistasis {NCASE}/{N - NCASE} samples x {M} SNPs "
+        "config": {"workload": f"{'configs[3]' if (M, N) == (500_000, 10_000) else 'configs[2]'}: exhaustive pairwise epistasis {NCASE}/{N - NCASE} samples x {M} SNPs "
                                f"({M * (M - 1) // 2} pairs), 3x3x2 contingency + KSA statistic, threshold 30",
                    "engine": {2: "tensor cores", 1: "AND+POPC"}.get(engine, "?"),
                    "parallelism": f"128x128 SNP tile pairs dealt in chunks of 64 over {world} rank(s); NCCL all_gather of hits"},
         "roofline": {"bound": "int_popc", "achieved": round(achieved / 1e12, 4), "peak": round(peak_cells / 1e12, 4),
-                     "unit": "T word-cells/s (32-bit AND+POPC)", "frac": round(achieved / peak_cells, 4), "traffic": None,
+                     "unit": "T word-cells/s (32-bit AND+POPC)", "frac": round(achieved / peak_cells, 4),
+                     "traffic": NCU_TRAFFIC_PAIRWISE if (engine == 2 and world == 1 and (M, N, NCASE) == (PAIRWISE["n_snps"], PAIRWISE["n_samples"], PAIRWISE["n_case"])) else None,
                      "kernel": kernel, "kernel_ms": round(k_ms, 3),
                      "peak_source": f"register-only __popc microbenchmark run in this process (clock attr {clk:.0f} MHz); "
                                     "nominal 148 SMs x 16 POPC/clk x 1.965 GHz = 4.65",
@@ -528,7 +534,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--traffic-bytes", type=float, default=None,
-                    help="dram__bytes_read+write per launch of the scan kernel from the committed ncu capture")
+                    help="dram__bytes_read+write per launch of the scan kernel from the committed ncu capture "
+                         "(default: profiles/r1k_marginal_scan_full.md, valid for the default configs[1] shape only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
