@@ -53,41 +53,86 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+    The scan's timed region is milliseconds long, far below what `nvidia-smi -lms` can resolve, so the same NVML
+    counters nvidia-smi prints are polled in-process (pynvml, ~0.5 ms period); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index: int, uuid: str | None = None):
+        self.idx, self.uuid, self.rows, self.proc, self.nvml, self.source = gpu_index, uuid, [], None, None, None
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(ids[self.idx]) if self.idx < len(ids) else self.idx)
+            self.nvml, self.handle, self.source = pynvml, h, "nvml"
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(reasons_fn(h))
+                watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append((time.perf_counter(), [str(self.idx), sm, self.max_sm, watts, mask]))
+            except Exception:
+                pass
+            time.sleep(0.0005)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                mask = sum(bit for (bit, _), v in zip(self.REASONS, f[4:8]) if v.lower().startswith("active"))
+                self.rows.append((time.perf_counter(), [f[0], float(f[1]), float(f[2]), float(f[3]), mask]))
+            except (ValueError, IndexError):
+                pass
 
     def window(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        rows = [r for t, r in self.rows if t0 <= t <= t1]
+        where = "timed region"
+        if not rows:   # region shorter than one sampling period: the nearest samples around it
+            rows = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[:3]]
+            where = "nearest samples to the timed region"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[1]) for r in rows)
-        reasons = set()
+        sm = sorted(r[1] for r in rows)
+        mask = 0
         for r in rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+            mask |= r[4]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": rows[0][2], "reasons": sorted(n for b, n in self.REASONS if mask & b),
+                "samples": len(rows), "power_w_max": round(max(r[3] for r in rows), 1), "source": self.source, "window": where}
 
     def stop(self):
+        self._stop.set()
         if self.proc:
             self.proc.terminate()
 
@@ -130,7 +175,11 @@ def gpu_arm(args):
         return float(t.item())
 
     peaks, peak_src = measured_peaks()
-    sampler = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
     K, W = args.steps, args.warmup

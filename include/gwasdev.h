@@ -105,6 +105,32 @@ GWASDEV_API int gwasdev_get_rows(gwasdev_store *s, uint64_t first_row, uint64_t 
 /* GenoTable::operator()(r, c) + decodeGenotype (compressed_genotype_table5.cpp:400-432,1225-1231). */
 GWASDEV_API int gwasdev_call_at(gwasdev_store *s, uint64_t row, uint32_t col, char out[3]);
 
+/* ---- file / text ingestion on the device ---------------------------------------------
+ * Transposed-PLINK text straight into the store: replaces TpedGenotypeFile::parseNextGenotypeRecord
+ * (genetics/individual/tped_genotype_file.cpp:110-185: trim, four marker fields, alleles 1234 -> ACGT, one allele
+ * every other character) + GenoTable::addGenotypeRow (compressed_genotype_table5.cpp:277-365) for every line of
+ * `text`. Lines end in '\n'; blank lines are skipped; the k-th non-blank line becomes row first_row + k. Only whole
+ * lines are consumed: *bytes_used (may be NULL) is the offset after the last '\n', the caller keeps the rest for
+ * its next call. *rows_done (may be NULL) = rows written. The host does not look at the text beyond finding that
+ * last newline: line index, label resolution and bit-packing run on the device. GWASDEV_EINVAL where the reference
+ * aborts (third spelling of one genotype kind) and for lines without four marker fields or more lines than rows. */
+GWASDEV_API int gwasdev_put_tped_text(gwasdev_store *s, uint64_t first_row, const char *text, size_t len, uint64_t *rows_done,
+                          size_t *bytes_used);
+/* Table dimensions of a TPED file (plain or .gz): non-blank lines, and the genotype columns of the first line counted
+ * the way the reference sizes its row buffer (tped_genotype_file.cpp:132-136). */
+GWASDEV_API int gwasdev_tped_dims(const char *path, uint64_t *n_rows, uint32_t *n_samples);
+/* Whole TPED file (plain or .gz, read through zlib) into rows first_row.., double-buffered through pinned memory so
+ * that reading chunk k+1 overlaps the device work on chunk k. A .gz needs no rewind: dims and load each open it once
+ * (the reference's two-pass reader seeks, which its gzstream cannot: individual_genotype_file.cpp:94). */
+GWASDEV_API int gwasdev_load_tped(gwasdev_store *s, const char *path, uint64_t first_row, uint64_t *rows_done);
+/* PLINK .bed rows (SNP-major, ceil(n_samples/4) bytes per SNP, no magic; 0 = hom A1, 1 = missing, 2 = het,
+ * 3 = hom A2) into rows [first_row, first_row + n_rows). alleles (may be NULL = A, C) holds the indices of A1 and A2
+ * in "ACGT" per row; labels come out as the text loader would give the same calls spelled A1A1 / A1A2 / A2A2 in
+ * sample order. The reference has no .bed reader; this is the input SURVEY.md 8f1 adds. */
+GWASDEV_API int gwasdev_put_bed(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, const uint8_t *bed, const uint8_t *alleles);
+GWASDEV_API int gwasdev_bed_dims(const char *bed_path, uint32_t n_samples, uint64_t *n_rows);
+GWASDEV_API int gwasdev_load_bed(gwasdev_store *s, const char *bed_path, const uint8_t *alleles, uint64_t first_row, uint64_t *rows_done);
+
 /* Synthetic cohort generated directly in HBM: fixed-seed restatement of data/simulate_data.cpp:160-207
  * over one panel of data/maf_spectrum.tab (bin_counts[b] = SNP count at MAF b %). missing_q32/2^32
  * is the per-genotype missing probability. Labels are first-seen, as the text loader would give. */

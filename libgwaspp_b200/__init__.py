@@ -50,7 +50,8 @@ ABI_SYMBOLS = [
     "gwasdev_pairwise_scan", "gwasdev_ksa", "gwasdev_ksa_screen_f32", "gwasdev_gtest", "gwasdev_pairwise_epi_test",
     "gwasdev_popc_peak", "gwasdev_hbm_read_peak", "gwasdev_set_pair_engine", "gwasdev_mma_tile_counts",
     "gwasdev_ksa_screen_mma_f32", "gwasdev_pack_row_text_block", "gwasdev_simulate_block", "gwasdev_marginal_accumulate",
-    "gwasdev_marginal_finalize",
+    "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
+    "gwasdev_bed_dims", "gwasdev_load_bed",
 ]
 
 
@@ -96,6 +97,12 @@ def load_library():
     L.gwasdev_marginal_accumulate.argtypes = [vp, u64, u64, vp, i32]
     L.gwasdev_marginal_finalize.argtypes = [i32, u64, vp, vp, vp, i32]
     L.gwasdev_set_pair_engine.argtypes = [vp, i32]
+    L.gwasdev_put_tped_text.argtypes = [vp, u64, vp, C.c_size_t, C.POINTER(u64), C.POINTER(C.c_size_t)]
+    L.gwasdev_tped_dims.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u32)]
+    L.gwasdev_load_tped.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64)]
+    L.gwasdev_put_bed.argtypes = [vp, u64, u64, vp, vp]
+    L.gwasdev_bed_dims.argtypes = [C.c_char_p, u32, C.POINTER(u64)]
+    L.gwasdev_load_bed.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
     L.gwasdev_mma_tile_counts.argtypes = [vp, u32, u32, vp]
     L.gwasdev_ksa_screen_mma_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_pairwise_epi_test.argtypes = [i32, u64, vp, vp, vp, vp]
@@ -192,6 +199,19 @@ def pairwise_epi_test(cs, ct, device: int = 0):
     return ll, p
 
 
+def tped_dims(path: str) -> tuple[int, int]:
+    """(non-blank lines, genotype columns of the first line) of a TPED file, plain or .gz."""
+    rows, cols = C.c_uint64(), C.c_uint32()
+    _check(load_library().gwasdev_tped_dims(os.fsencode(path), C.byref(rows), C.byref(cols)), "gwasdev_tped_dims")
+    return int(rows.value), int(cols.value)
+
+
+def bed_dims(path: str, n_samples: int) -> int:
+    rows = C.c_uint64()
+    _check(load_library().gwasdev_bed_dims(os.fsencode(path), n_samples, C.byref(rows)), "gwasdev_bed_dims")
+    return int(rows.value)
+
+
 def launch_count() -> int:
     return int(load_library().gwasdev_launch_count())
 
@@ -238,6 +258,33 @@ class GenoStore:
 
     def put_text_rows(self, lines, first_row: int = 0):
         self.put_rows(np.stack([pack_row_text(l, self.n_samples) for l in lines]), first_row)
+
+    def put_tped_text(self, text: bytes, first_row: int = 0) -> tuple[int, int]:
+        """TPED lines parsed, labelled and packed on the device; returns (rows written, bytes consumed)."""
+        rows, used = C.c_uint64(), C.c_size_t()
+        buf = np.frombuffer(text, np.uint8) if len(text) else np.zeros(1, np.uint8)
+        _check(self.L.gwasdev_put_tped_text(self.h, first_row, _ptr(buf), len(text), C.byref(rows), C.byref(used)), "gwasdev_put_tped_text")
+        return int(rows.value), int(used.value)
+
+    def load_tped(self, path: str, first_row: int = 0) -> int:
+        rows = C.c_uint64()
+        _check(self.L.gwasdev_load_tped(self.h, os.fsencode(path), first_row, C.byref(rows)), "gwasdev_load_tped")
+        return int(rows.value)
+
+    def put_bed(self, bed: np.ndarray, alleles: np.ndarray | None = None, first_row: int = 0):
+        bed = np.ascontiguousarray(bed, np.uint8)
+        assert bed.ndim == 2 and bed.shape[1] == (self.n_samples + 3) // 4, bed.shape
+        if alleles is not None:
+            alleles = np.ascontiguousarray(alleles, np.uint8)
+            assert alleles.shape == (bed.shape[0], 2)
+        _check(self.L.gwasdev_put_bed(self.h, first_row, bed.shape[0], _ptr(bed), _ptr(alleles)), "gwasdev_put_bed")
+
+    def load_bed(self, path: str, alleles: np.ndarray | None = None, first_row: int = 0) -> int:
+        rows = C.c_uint64()
+        if alleles is not None:
+            alleles = np.ascontiguousarray(alleles, np.uint8)
+        _check(self.L.gwasdev_load_bed(self.h, os.fsencode(path), _ptr(alleles), first_row, C.byref(rows)), "gwasdev_load_bed")
+        return int(rows.value)
 
     def get_rows(self, first_row: int = 0, n_rows: int | None = None) -> np.ndarray:
         n_rows = self.n_snps - first_row if n_rows is None else n_rows

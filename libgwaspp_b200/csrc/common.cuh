@@ -176,10 +176,13 @@ struct gwasdev_store {
     Scratch sc_pi, sc_pj, sc_a, sc_b;                        // pair probes
     Scratch sc_stage;                                        // row upload / download staging
     unsigned long long *h_cnt = nullptr;                     // pinned host counters
+    void *ingest = nullptr;                                  // file / text ingestion state (ingest.cu)
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     double last_scan_ms = 0.0;
 };
+
+void gwasdev_internal_free_ingest(gwasdev_store *s);
 
 namespace gwasdev {
 // make sure sc holds at least `bytes`; contents are not preserved

@@ -279,6 +279,7 @@ static void invalidate_selection(gwasdev_store *s) {
 void gwasdev_destroy(gwasdev_store *s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    gwasdev_internal_free_ingest(s);
     cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
     cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
     free(s->tmap); free(s->tmap_mm);

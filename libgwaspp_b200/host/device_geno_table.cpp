@@ -74,6 +74,22 @@ void DeviceGenoTable::flush() {
     selected_rev = 0;
 }
 
+int DeviceGenoTable::loadTransposedPlink(const std::string &tped_path, int first_row) {
+    flush();
+    uint64_t rows = 0;
+    GW_MUST(gwasdev_load_tped(store, tped_path.c_str(), (uint64_t)first_row, &rows));
+    selected_rev = 0;
+    return (int)rows;
+}
+
+int DeviceGenoTable::loadBed(const std::string &bed_path, const std::vector<unsigned char> &alleles, int first_row) {
+    flush();
+    uint64_t rows = 0;
+    GW_MUST(gwasdev_load_bed(store, bed_path.c_str(), alleles.empty() ? nullptr : alleles.data(), (uint64_t)first_row, &rows));
+    selected_rev = 0;
+    return (int)rows;
+}
+
 void DeviceGenoTable::addGenotypeRow(int rIdx, const char *p_begin, const char *p_end, char /*delim*/) {
     if (p_begin >= p_end) return;
     assert(rIdx >= 0 && rIdx < max_row);

@@ -58,6 +58,12 @@ public:
                                         const marginal_information &m2, CaseControlContingencyTable &ccct);
 
     // ---- batch entry points (no reference counterpart: one call instead of a host loop)
+    // whole genotype file parsed, labelled and packed on the device (rows from first_row on): what the reference's
+    // TpedGenotypeFile::parseNextGenotypeRecord + addGenotypeRow loop does line by line on the host
+    // (genetics/individual/individual_genotype_file.cpp:63-106, tped_genotype_file.cpp:110-185). Returns rows loaded.
+    int loadTransposedPlink(const std::string &tped_path, int first_row = 0);
+    // PLINK .bed (SNP-major); alleles = 2 per row, indices into "ACGT" of A1 / A2 (may be empty: A, C)
+    int loadBed(const std::string &bed_path, const std::vector<unsigned char> &alleles = std::vector<unsigned char>(), int first_row = 0);
     void flush();                                                       // push buffered rows to the device
     void computeMargins(std::vector<marginal_information> &out);        // == algorithms::computeMargins over all rows
     void scanCaseControl(std::vector<frequency_table> &cases, std::vector<frequency_table> &controls,

@@ -1,8 +1,9 @@
 // Minimal harness in the shape of the reference's GWAS executable (src/test/gwas_basic.cpp:126-244) for
-// the association flags only: loads a transposed-PLINK pair (TPED/TFAM), then runs one test-class
-// function through compute(). File parsing here is the small subset the harness needs: alleles
-// 1/2/3/4 -> A/C/G/T and pair collapse as in genetics/individual/tped_genotype_file.cpp:127-190,
-// phenotype column 6 with '1' = case, '0' = control as in tfam_annotation_file.cpp:68-77.
+// the association flags only: loads a transposed-PLINK pair (TPED/TFAM; the TPED may be .gz, or a SNP-major
+// .bed), then runs one test-class function through compute(). The genotype file goes to the device as text
+// and is parsed there (csrc/ingest.cu: alleles 1/2/3/4 -> A/C/G/T and pair collapse as in
+// genetics/individual/tped_genotype_file.cpp:127-190); the phenotype file is read here, column 6 with
+// '1' = case, '0' = control as in tfam_annotation_file.cpp:68-77.
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -23,6 +24,7 @@ static void usage() {
 int main(int argc, char **argv) {
     std::string geno, pheno, outfile, test;
     int device = 0;
+    bool host_parse = false;
     for (int a = 1; a < argc; ++a) {
         std::string s = argv[a];
         if ((s == "-g" || s == "--geno") && a + 1 < argc) geno = argv[++a];
@@ -31,6 +33,7 @@ int main(int argc, char **argv) {
         else if (s == "--device" && a + 1 < argc) device = atoi(argv[++a]);
         else if (s == "--comp-level" && a + 1 < argc) ++a;          // accepted for command-line compatibility
         else if (s == "--tplink") {}
+        else if (s == "--host-parse") host_parse = true;
         else if (s.rfind("--", 0) == 0) test = s.substr(2);
     }
     if (geno.empty() || pheno.empty() || test.empty()) { usage(); return 1; }
@@ -52,17 +55,22 @@ int main(int argc, char **argv) {
             ++n_individs;
         }
     }
-    int n_markers = 0;
-    {
-        std::ifstream f(geno.c_str());
-        if (!f.is_open()) { std::cerr << "cannot open " << geno << std::endl; return 1; }
-        std::string line;
-        while (std::getline(f, line)) if (!line.empty()) ++n_markers;
-    }
+    // Genotypes: the whole file is parsed, labelled and packed on the device (gwasdev_load_tped; .gz works, a .bed is
+    // taken as SNP-major PLINK binary). --host-parse keeps the reference-shaped loop -- one addGenotypeRow per line
+    // with the host packer -- as a cross-check.
+    const bool is_bed = geno.size() > 4 && geno.compare(geno.size() - 4, 4, ".bed") == 0;
+    uint64_t n_rows64 = 0;
+    uint32_t n_cols = 0;
+    if (is_bed) {
+        if (gwasdev_bed_dims(geno.c_str(), (uint32_t)n_individs, &n_rows64) != GWASDEV_OK) { std::cerr << gwasdev_last_error() << std::endl; return 1; }
+    } else if (gwasdev_tped_dims(geno.c_str(), &n_rows64, &n_cols) != GWASDEV_OK) { std::cerr << gwasdev_last_error() << std::endl; return 1; }
+    const int n_markers = (int)n_rows64;
     std::cout << "Found " << n_individs << " individuals." << std::endl;
     std::cout << "Found " << n_markers << " markers" << std::endl;
     GeneticData gd(n_markers, n_individs, device);
-    {
+    if (is_bed) gd.getGenotypeTable()->loadBed(geno);
+    else if (!host_parse) gd.getGenotypeTable()->loadTransposedPlink(geno);
+    else {
         std::ifstream f(geno.c_str());
         std::string line, buf;
         int row = 0;

@@ -118,3 +118,28 @@ def test_block_packer_carries_first_seen_labels_across_sample_blocks(lib, golden
     _, st = gw.pack_row_text_block(b"AC\tAA", 2, 0)
     with pytest.raises(gw.GwasDevError, match="third genotype spelling"):
         gw.pack_row_text_block(b"CA", 1, st)
+
+
+def test_file_dims_helpers_run_on_the_host(lib, golden_dir, tmp_path):
+    """gwasdev_tped_dims / gwasdev_bed_dims only read files (no device): rows = non-blank lines, columns counted the
+    way the reference sizes its row buffer from the first line (tped_genotype_file.cpp:132-136); .gz via zlib."""
+    import gzip
+    for name in ("simple", "cc"):
+        path = os.path.join(golden_dir, f"perl_{name}.tped")
+        lines = open(path, "rb").read().splitlines()
+        assert gw.tped_dims(path) == (len(lines), (len(lines[0].split(b"\t")) - 4) // 2)
+    text = b"\n  \n1 rs1 0 5 A A C C 0 0\r\n\n2 rs2 0 6 A C A C A A"          # blank lines, CRLF, no final newline
+    p = tmp_path / "t.tped"
+    p.write_bytes(text)
+    assert gw.tped_dims(str(p)) == (2, 3)
+    with gzip.open(tmp_path / "t.tped.gz", "wb") as f:
+        f.write(text)
+    assert gw.tped_dims(str(tmp_path / "t.tped.gz")) == (2, 3)
+    bed = tmp_path / "t.bed"
+    bed.write_bytes(bytes([0x6C, 0x1B, 0x01]) + bytes(3 * 5))
+    assert gw.bed_dims(str(bed), 10) == 5                                   # ceil(10/4) = 3 bytes per SNP
+    with pytest.raises(gw.GwasDevError, match="whole rows"):
+        gw.bed_dims(str(bed), 13)
+    bed.write_bytes(b"not a bed file")
+    with pytest.raises(gw.GwasDevError, match="not a PLINK .bed"):
+        gw.bed_dims(str(bed), 10)
