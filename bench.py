@@ -240,12 +240,17 @@ def gpu_arm(args):
         st.marginal_scan_into(0, M, counts=h_counts, stats=h_stats, on_device=False)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - te0) / e2e_steps)
+    e2e_kernel_ms = st.last_scan_ms()
     wr = (st.P // 2 + 3) // 4 * 4                              # device words per raw plane
-    h2d = int(2 * 4 * wr + 2 * 4 * (7 * wr + 1) + 4 * ((NCASE + 31) // 32 + (N - NCASE + 31) // 32))   # masks + compaction tables
+    h2d = int(3 * 4 * wr + 2 * 4 * (7 * wr + 1) + 4 * ((NCASE + 31) // 32 + (N - NCASE + 31) // 32))   # 3 masks + compaction tables
     d2h = int(h_counts.numel() * 4 + h_stats.numel() * 8)
     e2e = {"value": round(world * bytes_per_step / e2e_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
-           "what": "gwasdev_select_case_control(host masks) + gwasdev_marginal_scan(host pinned outputs)"}
+           "what": "gwasdev_select_case_control(host masks) + gwasdev_marginal_scan(host pinned outputs): the first scan after a "
+                   "selection runs marginal_scan_masked_kernel on the raw rows (select fused into the scan, no compaction), "
+                   "in pieces whose D2H copies overlap the next piece's scan",
+           "kernel": "marginal_scan_masked_kernel", "kernel_span_ms": round(e2e_kernel_ms, 4),
+           "bound": "PCIe D2H of the 96 B/SNP results"}
     # sanity: the device and host paths agree, and the scan did real work
     assert torch.equal(h_counts, d_counts.cpu()) and int(h_counts[:, :4].sum(1).min()) == NCASE
     st.close()

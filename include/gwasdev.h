@@ -149,6 +149,12 @@ GWASDEV_API int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, ui
  * SNP-tiled pairwise store) on the device; the raw store stays resident, so this can be called
  * again with other masks. */
 GWASDEV_API int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask);
+/* Compaction is lazy by default: the call above uploads the masks and the compaction tables, and the compacted rows
+ * are built (kernel K0) when something first needs them -- the pairwise screen, the layout probes, or a second
+ * marginal scan; a single marginal scan after a selection counts through the masks on the raw rows instead, which
+ * is the reference's mask-on-the-fly overload (:609-657) and gives identical counts. eager != 0 runs K0 inside
+ * gwasdev_select_case_control. */
+GWASDEV_API int gwasdev_set_select_mode(gwasdev_store *s, int eager);
 GWASDEV_API int gwasdev_case_control_counts(gwasdev_store *s, uint32_t *n_case, uint32_t *n_ctrl);
 /* Compacted rows in the reference's layout [case p1: Pca][case p2: Pca][ctrl p1: Pco][ctrl p2: Pco]
  * (16-bit blocks, Pca = gwasdev_plane_blocks(n_case)) -- layout-parity probe. */

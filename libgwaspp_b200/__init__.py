@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "gwasdev_popc_peak", "gwasdev_hbm_read_peak", "gwasdev_set_pair_engine", "gwasdev_mma_tile_counts",
     "gwasdev_ksa_screen_mma_f32", "gwasdev_pack_row_text_block", "gwasdev_simulate_block", "gwasdev_marginal_accumulate",
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
-    "gwasdev_bed_dims", "gwasdev_load_bed",
+    "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode",
 ]
 
 
@@ -97,6 +97,7 @@ def load_library():
     L.gwasdev_marginal_accumulate.argtypes = [vp, u64, u64, vp, i32]
     L.gwasdev_marginal_finalize.argtypes = [i32, u64, vp, vp, vp, i32]
     L.gwasdev_set_pair_engine.argtypes = [vp, i32]
+    L.gwasdev_set_select_mode.argtypes = [vp, i32]
     L.gwasdev_put_tped_text.argtypes = [vp, u64, vp, C.c_size_t, C.POINTER(u64), C.POINTER(C.c_size_t)]
     L.gwasdev_tped_dims.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u32)]
     L.gwasdev_load_tped.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64)]
@@ -309,6 +310,10 @@ class GenoStore:
         _check(self.L.gwasdev_simulate_block(self.h, seed, _ptr(bins), q, first_sample, n_total_samples), "gwasdev_simulate_block")
 
     # -- case/control
+    def set_select_mode(self, eager: bool):
+        """eager: build the compacted rows inside select_case_control; default lazy (see include/gwasdev.h)."""
+        _check(self.L.gwasdev_set_select_mode(self.h, int(bool(eager))), "gwasdev_set_select_mode")
+
     def select_case_control(self, pheno=None, *, case_mask=None, ctrl_mask=None):
         if pheno is not None:
             case_mask, ctrl_mask = stream_masks(pheno)

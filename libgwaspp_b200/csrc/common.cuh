@@ -128,12 +128,16 @@ struct gwasdev_store {
     uint32_t *d_raw = nullptr;    // [M][2][Wr]: plane1 (codes 1,3), plane2 (codes 2,3); sample c = bit c&31 of word c>>5
 
     // case/control selection
-    bool selected = false;
+    bool selected = false;        // masks, class sizes and compaction tables of the last selection are on the device
+    bool sel_built = false;       // d_sel holds the compacted rows of that selection (K0 has run)
+    bool eager_select = false;    // run K0 inside gwasdev_select_case_control (gwasdev_set_select_mode)
+    uint32_t scans_since_select = 0;
     uint32_t n_case = 0, n_ctrl = 0;
     uint32_t Pca = 0, Pco = 0;    // reference geometry of the compacted streams (16-bit blocks)
     uint32_t Wc = 0, Wt = 0;      // words per plane per class in the scan layout (multiples of 4)
     uint32_t Kc = 0, Kt = 0;      // tight word counts ceil(n/32) (pairwise layout)
-    uint32_t *d_case_mask = nullptr, *d_ctrl_mask = nullptr;   // [Wr]
+    uint32_t *d_case_mask = nullptr, *d_ctrl_mask = nullptr;   // [Wr] stream masks as given (a sample may be in both)
+    uint32_t *d_ctrl_sel_mask = nullptr;                       // [Wr] controls of the compaction: ctrl & ~case
     uint32_t *d_case_idx = nullptr, *d_ctrl_idx = nullptr;     // sample index of the k-th case / control
     uint32_t *d_sel = nullptr;    // scan layout [M][cases: Wc/4 x (p1 chunk, p2 chunk)][controls: Wt/4 x (p1 chunk, p2 chunk)]
     size_t cap_sel = 0, cap_case_idx = 0, cap_ctrl_idx = 0, cap_mask = 0;   // bytes allocated (grow-only)
@@ -179,10 +183,14 @@ struct gwasdev_store {
     void *ingest = nullptr;                                  // file / text ingestion state (ingest.cu)
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    static constexpr int MAX_PIECES = 8;                     // host-output scans: pieces whose copies overlap the next piece's scan
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_piece[MAX_PIECES] = {};
     double last_scan_ms = 0.0;
 };
 
 void gwasdev_internal_free_ingest(gwasdev_store *s);
+int gwasdev_internal_ensure_compacted(gwasdev_store *s);   // K0 on demand (store.cu)
 
 namespace gwasdev {
 // make sure sc holds at least `bytes`; contents are not preserved

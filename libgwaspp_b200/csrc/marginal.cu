@@ -229,6 +229,83 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
     }
 }
 
+// ---- select + scan in one pass --------------------------------------------------------------------------------
+// The same scan on the RAW rows with the class masks applied on the fly: the reference's
+// getCaseControlGenotypeDistribution(rIdx, ccs, ccgd) (compressed_genotype_table5.cpp:609-657), which is what
+// select_cc_maf needs when the compacted rows are used once. A row is [plane 1: Q chunks][plane 2: Q chunks]; the
+// masks (case, control-and-not-case: the compaction's classes) sit in shared memory. Six popcount streams per
+// chunk pair instead of three, no K0 and no second copy of the table: algorithmic bytes are again n_samples / 4
+// per SNP.
+__device__ __forceinline__ void accumulate_masked(const uint4 &x, const uint4 &y, const uint4 &m, HS &h1, HS &h2, HS &hb) {
+    const uint4 xm = make_uint4(x.x & m.x, x.y & m.y, x.z & m.z, x.w & m.w);
+    const uint4 ym = make_uint4(y.x & m.x, y.y & m.y, y.z & m.z, y.w & m.w);
+    hs_add4(h1, xm.x, xm.y, xm.z, xm.w);
+    hs_add4(h2, ym.x, ym.y, ym.z, ym.w);
+    hs_add4(hb, xm.x & y.x, xm.y & y.y, xm.z & y.z, xm.w & y.w);
+}
+
+template <int G, int SLOTS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+marginal_scan_masked_kernel(const uint4 *__restrict__ raw, uint32_t Q, const uint4 *__restrict__ mask_case,
+                            const uint4 *__restrict__ mask_ctrl, uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin,
+                            uint64_t snp_end, uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
+                            gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
+    extern __shared__ uint4 sm_mask[];   // [Q] case, [Q] control
+    for (uint32_t q = threadIdx.x; q < 2 * Q; q += blockDim.x) sm_mask[q] = q < Q ? mask_case[q] : mask_ctrl[q - Q];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
+    const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_snps = snp_end - snp_begin;
+    constexpr uint32_t NG = 32 / G;
+    const uint32_t my_row = l * NG + g;
+    auto batch = [&](uint64_t base, uint32_t in_batch) {
+        const uint32_t passes = (in_batch + NG - 1) / NG;
+        uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;
+        for (uint32_t it = 0; it < passes; ++it) {
+            const uint32_t brow = it * NG + g;
+            const bool valid = brow < in_batch;
+            const uint4 *row = raw + (base + (valid ? brow : 0)) * (uint64_t)(2 * Q);
+            HS a1 = {0, 0, 0}, a2 = {0, 0, 0}, ab = {0, 0, 0}, b1 = {0, 0, 0}, b2 = {0, 0, 0}, bb = {0, 0, 0};
+            for (uint32_t q0 = l; q0 < Q; q0 += SLOTS * G) {
+                uint4 x[SLOTS], y[SLOTS];
+#pragma unroll
+                for (int u = 0; u < SLOTS; ++u) {
+                    const uint32_t q = q0 + u * G;
+                    x[u] = make_uint4(0, 0, 0, 0); y[u] = x[u];
+                    if (valid && q < Q) {
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(x[u].x), "=r"(x[u].y), "=r"(x[u].z), "=r"(x[u].w) : "l"(row + q));
+                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(y[u].x), "=r"(y[u].y), "=r"(y[u].z), "=r"(y[u].w) : "l"(row + Q + q));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SLOTS; ++u) {
+                    const uint32_t q = q0 + u * G;
+                    if (q < Q) {
+                        accumulate_masked(x[u], y[u], sm_mask[q], a1, a2, ab);
+                        accumulate_masked(x[u], y[u], sm_mask[Q + q], b1, b2, bb);
+                    }
+                }
+            }
+            uint32_t s1 = hs_total(a1), s2 = hs_total(a2), sb = hs_total(ab), t1 = hs_total(b1), t2 = hs_total(b2), tb = hs_total(bb);
+            s1 = __reduce_add_sync(group_mask, s1); s2 = __reduce_add_sync(group_mask, s2);
+            sb = __reduce_add_sync(group_mask, sb); t1 = __reduce_add_sync(group_mask, t1);
+            t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
+            if (l == it) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
+        }
+        if (my_row < in_batch)
+            finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + my_row - out_base, counts, mi, stats);
+    };
+    const uint64_t rounds = n_snps / (n_warps * 32);
+    for (uint64_t r = 0; r < rounds; ++r) batch(snp_begin + (r * n_warps + warp) * 32, 32);
+    const uint64_t rem_begin = snp_begin + rounds * n_warps * 32, rem = snp_end - rem_begin;
+    const uint64_t b0 = rem_begin + warp * rem / n_warps, b1 = rem_begin + (warp + 1) * rem / n_warps;
+    for (uint64_t base = b0; base < b1; base += 32) batch(base, (uint32_t)min((uint64_t)32, b1 - base));
+}
+
 // Streaming in sample blocks: counts are additive over disjoint sample blocks of one cohort.
 __global__ void add_counts_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ acc, uint64_t n4) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,7 +356,7 @@ __global__ void raw_counts_kernel(const uint32_t *__restrict__ raw, uint32_t Wr,
 using namespace gwasdev;
 
 // Launch the scan with DEVICE output pointers (any may be NULL). Outputs are indexed from snp_begin.
-int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
+static int scan_compacted(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
                           gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats) {
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
@@ -298,7 +375,6 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     int slots = 5, minb = 3, interleave = 1;
     if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d,%d,%d", &slots, &minb, &G, &interleave);
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * minb, (n + 255) / 256));
-    GW_CUDA(cudaEventRecord(s->ev0, s->stream));
 #define SCAN_LAUNCH(GG, SS, BB)                                                                                          \
     marginal_scan_kernel<GG, SS, BB><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, \
                                                                     snp_end, d_counts, d_mi, d_stats, snp_begin, interleave)
@@ -319,8 +395,79 @@ int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
 #undef SCAN_CFG
 #undef SCAN_LAUNCH
     GW_LAUNCHED();
+    return GWASDEV_OK;
+}
+
+// Compacted scan for the other translation units (margins of the pairwise screen, probes): builds the compacted
+// layout when it is missing and times the kernel for gwasdev_last_scan_ms.
+int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
+                          gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats) {
+    { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
+    GW_CUDA(cudaEventRecord(s->ev0, s->stream));
+    const int rc = scan_compacted(s, snp_begin, snp_end, d_counts, d_mi, d_stats);
+    if (rc != GWASDEV_OK) return rc;
     GW_CUDA(cudaEventRecord(s->ev1, s->stream));
     return GWASDEV_OK;
+}
+
+// The masked scan over the raw rows (no compacted store needed). Same outputs as gwasdev_internal_scan.
+static int scan_masked(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
+                       gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats, uint64_t out_base) {
+    int sms = 0;
+    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const uint32_t Q = s->Wr / 4;
+    int G = 8;
+    double best = 1e30;
+    for (int cand : {8, 16, 32}) {
+        const double waste = (double)((Q + cand - 1) / cand) * cand / (double)Q;
+        if (waste < best - 1e-9) { best = waste; G = cand; }
+    }
+    int slots = 2, minb = 4;   // B200 sweep (tools/sweep_mscan.py): the kernel is ALU-bound, occupancy pays more than loads in flight
+    if (const char *cfg = getenv("GWASDEV_MSCAN_CFG")) sscanf(cfg, "%d,%d,%d", &slots, &minb, &G);
+    const uint64_t n = snp_end - snp_begin;
+    const size_t smem = 2ull * Q * sizeof(uint4);
+    GW_REQUIRE(smem <= 200 * 1024, "masked scan: %u samples exceed the shared-memory mask buffer", s->N);
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * minb, (n + 255) / 256));
+    const uint4 *raw = reinterpret_cast<const uint4 *>(s->d_raw);
+    const uint4 *mca = reinterpret_cast<const uint4 *>(s->d_case_mask), *mco = reinterpret_cast<const uint4 *>(s->d_ctrl_sel_mask);
+#define MSCAN(GG, SS, BB)                                                                                                          \
+    do {                                                                                                                           \
+        if (smem > 48 * 1024) GW_CUDA(cudaFuncSetAttribute(marginal_scan_masked_kernel<GG, SS, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        marginal_scan_masked_kernel<GG, SS, BB><<<blocks, 256, smem, s->stream>>>(raw, Q, mca, mco, s->n_case, s->n_ctrl, snp_begin, \
+                                                                                 snp_end, d_counts, d_mi, d_stats, out_base);      \
+    } while (0)
+#define MSCAN_G(GG)                                                                                  \
+    do {                                                                                             \
+        if (slots == 2 && minb == 3) MSCAN(GG, 2, 3);                                                \
+        else if (slots == 3 && minb == 3) MSCAN(GG, 3, 3);                                           \
+        else if (slots == 4 && minb == 3) MSCAN(GG, 4, 3);                                           \
+        else if (slots == 4 && minb == 2) MSCAN(GG, 4, 2);                                           \
+        else if (slots == 6 && minb == 2) MSCAN(GG, 6, 2);                                           \
+        else if (slots == 2 && minb == 4) MSCAN(GG, 2, 4);                                           \
+        else if (slots == 3 && minb == 4) MSCAN(GG, 3, 4);                                           \
+        else if (slots == 2 && minb == 5) MSCAN(GG, 2, 5);                                           \
+        else if (slots == 1 && minb == 5) MSCAN(GG, 1, 5);                                           \
+        else if (slots == 1 && minb == 6) MSCAN(GG, 1, 6);                                           \
+        else if (slots == 2 && minb == 6) MSCAN(GG, 2, 6);                                           \
+        else { set_error("GWASDEV_MSCAN_CFG=%d,%d is not an instantiated configuration", slots, minb); return GWASDEV_EINVAL; } \
+    } while (0)
+    if (G == 8) MSCAN_G(8);
+    else if (G == 16) MSCAN_G(16);
+    else MSCAN_G(32);
+#undef MSCAN_G
+#undef MSCAN
+    GW_LAUNCHED();
+    return GWASDEV_OK;
+}
+
+// one scan of [b, e) with the kernel the store's state calls for; outputs indexed from out_base
+static int scan_dispatch(gwasdev_store *s, bool masked, uint64_t b, uint64_t e, uint32_t *d_counts, gwasdev_marginal_information *d_mi,
+                         gwasdev_snp_stats *d_stats, uint64_t out_base) {
+    if (masked)
+        return scan_masked(s, b, e, d_counts ? d_counts + 8 * (b - out_base) : nullptr, d_mi ? d_mi + (b - out_base) : nullptr,
+                           d_stats ? d_stats + (b - out_base) : nullptr, b);
+    return scan_compacted(s, b, e, d_counts ? d_counts + 8 * (b - out_base) : nullptr, d_mi ? d_mi + (b - out_base) : nullptr,
+                          d_stats ? d_stats + (b - out_base) : nullptr);
 }
 
 extern "C" {
@@ -335,9 +482,18 @@ int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     GW_CUDA(cudaSetDevice(s->device));
     const uint64_t n = snp_end - snp_begin;
     const bool full = snp_begin == 0 && snp_end == s->M;
+    // Which kernel: the compacted layout when it exists; otherwise the first scan after a selection counts through the
+    // masks on the raw rows (no K0), and a second scan builds the compacted layout, which every later scan streams
+    // with half the popcount work per byte.
+    const bool masked = !s->sel_built && s->scans_since_select == 0 && !getenv("GWASDEV_NO_MASKED_SCAN");
+    ++s->scans_since_select;
+    if (!masked) { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
+    GW_CUDA(cudaEventRecord(s->ev0, s->stream));   // ev0..ev1: the scan kernel(s) of this call (gwasdev_last_scan_ms)
     if (on_device) {
-        int rc = gwasdev_internal_scan(s, snp_begin, snp_end, counts, mi, stats);
-        return rc;
+        const int rc = scan_dispatch(s, masked, snp_begin, snp_end, counts, mi, stats, snp_begin);
+        if (rc != GWASDEV_OK) return rc;
+        GW_CUDA(cudaEventRecord(s->ev1, s->stream));
+        return GWASDEV_OK;
     }
     uint32_t *d_counts = nullptr;
     gwasdev_marginal_information *d_mi = nullptr;
@@ -350,12 +506,28 @@ int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
             d_mi = s->d_mi;
         } else { GW_CUDA(reserve(s->sc_out_mi, n * sizeof(gwasdev_marginal_information))); d_mi = (gwasdev_marginal_information *)s->sc_out_mi.p; }
     }
-    int rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, d_mi, d_stats);
-    if (rc != GWASDEV_OK) return rc;
+    // Host outputs: the SNP range is scanned in pieces and every piece's results leave on a second stream while the
+    // next piece is scanned, so the PCIe copy (96 to 288 bytes per SNP) overlaps the scan.
+    if (!s->copy_stream) {
+        GW_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t &e : s->ev_piece) GW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const uint64_t out_bytes = n * ((counts ? 32 : 0) + (stats ? sizeof(gwasdev_snp_stats) : 0) + (mi ? sizeof(gwasdev_marginal_information) : 0));
+    const int pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(gwasdev_store::MAX_PIECES, out_bytes / (4ull << 20)));
     cudaError_t e = cudaSuccess;
-    if (counts) e = cudaMemcpyAsync(counts, d_counts, n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess && stats) e = cudaMemcpyAsync(stats, d_stats, n * sizeof(gwasdev_snp_stats), cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess && mi) e = cudaMemcpyAsync(mi, d_mi, n * sizeof(gwasdev_marginal_information), cudaMemcpyDeviceToHost, s->stream);
+    for (int p = 0; p < pieces && e == cudaSuccess; ++p) {
+        const uint64_t b = snp_begin + n * p / pieces, en = snp_begin + n * (p + 1) / pieces, o = b - snp_begin, k = en - b;
+        if (k == 0) continue;
+        int rc = scan_dispatch(s, masked, b, en, d_counts, d_mi, d_stats, snp_begin);
+        if (rc != GWASDEV_OK) return rc;
+        e = cudaEventRecord(s->ev_piece[p], s->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s->copy_stream, s->ev_piece[p], 0);
+        if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts + 8 * o, d_counts + 8 * o, k * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream);
+        if (e == cudaSuccess && stats) e = cudaMemcpyAsync(stats + o, d_stats + o, k * sizeof(gwasdev_snp_stats), cudaMemcpyDeviceToHost, s->copy_stream);
+        if (e == cudaSuccess && mi) e = cudaMemcpyAsync(mi + o, d_mi + o, k * sizeof(gwasdev_marginal_information), cudaMemcpyDeviceToHost, s->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(s->ev1, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->copy_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) { set_error("gwasdev_marginal_scan: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     if (mi && full) { s->mi_valid = true; s->side_valid = false; s->mma_side_valid = false; }
@@ -372,7 +544,9 @@ int gwasdev_marginal_accumulate(gwasdev_store *s, uint64_t snp_begin, uint64_t s
     const uint64_t n = snp_end - snp_begin;
     GW_CUDA(reserve(s->sc_out_counts, n * 8 * sizeof(uint32_t)));
     uint32_t *d_counts = (uint32_t *)s->sc_out_counts.p, *d_acc = acc;
-    int rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, nullptr, nullptr);
+    // a block's rows are used once: count through the masks unless the compacted layout already exists
+    int rc = s->sel_built ? gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, nullptr, nullptr)
+                          : scan_masked(s, snp_begin, snp_end, d_counts, nullptr, nullptr, snp_begin);
     if (rc != GWASDEV_OK) return rc;
     if (!on_device) {
         GW_CUDA(reserve(s->sc_stage, n * 8 * sizeof(uint32_t)));

@@ -273,14 +273,14 @@ int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_stor
 static void free_scratch(gwasdev_store::Scratch &sc) { if (sc.p) cudaFree(sc.p); sc.p = nullptr; sc.cap = 0; }
 
 static void invalidate_selection(gwasdev_store *s) {
-    s->selected = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mma_side_valid = false;
+    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mma_side_valid = false;
 }
 
 void gwasdev_destroy(gwasdev_store *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     gwasdev_internal_free_ingest(s);
-    cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
+    cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_ctrl_sel_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
     cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
     free(s->tmap); free(s->tmap_mm);
     cudaFree(s->d_mm); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col);
@@ -294,6 +294,8 @@ void gwasdev_destroy(gwasdev_store *s) {
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
     if (s->ev3) cudaEventDestroy(s->ev3);
+    for (cudaEvent_t e : s->ev_piece) if (e) cudaEventDestroy(e);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
 }
 
@@ -522,7 +524,6 @@ int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, con
     s->Kt = (nco + 31) / 32;
     s->Wc = round_up(std::max(s->Kc, 1u), 4);
     s->Wt = round_up(std::max(s->Kt, 1u), 4);
-    const uint32_t stride = 2 * (s->Wc + s->Wt);
     std::vector<uint32_t> bca, bco;
     build_select_tables(mca, nca, s->Kc, bca);
     build_select_tables(mco_sel, nco, s->Kt, bco);
@@ -530,14 +531,67 @@ int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, con
     { size_t cap2 = s->d_ctrl_mask ? s->cap_mask : 0; GW_CUDA(reserve_raw(s->d_ctrl_mask, cap2, s->Wr * 4ull)); }
     GW_CUDA(reserve_raw(s->d_case_idx, s->cap_case_idx, bca.size() * 4));
     GW_CUDA(reserve_raw(s->d_ctrl_idx, s->cap_ctrl_idx, bco.size() * 4));
-    GW_CUDA(reserve_raw(s->d_sel, s->cap_sel, s->M * (uint64_t)stride * 4));
+    { size_t cap3 = s->d_ctrl_sel_mask ? s->cap_mask : 0; GW_CUDA(reserve_raw(s->d_ctrl_sel_mask, cap3, s->Wr * 4ull)); }
     GW_CUDA(cudaMemcpyAsync(s->d_case_mask, mca.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->d_ctrl_mask, mco.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->d_case_idx, bca.data(), bca.size() * 4, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->d_ctrl_idx, bco.data(), bco.size() * 4, cudaMemcpyHostToDevice, s->stream));
+    GW_CUDA(cudaMemcpyAsync(s->d_ctrl_sel_mask, mco_sel.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
+    GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
+    s->selected = true;
+    s->sel_built = false;
+    s->scans_since_select = 0;
+    // Compaction (K0) is deferred until something needs the compacted layout (pairwise screen, layout probes, a
+    // second marginal scan): the first marginal scan after a selection counts through the masks on the raw rows,
+    // the reference's own mask-on-the-fly overload (compressed_genotype_table5.cpp:609-657), and needs no K0.
+    if (s->eager_select) return gwasdev_internal_ensure_compacted(s);
+    return GWASDEV_OK;
+}
+
+int gwasdev_set_select_mode(gwasdev_store *s, int eager) {
+    GW_REQUIRE(s != nullptr, "gwasdev_set_select_mode: NULL store");
+    s->eager_select = eager != 0;
+    return GWASDEV_OK;
+}
+
+int gwasdev_case_control_counts(gwasdev_store *s, uint32_t *n_case, uint32_t *n_ctrl) {
+    GW_REQUIRE(s && s->selected, "gwasdev_case_control_counts: no case/control selection");
+    if (n_case) *n_case = s->n_case;
+    if (n_ctrl) *n_ctrl = s->n_ctrl;
+    return GWASDEV_OK;
+}
+
+int gwasdev_get_selected_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint16_t *rows) {
+    GW_REQUIRE(s && rows, "gwasdev_get_selected_rows: NULL argument");
+    GW_REQUIRE(s->selected, "gwasdev_get_selected_rows: call gwasdev_select_case_control first");
+    GW_REQUIRE(first_row + n_rows <= s->M, "gwasdev_get_selected_rows: rows outside the table");
+    if (n_rows == 0) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
+    const uint64_t S = 2ull * (s->Pca + s->Pco);
+    GW_CUDA(reserve(s->sc_stage, n_rows * S * 2));
+    uint16_t *d_out = (uint16_t *)s->sc_stage.p;
+    export_selected_kernel<<<(unsigned)n_rows, 128, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, s->Pca, s->Pco, d_out, first_row);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rows, d_out, n_rows * S * 2, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) { set_error("gwasdev_get_selected_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    return GWASDEV_OK;
+}
+
+}  // extern "C"
+
+// K0 on demand: builds the compacted scan layout from the raw rows with the tables of the last selection.
+int gwasdev_internal_ensure_compacted(gwasdev_store *s) {
+    GW_REQUIRE(s->selected, "call gwasdev_select_case_control first");
+    if (s->sel_built) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint32_t stride = 2 * (s->Wc + s->Wt);
+    GW_CUDA(reserve_raw(s->d_sel, s->cap_sel, s->M * (uint64_t)stride * 4));
     SelectTables ta, to;
-    ta.m = s->d_case_idx; ta.mv = ta.m + s->Wr; ta.rank = ta.m + 6ull * s->Wr; ta.first = ta.rank + s->Wr + 1; ta.n_class = nca; ta.Kout = s->Kc;
-    to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.n_class = nco; to.Kout = s->Kt;
+    ta.m = s->d_case_idx; ta.mv = ta.m + s->Wr; ta.rank = ta.m + 6ull * s->Wr; ta.first = ta.rank + s->Wr + 1; ta.n_class = s->n_case; ta.Kout = s->Kc;
+    to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.n_class = s->n_ctrl; to.Kout = s->Kt;
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const bool trace = getenv("GWASDEV_TRACE") != nullptr;
@@ -558,44 +612,20 @@ int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, con
         select_kernel<false, 1><<<grid, 256, smem_rows / SNPS, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
     }
     GW_LAUNCHED();
-    if (trace) cudaEventRecord(s->ev3, s->stream);
-    GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
-    if (trace) { float ms = 0.f; cudaEventElapsedTime(&ms, s->ev2, s->ev3); fprintf(stderr, "[gwasdev trace] select_kernel %.3f ms\n", ms); }
-    s->selected = true;
+    if (trace) {
+        cudaEventRecord(s->ev3, s->stream);
+        GW_CUDA(cudaStreamSynchronize(s->stream));
+        float ms = 0.f; cudaEventElapsedTime(&ms, s->ev2, s->ev3); fprintf(stderr, "[gwasdev trace] select_kernel %.3f ms\n", ms);
+    }
+    s->sel_built = true;
     return GWASDEV_OK;
 }
-
-int gwasdev_case_control_counts(gwasdev_store *s, uint32_t *n_case, uint32_t *n_ctrl) {
-    GW_REQUIRE(s && s->selected, "gwasdev_case_control_counts: no case/control selection");
-    if (n_case) *n_case = s->n_case;
-    if (n_ctrl) *n_ctrl = s->n_ctrl;
-    return GWASDEV_OK;
-}
-
-int gwasdev_get_selected_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, uint16_t *rows) {
-    GW_REQUIRE(s && rows, "gwasdev_get_selected_rows: NULL argument");
-    GW_REQUIRE(s->selected, "gwasdev_get_selected_rows: call gwasdev_select_case_control first");
-    GW_REQUIRE(first_row + n_rows <= s->M, "gwasdev_get_selected_rows: rows outside the table");
-    if (n_rows == 0) return GWASDEV_OK;
-    GW_CUDA(cudaSetDevice(s->device));
-    const uint64_t S = 2ull * (s->Pca + s->Pco);
-    GW_CUDA(reserve(s->sc_stage, n_rows * S * 2));
-    uint16_t *d_out = (uint16_t *)s->sc_stage.p;
-    export_selected_kernel<<<(unsigned)n_rows, 128, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, s->Pca, s->Pco, d_out, first_row);
-    ++g_launches;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(rows, d_out, n_rows * S * 2, cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    if (e != cudaSuccess) { set_error("gwasdev_get_selected_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
-    return GWASDEV_OK;
-}
-
-}  // extern "C"
 
 // Builds the pairwise layout on first use (called from pairwise.cu).
 int gwasdev_internal_build_pairwise(gwasdev_store *s) {
     if (s->pw_built) return GWASDEV_OK;
     GW_REQUIRE(s->selected, "pairwise layout: call gwasdev_select_case_control first");
+    { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
     const uint32_t K = s->Kc + s->Kt;
     GW_CUDA(reserve_raw(s->d_pw, s->cap_pw, 3ull * K * s->Mpad * 4));
     dim3 block(32, 8), grid((unsigned)((s->Mpad + 31) / 32), (K + 7) / 8);

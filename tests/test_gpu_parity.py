@@ -79,6 +79,48 @@ def test_marginal_scan_matches_reference_golden(orc, name):
         assert np.array_equal(whole[:, 3], codes.shape[1] - g["whole"][:, :3].sum(1))   # what inline_maf_print prints
 
 
+@pytest.mark.parametrize("N,cfg", [(677, None), (2000, "3,3,16"), (3900, "2,3,32"), (130, "4,2,8"), (1111, "6,2,16")])
+def test_fused_select_scan_equals_compacted_scan(orc, monkeypatch, N, cfg):
+    """The first scan after a selection counts through the masks on the raw rows (no compaction, the reference's
+    mask-on-the-fly overload compressed_genotype_table5.cpp:609-657); later scans stream the compacted rows (:703-747).
+    Both must give the oracle's counts and bit-identical statistics -- also when samples belong to neither class or are
+    flagged in both masks (a case for the compaction, :541-561), and for every lane-group width of the kernels."""
+    if cfg:
+        monkeypatch.setenv("GWASDEV_MSCAN_CFG", cfg)             # loads in flight, CTAs per SM, lanes per row
+    M = 301
+    codes, _ = orc.simulate(77 + N, M, N, N // 2, missing_rate=0.03)
+    rng = np.random.default_rng(N)
+    pheno = rng.choice([0, 1, 2], size=N, p=[0.45, 0.4, 0.15]).astype(np.uint8)          # 2 = neither
+    rows = orc.pack_codes(codes)
+    ca, co = gw.stream_masks(pheno)
+    both = rng.choice(N, 9, replace=False)
+    for c in both:                                                                        # flagged in both masks
+        ca[c >> 4] |= np.uint16(1 << (c & 15))
+        co[c >> 4] |= np.uint16(1 << (c & 15))
+    eff = pheno.copy()
+    eff[both] = 1
+    sel, nca, nco = orc.select(rows, N, eff)
+    want = orc.cc_counts_selected(sel, nca, nco)
+    with gw.GenoStore(M, N) as lazy, gw.GenoStore(M, N) as eager:
+        eager.set_select_mode(True)
+        outs = []
+        for st in (lazy, eager):
+            st.put_rows(rows)
+            st.select_case_control(case_mask=ca, ctrl_mask=co)
+            assert (st.n_case, st.n_ctrl) == (nca, nco)
+            outs.append(st.marginal_scan())
+        second = lazy.marginal_scan()                                                     # compacted rows, built on demand
+        for o in outs + [second]:
+            assert np.array_equal(o["counts"], want)
+            for k in ("mi", "stats"):
+                assert o[k].tobytes() == outs[1][k].tobytes()
+        assert np.array_equal(lazy.get_selected_rows(), sel) and np.array_equal(eager.get_selected_rows(), sel)
+        # sub-range as the first scan after a new selection (masked kernel with a row offset)
+        lazy.select_case_control(case_mask=ca, ctrl_mask=co)
+        sub = lazy.marginal_scan(17, 230)
+        assert np.array_equal(sub["counts"], want[17:230]) and sub["stats"].tobytes() == outs[1]["stats"][17:230].tobytes()
+
+
 @pytest.mark.parametrize("name", COHORTS)
 def test_pair_tables_all_overloads(orc, name):
     g = load_golden(name)
