@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 SEED = 20121127
 MARGINAL = dict(n_snps=500_000, n_samples=10_000, n_case=5_000)       # BASELINE.json configs[1]
 PAIRWISE = dict(n_snps=50_000, n_samples=4_000, n_case=2_000)         # BASELINE.json configs[2]
+PAIRWISE_CFG3 = dict(n_snps=500_000, n_samples=10_000, n_case=5_000)  # BASELINE.json configs[3] (multi-GPU runs)
 NCU_TRAFFIC_MARGINAL = 1.2930e9       # dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r1k_marginal_scan_full.md)
 NCU_TRAFFIC_PAIRWISE = 1.9517e10      # same for pair_screen_mma_kernel at configs[2] on one GPU (profiles/r1h_pair_screen_mma_full.md)
 CPU_MARGINAL_SAMPLE_SNPS = 2_000
@@ -277,6 +278,10 @@ def gpu_arm(args):
     if not args.no_pairwise:
         out["pairwise"] = pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks,
                                        sum_over_ranks, sampler)
+        if world > 1 and not args.no_cfg3 and not args.pw_snps:
+            # BASELINE.json configs[3]: the north star's target problem, sharded by tile pairs over the ranks
+            out["pairwise_configs3"] = pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks,
+                                                    sum_over_ranks, sampler, shape=PAIRWISE_CFG3)
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline_marginal(N, NCASE, threads=1, steps=3)
@@ -351,9 +356,13 @@ def biobank_gpu(args, gw, torch, local, stream, peaks, peak_src):
     return res
 
 
-def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks, sum_over_ranks, sampler):
-    M, N, NCASE = args.pw_snps or PAIRWISE["n_snps"], args.pw_samples or PAIRWISE["n_samples"], args.pw_cases or PAIRWISE["n_case"]
-    K, W = max(1, min(args.steps, args.pw_steps)), min(args.warmup, 3)
+def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks, sum_over_ranks, sampler, shape=None):
+    if shape is None:
+        M, N, NCASE = args.pw_snps or PAIRWISE["n_snps"], args.pw_samples or PAIRWISE["n_samples"], args.pw_cases or PAIRWISE["n_case"]
+        K, W = max(1, min(args.steps, args.pw_steps)), min(args.warmup, 3)
+    else:   # configs[3]: every pass is 0.4 s (8 GPUs) to 1.4 s (2 GPUs) of tensor-core work
+        M, N, NCASE = shape["n_snps"], shape["n_samples"], shape["n_case"]
+        K, W = max(1, min(args.steps, 2)), 1
     st = gw.GenoStore(M, N, device=local)
     st.set_stream(stream.cuda_stream)
     st.simulate(SEED)                                          # the store is replicated on every rank
@@ -581,6 +590,7 @@ def main():
     ap.add_argument("--pw-cases", type=int, default=0)
     ap.add_argument("--pw-steps", type=int, default=5)
     ap.add_argument("--no-pairwise", action="store_true")
+    ap.add_argument("--no-cfg3", action="store_true", help="N > 1: skip the configs[3] (5k/5k x 500k SNPs) pairwise section")
     ap.add_argument("--biobank", action="store_true", help="add the configs[4] biobank-scale section (needs ~110 GB of HBM)")
     ap.add_argument("--bb-snps", type=int, default=1_000_000)
     ap.add_argument("--bb-stream-snps", type=int, default=100_000)

@@ -56,7 +56,11 @@ def full(src, dst, cmd):
     idx = {h: i for i, h in enumerate(hdr)}
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary\n\ncommand: `{cmd}`\n\nsource report: `{src}` (scratch, not committed)\n\n")
+        seen = set()
         for r in rows[2:]:
+            if r[idx["Kernel Name"]] in seen:      # one launch per kernel (the first captured)
+                continue
+            seen.add(r[idx["Kernel Name"]])
             f.write(f"## `{r[idx['Kernel Name']][:110]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
             for k in KEYS:
                 if k in idx:
