@@ -238,6 +238,14 @@ GWASDEV_API int gwasdev_gtest(gwasdev_store *s, uint64_t n, const uint32_t *pi, 
 GWASDEV_API int gwasdev_pairwise_epi_test(int device, uint64_t n, const int32_t *cs, const int32_t *ct, double *ll,
                               double *pval);
 
+/* The pair loop of EpistasisPerformance / EpistasisDebug (epistasis_func.cpp:263-347) for n given pairs: the pair's
+ * case/control tables by overload `mode` (as gwasdev_pair_tables; the reference uses mode 1), then the likelihood-ratio
+ * test of src/test/pairwise.c:50-133 on their 3x3 cores and pchisq(ll, 4, 0, 0), without shipping the tables to the
+ * host. (The reference's C++ copy of the test, epistasis_func.cpp:723-892, reads the 4x4 table as if it were 3x3;
+ * the C file is its clean form and the parity target) */
+GWASDEV_API int gwasdev_epi_pairs(gwasdev_store *s, uint64_t n, const uint32_t *pi, const uint32_t *pj, int mode, double *ll,
+                      double *pval);
+
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* Register-only __popc throughput in 32-bit word-cells (AND+POPC) per second on `device`; the
  * integer-pipe roofline denominator of the pairwise screen. */

@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "gwasdev_popc_peak", "gwasdev_hbm_read_peak", "gwasdev_set_pair_engine", "gwasdev_mma_tile_counts",
     "gwasdev_ksa_screen_mma_f32", "gwasdev_pack_row_text_block", "gwasdev_simulate_block", "gwasdev_marginal_accumulate",
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
-    "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode",
+    "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs",
 ]
 
 
@@ -98,6 +98,7 @@ def load_library():
     L.gwasdev_marginal_finalize.argtypes = [i32, u64, vp, vp, vp, i32]
     L.gwasdev_set_pair_engine.argtypes = [vp, i32]
     L.gwasdev_set_select_mode.argtypes = [vp, i32]
+    L.gwasdev_epi_pairs.argtypes = [vp, u64, vp, vp, i32, vp, vp]
     L.gwasdev_put_tped_text.argtypes = [vp, u64, vp, C.c_size_t, C.POINTER(u64), C.POINTER(C.c_size_t)]
     L.gwasdev_tped_dims.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u32)]
     L.gwasdev_load_tped.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64)]
@@ -415,6 +416,13 @@ class GenoStore:
         s, z = np.zeros(len(pi)), np.zeros(len(pi))
         _check(self.L.gwasdev_gtest(self.h, len(pi), _ptr(pi), _ptr(pj), _ptr(s), _ptr(z)), "gwasdev_gtest")
         return s, z
+
+    def epi_pairs(self, pi, pj, mode: int = 1):
+        """EpistasisPerformance's pair body: tables by overload `mode`, pairwise.c likelihood-ratio test, pchisq(ll, 4)."""
+        pi, pj = self._pairs(pi, pj)
+        ll, p = np.zeros(len(pi)), np.zeros(len(pi))
+        _check(self.L.gwasdev_epi_pairs(self.h, len(pi), _ptr(pi), _ptr(pj), mode, _ptr(ll), _ptr(p)), "gwasdev_epi_pairs")
+        return ll, p
 
     def pairwise_scan(self, threshold: float = 30.0, shard: int = 0, n_shards: int = 1, capacity: int = 1 << 20,
                       hits=None, on_device: bool = False):

@@ -18,7 +18,8 @@ using namespace libgwaspp::algorithms;
 
 static void usage() {
     std::cerr << "usage: gwas_b200 -g X.tped -p X.tfam [-o out] [--device N] "
-                 "(--test-inline-maf | --select-cc-maf | --inline-cc-maf | --dist-perform | --test-boost-epi)\n";
+                 "(--test-inline-maf | --select-cc-maf | --inline-cc-maf | --dist-perform | --test-boost-epi | "
+                 "--contin-debug | --contin-perform | --contin-cc-perform | --epi-debug | --epi-perform)\n";
 }
 
 int main(int argc, char **argv) {
@@ -133,6 +134,11 @@ int main(int argc, char **argv) {
     else if (test == "inline-cc-maf") compute(inline_cc_maf, &gd, out);
     else if (test == "dist-perform") compute(genotype_dist_performance, &gd, out);
     else if (test == "test-boost-epi") compute(computeBoost, &gd, out);
+    else if (test == "contin-debug") compute(ContingencyDebug, &gd, out);
+    else if (test == "contin-perform") compute(ContingencyPerformance, &gd, out);
+    else if (test == "contin-cc-perform") compute(ContingencyCCPerformance, &gd, out);
+    else if (test == "epi-debug") compute(EpistasisDebug, &gd, out);
+    else if (test == "epi-perform") compute(EpistasisPerformance, &gd, out);
     else { usage(); return 1; }
     std::cout << "DONE" << std::endl;
     return 0;

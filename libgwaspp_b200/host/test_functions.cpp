@@ -129,6 +129,119 @@ void genotype_dist_performance(GeneticData *gd, std::ostream *out) {
     for (int i = 0; i < M; ++i) { *out << (int)i; print_lapse(*out, "\t", per); *out << std::endl; }
 }
 
+// genetics/genotype/common_genotype_func.cpp:37-55 without the header row
+void printContingencyTable(const CONTIN_TABLE_T &ct, std::ostream &out) {
+    out << std::dec;
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 4; ++j) out << "\t" << ct.contin[i * 4 + j];
+        out << std::endl;
+    }
+}
+
+namespace {
+const size_t PAIR_BATCH = 1u << 18;
+// all pairs i < j of M markers in the reference's loop order, PAIR_BATCH at a time
+template <class F> void for_pair_batches(uint M, F f) {
+    std::vector<uint> pi, pj;
+    pi.reserve(PAIR_BATCH); pj.reserve(PAIR_BATCH);
+    uint64_t k0 = 0;
+    for (uint i = 0; i < M; ++i)
+        for (uint j = i + 1; j < M; ++j) {
+            pi.push_back(i); pj.push_back(j);
+            if (pi.size() == PAIR_BATCH) { f(k0, pi, pj); k0 += pi.size(); pi.clear(); pj.clear(); }
+        }
+    if (!pi.empty()) f(k0, pi, pj);
+}
+// EpistasisDebug / EpistasisPerformance build their own set: cases 0, 2, .., 398; controls 1, 3, .., 399 (:270-279)
+void fixed_epistasis_set(CaseControlSet &ccs) {
+    std::set<int> cases, ctrls;
+    for (int i = 0; i < 200; ++i) { cases.insert(i << 1); ctrls.insert((i << 1) + 1); }
+    ccs.setCases(cases);
+    ccs.setControls(ctrls);
+}
+}  // namespace
+
+void ContingencyDebug(GeneticData *gd, std::ostream *out) {
+    DeviceGenoTable &gt = *gd->getGenotypeTable();
+    std::vector<uint> tab;
+    for_pair_batches((uint)gd->getGenotypedMarkersCount(), [&](uint64_t, const std::vector<uint> &pi, const std::vector<uint> &pj) {
+        tab.resize(pi.size() * 32);
+        int rc = gwasdev_pair_tables(gt.handle(), pi.size(), pi.data(), pj.data(), 0, tab.data());
+        assert(rc == GWASDEV_OK); (void)rc;
+        for (size_t q = 0; q < pi.size(); ++q) {
+            *out << (int)pi[q] << " x " << (int)pj[q] << "\n";
+            printContingencyTable(*reinterpret_cast<const CONTIN_TABLE_T *>(&tab[32 * q]), *out);
+            *out << "\n";
+        }
+    });
+}
+
+namespace {
+// one timing line per pair (k, lapse): the batched call's time is shared out evenly
+void timed_tables(GeneticData *gd, std::ostream *out, int mode) {
+    DeviceGenoTable &gt = *gd->getGenotypeTable();
+    std::vector<uint> tab;
+    for_pair_batches((uint)gd->getGenotypedMarkersCount(), [&](uint64_t k0, const std::vector<uint> &pi, const std::vector<uint> &pj) {
+        tab.resize(pi.size() * 32);
+        Lap lap;
+        int rc = gwasdev_pair_tables(gt.handle(), pi.size(), pi.data(), pj.data(), mode, tab.data());
+        assert(rc == GWASDEV_OK); (void)rc;
+        const double per = lap.seconds() / (double)pi.size();
+        for (size_t q = 0; q < pi.size(); ++q) { *out << (int)(k0 + q); print_lapse(*out, "\t", per); *out << std::endl; }
+    });
+}
+}  // namespace
+
+void ContingencyPerformance(GeneticData *gd, std::ostream *out) { timed_tables(gd, out, 0); }
+
+void ContingencyCCPerformance(GeneticData *gd, std::ostream *out) {
+    DeviceGenoTable &gt = *gd->getGenotypeTable();
+    gt.selectCaseControl(*gd->getCaseControlSet());      // pre-select, margins are computed on first use (:150-156)
+    timed_tables(gd, out, 3);
+}
+
+void EpistasisDebug(GeneticData *gd, std::ostream *out) {
+    DeviceGenoTable &gt = *gd->getGenotypeTable();
+    CaseControlSet ccs(gd->getGenotypedIndividualsCount());
+    fixed_epistasis_set(ccs);
+    gt.selectCaseControl(ccs);
+    std::vector<uint> tab;
+    std::vector<double> ll, pval;
+    for_pair_batches((uint)gd->getGenotypedMarkersCount(), [&](uint64_t, const std::vector<uint> &pi, const std::vector<uint> &pj) {
+        tab.resize(pi.size() * 32); ll.resize(pi.size()); pval.resize(pi.size());
+        int rc = gwasdev_pair_tables(gt.handle(), pi.size(), pi.data(), pj.data(), 1, tab.data());
+        assert(rc == GWASDEV_OK);
+        rc = gwasdev_epi_pairs(gt.handle(), pi.size(), pi.data(), pj.data(), 1, ll.data(), pval.data());
+        assert(rc == GWASDEV_OK); (void)rc;
+        for (size_t q = 0; q < pi.size(); ++q) {
+            *out << (int)pi[q] << " x " << (int)pj[q] << std::endl;
+            *out << "Cases\n";
+            printContingencyTable(*reinterpret_cast<const CONTIN_TABLE_T *>(&tab[32 * q]), *out);
+            *out << "\nControls\n";
+            printContingencyTable(*reinterpret_cast<const CONTIN_TABLE_T *>(&tab[32 * q + 16]), *out);
+            out->flush();
+            printf("\nLog likelihood: %f; p-value: %g\n\n", ll[q], pval[q]);      // to stdout, as the reference does (:302)
+        }
+    });
+}
+
+void EpistasisPerformance(GeneticData *gd, std::ostream *out) {
+    DeviceGenoTable &gt = *gd->getGenotypeTable();
+    CaseControlSet ccs(gd->getGenotypedIndividualsCount());
+    fixed_epistasis_set(ccs);
+    gt.selectCaseControl(ccs);
+    std::vector<double> ll, pval;
+    Lap lap;
+    for_pair_batches((uint)gd->getGenotypedMarkersCount(), [&](uint64_t, const std::vector<uint> &pi, const std::vector<uint> &pj) {
+        ll.resize(pi.size()); pval.resize(pi.size());
+        int rc = gwasdev_epi_pairs(gt.handle(), pi.size(), pi.data(), pj.data(), 1, ll.data(), pval.data());
+        assert(rc == GWASDEV_OK); (void)rc;
+    });
+    *out << "Case/Control Contingencies " << gd->getGenotypedMarkersCount() << ": ";
+    print_lapse(std::cout, "", lap.seconds());
+    std::cout << std::endl;
+}
+
 void computeMargins(DeviceGenoTable &gt, int nIndivids, marginal_information *&pMargins, int &nMarkerCount) {
     (void)nIndivids;
     nMarkerCount = gt.row_size();

@@ -58,6 +58,17 @@ void inline_cc_maf(GeneticData *gd, std::ostream *out);
 void inline_maf_print(GeneticData *gd, std::ostream *out);
 void genotype_dist_performance(GeneticData *gd, std::ostream *out);
 
+// --contin-debug / --contin-perform / --contin-cc-perform / --epi-debug / --epi-perform
+// (algorithms/epistasis_func.cpp:84-103, 105-135, 137-202, 263-305, 307-347). The reference passes an IndexedInput as
+// void*; only its GeneticData is read, so these take the GeneticData directly. Pairs are enumerated in the reference's
+// order and evaluated in batches on the device.
+void ContingencyDebug(GeneticData *gd, std::ostream *out);
+void ContingencyPerformance(GeneticData *gd, std::ostream *out);
+void ContingencyCCPerformance(GeneticData *gd, std::ostream *out);
+void EpistasisDebug(GeneticData *gd, std::ostream *out);
+void EpistasisPerformance(GeneticData *gd, std::ostream *out);
+void printContingencyTable(const CONTIN_TABLE_T &ct, std::ostream &out);
+
 void computeMargins(DeviceGenoTable &gt, int nIndivids, marginal_information *&pMargins, int &nMarkerCount);
 void computeGTest(DeviceGenoTable &gt, marginal_information *pMargins, uint nIndivids,
                   std::vector<SNPInteractionPair> &passingThreshold, std::vector<double> &zval);

@@ -341,7 +341,7 @@ class Ref:
 
     def run(self, which, cap=1 << 26):
         names = {"computeBoost": 0, "select_cc_maf": 1, "inline_cc_maf": 2, "inline_maf_print": 3,
-                 "genotype_dist_performance": 4}
+                 "genotype_dist_performance": 4, "ContingencyDebug": 5, "EpistasisDebug": 6}
         buf = C.create_string_buffer(cap)
         n = self.L.gwasref_run(self.h, names[which], buf, cap)
         if n >= cap:

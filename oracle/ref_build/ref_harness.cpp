@@ -25,7 +25,9 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <fcntl.h>
 #include <sys/time.h>
+#include <unistd.h>
 #include <time.h>
 
 // The harness needs the private table/case-control members of GeneticData and the protected layout
@@ -258,6 +260,22 @@ int gwasref_run(void *h, int which, char *buf, long cap) {
     case 2: compute(inline_cc_maf, r->gd, &out); break;
     case 3: compute(inline_maf_print, r->gd, &out); break;
     case 4: compute(genotype_dist_performance, r->gd, &out); break;
+    case 5: case 6: {   // ContingencyDebug / EpistasisDebug (epistasis_func.cpp:84-103, 263-305): only inp.gd is read
+        std::set<std::string> mids, iids;
+        BasicInput bi(r->gd, &mids, &iids);
+        IndexedInput ii(&bi);
+        if (which == 5) ContingencyDebug(&ii, &out);
+        else {          // its log-likelihood lines go to stdout through printf: keep them out of the test log
+            fflush(stdout);
+            const int keep = dup(1), nul = open("/dev/null", O_WRONLY);
+            dup2(nul, 1);
+            EpistasisDebug(&ii, &out);
+            fflush(stdout);
+            dup2(keep, 1);
+            close(keep); close(nul);
+        }
+        break;
+    }
     default: return -1;
     }
     return copy_out(out.str(), buf, cap);

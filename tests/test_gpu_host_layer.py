@@ -95,3 +95,37 @@ def test_per_call_virtuals_against_golden(tmp_path):
                 half = ref[:16] if (mode == 0 or tag.endswith("ca")) else ref[16:]
                 assert list(map(int, p[3:19])) == half.tolist()
     assert {"call", "whole", "mask_ca", "sel_co", "mar_ca", "t0", "t1_ca", "t2_co", "t3_ca"} <= seen
+
+
+@pytest.mark.parametrize("name", ["cohort_missing", "cohort_complete"])
+def test_contin_and_epi_debug_output_equals_reference_output(orc, tmp_path, name):
+    """--contin-debug and --epi-debug (ContingencyDebug / EpistasisDebug, epistasis_func.cpp:84-103, 263-305): the text
+    written to the output stream must be the unmodified reference's (tests/golden/make_golden_debug.py); the
+    likelihood-ratio values behind --epi-debug / --epi-perform are checked against the pinned pairwise.c restatement."""
+    import libgwaspp_b200 as gw
+    g, dbg = load_golden(name), load_golden("debug_prints")
+    n = int(dbg[name + "_n_snps"])
+    codes, pheno = g["codes"][:n], g["pheno"]
+    tped, tfam = write_tplink(tmp_path, codes, pheno)
+    assert run_cli(tped, tfam, "--contin-debug", tmp_path) == str(dbg[name + "_contin_debug"])
+    assert run_cli(tped, tfam, "--epi-debug", tmp_path) == str(dbg[name + "_epi_debug"])
+    lines = run_cli(tped, tfam, "--contin-perform", tmp_path).splitlines()
+    assert [l.split("\t")[0] for l in lines] == [str(k) for k in range(n * (n - 1) // 2)]
+    assert len(run_cli(tped, tfam, "--contin-cc-perform", tmp_path).splitlines()) == n * (n - 1) // 2
+    assert run_cli(tped, tfam, "--epi-perform", tmp_path).startswith(f"Case/Control Contingencies {n}: ")
+    # gwasdev_epi_pairs == pairwise.c on the 3x3 cores of the mode-1 tables, with EpistasisDebug's fixed set
+    N = codes.shape[1]
+    ph = np.full(N, 2, np.uint8)
+    ph[0:400:2], ph[1:400:2] = 1, 0
+    pi, pj = np.triu_indices(n, 1)
+    with gw.GenoStore(n, N) as st:
+        st.put_rows(orc.pack_codes(codes))
+        st.select_case_control(ph)
+        tabs = st.pair_tables(pi, pj, 1)
+        ll, p = st.epi_pairs(pi, pj, 1)
+    core = [0, 1, 2, 4, 5, 6, 8, 9, 10]
+    for q in range(len(pi)):
+        want = orc.pairwise_epi_test(tabs[q, :16][core], tabs[q, 16:][core])
+        assert (np.isnan(want) and np.isnan(ll[q])) or abs(ll[q] - want) <= 1e-12 * abs(want)
+        wp = orc.chisq_upper(want, 4)
+        assert (np.isnan(wp) and np.isnan(p[q])) or abs(p[q] - wp) <= 1e-10 * abs(wp)
