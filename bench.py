@@ -243,7 +243,7 @@ def gpu_arm(args):
     e2e_s = max_over_ranks((time.perf_counter() - te0) / e2e_steps)
     e2e_kernel_ms = st.last_scan_ms()
     wr = (st.P // 2 + 3) // 4 * 4                              # device words per raw plane
-    h2d = int(3 * 4 * wr + 2 * 4 * (7 * wr + 1) + 4 * ((NCASE + 31) // 32 + (N - NCASE + 31) // 32))   # 3 masks + compaction tables
+    h2d = int(3 * 4 * wr + 2 * 4 * (12 * wr + 1) + 4 * ((NCASE + 31) // 32 + (N - NCASE + 31) // 32))   # 3 masks + compaction tables
     d2h = int(h_counts.numel() * 4 + h_stats.numel() * 8)
     e2e = {"value": round(world * bytes_per_step / e2e_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,

@@ -65,6 +65,7 @@ struct SelectTables {
     const uint32_t *mv;     // [Wr][5]   compress move masks
     const uint32_t *rank;   // [Wr + 1]  members before source word sw
     const uint32_t *first;  // [Kout]    first source word contributing to output word o
+    const uint32_t *mvl;    // [Wr][5]   move masks of the compress towards the most significant end
     uint32_t n_class, Kout;
 };
 
@@ -123,6 +124,84 @@ select_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, SelectTables ca, Se
         uint4 *dst = reinterpret_cast<uint4 *>(sel + snp0 * (uint64_t)sel_stride);
         uint4 *src = reinterpret_cast<uint4 *>(rows);
         for (uint32_t q = threadIdx.x; q < n_here * sel_stride / 4; q += blockDim.x) { dst[q] = src[q]; src[q] = make_uint4(0, 0, 0, 0); }
+        __syncthreads();
+    }
+}
+
+// K0, register form (cohorts up to 32 768 samples): thread t owns SOURCE COLUMN t -- the 32-sample word t of every row -- so
+// that everything derived from the masks (member mask, the five compress move masks, where the compressed piece lands in
+// the output row) is loaded once into registers and the per-row work is two loads, four bit-compresses and the ORs into
+// the shared-memory row buffer. The table-driven kernel above spends ~260 instructions per source word on table reads,
+// index arithmetic and divisions (ncu r1m); this one ~100.
+struct ColumnTables { uint32_t m, mv[5], sh, down, lo, hi; };   // down = 32 - members; lo / hi: word offsets (plane 1) of the piece's two output words
+
+// compress towards the MOST significant end: the moves are left shifts by constants, which ptxas issues as IMAD.SHL on the
+// FMA pipe, leaving two LOP3 per stage on the ALU pipe that bounds this kernel (ncu r1o: ALU 68 % busy, everything else idle)
+__device__ __forceinline__ uint32_t compress_bits_left(uint32_t x, const uint32_t *mvl) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const uint32_t t = x & mvl[i];
+        x = (x ^ t) | (t << (1 << i));
+    }
+    return x;
+}
+
+__device__ __forceinline__ ColumnTables load_column(const SelectTables &t, uint32_t Wr, uint32_t sw, uint32_t class_off, uint32_t W) {
+    ColumnTables c;
+    c.m = t.m[sw];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) c.mv[i] = t.mvl[5 * sw + i];
+    const uint32_t pos = t.rank[sw], o = pos >> 5;
+    c.sh = pos & 31;
+    c.down = 32 - __popc(c.m);
+    c.lo = sel_word(class_off, 0, min(o, W - 1));
+    c.hi = sel_word(class_off, 0, min(o + 1, W - 1));
+    return c;
+}
+
+__device__ __forceinline__ void place_piece(uint32_t *row, const ColumnTables &c, uint32_t w1, uint32_t w2) {
+    if (c.m == 0) return;   // (whole column outside the class; never true for a lane of a mixed cohort)
+    const uint32_t x = compress_bits_left(w1 & c.m, c.mv) >> c.down, y = compress_bits_left(w2 & c.m, c.mv) >> c.down;
+    const uint32_t xh = __funnelshift_l(x, 0u, c.sh), yh = __funnelshift_l(y, 0u, c.sh);   // x >> (32 - sh), 0 when sh == 0
+    atomicOr(&row[c.lo], x << c.sh);       // unconditional: a test per OR costs more issue slots than the zero ORs
+    atomicOr(&row[c.lo + 4], y << c.sh);
+    atomicOr(&row[c.hi], xh);
+    atomicOr(&row[c.hi + 4], yh);
+}
+
+template <int SNPS>
+__global__ void __launch_bounds__(1024)
+select_columns_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, SelectTables ca, SelectTables co,
+                      uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Wt, uint64_t M) {
+    extern __shared__ uint32_t rows[];   // [SNPS][sel_stride]
+    const uint32_t sw = threadIdx.x;
+    const bool live = sw < Wr;
+    ColumnTables ta, to;
+    if (live) { ta = load_column(ca, Wr, sw, 0, Wc); to = load_column(co, Wr, sw, 2 * Wc, Wt); }
+    else { ta.m = 0; to.m = 0; }
+    for (uint32_t q = threadIdx.x; q < SNPS * sel_stride; q += blockDim.x) rows[q] = 0;
+    __syncthreads();
+    for (uint64_t snp0 = (uint64_t)blockIdx.x * SNPS; snp0 < M; snp0 += (uint64_t)gridDim.x * SNPS) {
+        const uint32_t n_here = (uint32_t)min((uint64_t)SNPS, M - snp0);
+        uint32_t w1[SNPS], w2[SNPS];
+#pragma unroll
+        for (int r = 0; r < SNPS; ++r) {   // all loads of the iteration first
+            w1[r] = w2[r] = 0;
+            if (live && r < (int)n_here) {
+                const uint32_t *p = raw + (snp0 + r) * 2ull * Wr + sw;
+                w1[r] = __ldcs(p); w2[r] = __ldcs(p + Wr);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SNPS; ++r) {
+            uint32_t *row = rows + r * sel_stride;
+            place_piece(row, ta, w1[r], w2[r]);
+            place_piece(row, to, w1[r], w2[r]);
+        }
+        __syncthreads();
+        uint4 *dst = reinterpret_cast<uint4 *>(sel + snp0 * (uint64_t)sel_stride);
+        uint4 *src = reinterpret_cast<uint4 *>(rows);
+        for (uint32_t q = threadIdx.x; q < n_here * sel_stride / 4; q += blockDim.x) { __stcs(dst + q, src[q]); src[q] = make_uint4(0, 0, 0, 0); }
         __syncthreads();
     }
 }
@@ -474,22 +553,27 @@ int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, uint32_t n_cas
 static void build_select_tables(const std::vector<uint32_t> &mask, uint32_t n_class, uint32_t Kout,
                                 std::vector<uint32_t> &blob /* m | mv | rank | first */) {
     const uint32_t Wr = (uint32_t)mask.size();
-    blob.assign(7ull * Wr + 1 + std::max(Kout, 1u), 0);
-    uint32_t *m = blob.data(), *mv = m + Wr, *rank = m + 6ull * Wr, *first = rank + Wr + 1;
+    const uint32_t Kf = std::max(Kout, 1u);
+    blob.assign(7ull * Wr + 1 + Kf + 5ull * Wr, 0);
+    uint32_t *m = blob.data(), *mv = m + Wr, *rank = m + 6ull * Wr, *first = rank + Wr + 1, *mvl = first + Kf;
+    auto rev32 = [](uint32_t v) { uint32_t r = 0; for (int b = 0; b < 32; ++b) r |= ((v >> b) & 1u) << (31 - b); return r; };
     uint32_t r = 0;
     for (uint32_t sw = 0; sw < Wr; ++sw) {
         uint32_t mm = mask[sw];
         m[sw] = mm;
         rank[sw] = r;
         r += (uint32_t)__builtin_popcount(mm);
-        uint32_t mk = ~mm << 1;
-        for (int i = 0; i < 5; ++i) {
-            uint32_t mp = mk ^ (mk << 1);
-            mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
-            const uint32_t v = mp & mm;
-            mv[5 * sw + i] = v;
-            mm = (mm ^ v) | (v >> (1 << i));
-            mk &= ~mp;
+        for (int left = 0; left < 2; ++left) {   // the left-compress masks are those of the bit-reversed problem, reversed
+            uint32_t mq = left ? rev32(mask[sw]) : mm;
+            uint32_t mk = ~mq << 1;
+            for (int i = 0; i < 5; ++i) {
+                uint32_t mp = mk ^ (mk << 1);
+                mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+                const uint32_t v = mp & mq;
+                if (left) mvl[5 * sw + i] = rev32(v); else mv[5 * sw + i] = v;
+                mq = (mq ^ v) | (v >> (1 << i));
+                mk &= ~mp;
+            }
         }
     }
     rank[Wr] = r;
@@ -590,8 +674,8 @@ int gwasdev_internal_ensure_compacted(gwasdev_store *s) {
     const uint32_t stride = 2 * (s->Wc + s->Wt);
     GW_CUDA(reserve_raw(s->d_sel, s->cap_sel, s->M * (uint64_t)stride * 4));
     SelectTables ta, to;
-    ta.m = s->d_case_idx; ta.mv = ta.m + s->Wr; ta.rank = ta.m + 6ull * s->Wr; ta.first = ta.rank + s->Wr + 1; ta.n_class = s->n_case; ta.Kout = s->Kc;
-    to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.n_class = s->n_ctrl; to.Kout = s->Kt;
+    ta.m = s->d_case_idx; ta.mv = ta.m + s->Wr; ta.rank = ta.m + 6ull * s->Wr; ta.first = ta.rank + s->Wr + 1; ta.mvl = ta.first + std::max(s->Kc, 1u); ta.n_class = s->n_case; ta.Kout = s->Kc;
+    to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.mvl = to.first + std::max(s->Kt, 1u); to.n_class = s->n_ctrl; to.Kout = s->Kt;
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const bool trace = getenv("GWASDEV_TRACE") != nullptr;
@@ -599,7 +683,16 @@ int gwasdev_internal_ensure_compacted(gwasdev_store *s) {
     constexpr int SNPS = 4;                                     // rows assembled per block iteration
     const size_t smem_rows = (size_t)SNPS * stride * sizeof(uint32_t);
     const size_t smem_tab = 2 * (7ull * s->Wr + 1) * sizeof(uint32_t);
-    if (smem_rows + smem_tab <= 160 * 1024) {   // tables staged in shared memory (up to ~80 000 samples), else read through L1/L2
+    if (s->Wr <= 1024 && !getenv("GWASDEV_SELECT_TABLE_KERNEL")) {   // register form: one thread per source column
+        constexpr int CS = 8;
+        const unsigned threads = round_up(s->Wr, 32);
+        const size_t smem = (size_t)CS * stride * sizeof(uint32_t);
+        GW_CUDA(cudaFuncSetAttribute(select_columns_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        GW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_columns_kernel<CS>, (int)threads, smem));
+        const unsigned grid = (unsigned)std::min<uint64_t>((s->M + CS - 1) / CS, (uint64_t)sms * std::max(per_sm, 1));
+        select_columns_kernel<CS><<<grid, threads, smem, s->stream>>>(s->d_raw, s->Wr, ta, to, s->d_sel, stride, s->Wc, s->Wt, s->M);
+    } else if (smem_rows + smem_tab <= 160 * 1024) {   // tables staged in shared memory (up to ~80 000 samples), else read through L1/L2
         const size_t smem = smem_rows + smem_tab;
         GW_CUDA(cudaFuncSetAttribute(select_kernel<true, SNPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));

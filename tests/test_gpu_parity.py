@@ -26,8 +26,11 @@ def make_store(orc, codes, pheno=None):
     return st
 
 
+@pytest.mark.parametrize("k0", ["columns", "tables"])
 @pytest.mark.parametrize("name", COHORTS)
-def test_store_layout_roundtrip(orc, name):
+def test_store_layout_roundtrip(orc, monkeypatch, name, k0):
+    if k0 == "tables":          # the table-driven compaction kernel (cohorts beyond 32 768 samples) on the same fixtures
+        monkeypatch.setenv("GWASDEV_SELECT_TABLE_KERNEL", "1")
     g = load_golden(name)
     codes, pheno = g["codes"], g["pheno"]
     with make_store(orc, codes) as st:
