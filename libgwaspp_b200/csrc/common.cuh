@@ -167,6 +167,7 @@ struct gwasdev_store {
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
     float mma_qc = 0.f, mma_q0 = 0.f;   // constants of the upper-bound pre-filter (pairwise_mma.cu)
+    uint32_t mma_bound_ncase = 0xffffffffu, mma_bound_n = 0;   // class split they were computed for
     std::vector<uint8_t> h_tile_missing;   // host copy of d_tile_missing (valid with side_valid)
     size_t cap_mm = 0, cap_mma_row = 0, cap_mma_col = 0;
     bool mma_side_valid = false;

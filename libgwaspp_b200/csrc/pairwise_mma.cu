@@ -810,7 +810,10 @@ static int ensure_mma_inputs(gwasdev_store *s) {
             for (uint32_t J = BAND * (n_bands - 1); J < TB; ++J) tiles += column_height(na, J - BAND * (n_bands - 1));
         }
         s->mm_tiles = tiles;
-        bound_constants(s->n_case, s->n_case + s->n_ctrl, &s->mma_qc, &s->mma_q0);
+        if (s->mma_bound_ncase != s->n_case || s->mma_bound_n != s->n_case + s->n_ctrl) {   // 2.5 ms of host arithmetic: once per class split
+            bound_constants(s->n_case, s->n_case + s->n_ctrl, &s->mma_qc, &s->mma_q0);
+            s->mma_bound_ncase = s->n_case; s->mma_bound_n = s->n_case + s->n_ctrl;
+        }
         s->mm_built = true;
     }
     if (!s->mma_side_valid) {
@@ -922,8 +925,16 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
 // Launches the tensor-core screen for this shard's clean tiles. thr already carries the fp32 margin.
 int gwasdev_internal_screen_mma(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, void *cand,
                                 unsigned long long *n_cand, uint64_t cap) {
+    const bool trace = getenv("GWASDEV_TRACE") != nullptr;
+    if (trace) cudaEventRecord(s->ev2, s->stream);
     int rc = ensure_mma_inputs(s);
     if (rc != GWASDEV_OK) return rc;
+    if (trace) {
+        cudaEventRecord(s->ev3, s->stream);
+        cudaStreamSynchronize(s->stream);
+        float ms = 0.f; cudaEventElapsedTime(&ms, s->ev2, s->ev3);
+        fprintf(stderr, "[gwasdev trace] tensor-core operands + per-SNP records %.3f ms\n", ms);
+    }
     MmaParams p;
     fill_params(s, p, shard, n_shards);
     const uint64_t n_tiles = s->mm_tiles;
