@@ -138,6 +138,20 @@ class ClockSampler:
             self.proc.terminate()
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU: run this rank's host thread on the CPUs next to its GPU (NVML's ideal affinity), so that the
+    pinned host buffers of the e2e path land on that NUMA node instead of wherever torchrun started the process."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
@@ -152,6 +166,7 @@ def gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)     # pinned result buffers are first-touched on the GPU's own node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream()
@@ -251,6 +266,7 @@ def gpu_arm(args):
                    "selection runs marginal_scan_masked_kernel on the raw rows (select fused into the scan, no compaction), "
                    "in pieces whose D2H copies overlap the next piece's scan",
            "kernel": "marginal_scan_masked_kernel", "kernel_span_ms": round(e2e_kernel_ms, 4),
+           "host_cpus": (f"{numa[0]}-{numa[-1]} ({len(numa)}, NVML affinity of the GPU)" if numa else "unbound"),
            "bound": "PCIe D2H of the 96 B/SNP results"}
     # sanity: the device and host paths agree, and the scan did real work
     assert torch.equal(h_counts, d_counts.cpu()) and int(h_counts[:, :4].sum(1).min()) == NCASE

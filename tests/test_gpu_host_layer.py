@@ -129,3 +129,28 @@ def test_contin_and_epi_debug_output_equals_reference_output(orc, tmp_path, name
         assert (np.isnan(want) and np.isnan(ll[q])) or abs(ll[q] - want) <= 1e-12 * abs(want)
         wp = orc.chisq_upper(want, 4)
         assert (np.isnan(wp) and np.isnan(p[q])) or abs(p[q] - wp) <= 1e-10 * abs(wp)
+
+
+def test_cli_reads_gz_and_bed_genotype_files(tmp_path):
+    """The harness hands the genotype file to the device loaders: a gzip-compressed TPED (which the reference's two-pass
+    reader cannot rewind) and a SNP-major PLINK .bed give the output of the plain TPED, i.e. the reference's own."""
+    import gzip
+    from test_gpu_ingest import bed_encode
+    g = load_golden("cohort_missing")
+    tped, tfam = write_tplink(tmp_path, g["codes"], g["pheno"])
+    want = str(g["inline_maf_print"])
+    assert run_cli(tped, tfam, "--test-inline-maf", tmp_path) == want
+    gz = tmp_path / "c.tped.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(open(tped, "rb").read())
+    assert run_cli(gz, tfam, "--test-inline-maf", tmp_path) == want
+    bed = tmp_path / "c.bed"
+    bed.write_bytes(bytes([0x6C, 0x1B, 0x01]) + bed_encode(g["codes"]).tobytes())
+    assert run_cli(bed, tfam, "--test-inline-maf", tmp_path) == want
+    got = run_cli(bed, tfam, "--test-boost-epi", tmp_path).splitlines()
+    assert got[2:] == str(g["boost_text"]).splitlines()[2:]
+    # the reference-shaped host loop (one addGenotypeRow per line) stays available and agrees
+    out = tmp_path / "hp.txt"
+    r = subprocess.run([CLI, "--tplink", "-g", str(tped), "-p", str(tfam), "--host-parse", "--test-inline-maf", "-o", str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and out.read_text() == want
