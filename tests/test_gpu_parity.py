@@ -240,6 +240,48 @@ def test_error_behaviour():
         assert len(hits) == 0 and stats.pairs_tested == 45
 
 
+@pytest.mark.parametrize("M,N,n_case", [(1, 1, 1), (2, 15, 7), (3, 16, 0), (5, 17, 17), (33, 31, 15), (40, 33, 16),
+                                         (70, 127, 64), (129, 129, 1), (64, 513, 256), (65, 1025, 1000)])
+def test_ragged_and_degenerate_shapes(orc, M, N, n_case):
+    """Tables of one SNP or one sample, sizes around the 16-/32-/128-sample block edges, one empty class: layout, both scan
+    kernels, every table overload, the screen and the G-test against the oracle."""
+    codes, _ = orc.simulate(1000 + 7 * M + N, M, N, max(n_case, 1) if n_case < N else N, missing_rate=0.05)
+    pheno = np.zeros(N, np.uint8)
+    pheno[np.random.default_rng(N).permutation(N)[:n_case]] = 1
+    rows = orc.pack_codes(codes)
+    sel, nca, nco = orc.select(rows, N, pheno)
+    assert (nca, nco) == (n_case, N - n_case)
+    want = orc.cc_counts_selected(sel, nca, nco)
+    with gw.GenoStore(M, N) as st:
+        st.put_rows(rows)
+        assert np.array_equal(st.get_rows(), rows)
+        st.select_case_control(pheno)
+        first = st.marginal_scan()                                  # masked scan on the raw rows
+        assert np.array_equal(st.get_selected_rows(), sel)          # K0
+        second = st.marginal_scan()                                 # compacted rows
+        for o in (first, second):
+            assert np.array_equal(o["counts"], want)
+        assert first["mi"].tobytes() == second["mi"].tobytes() and first["stats"].tobytes() == second["stats"].tobytes()
+        mar = orc.margins(sel, nca, nco)
+        assert np.array_equal(first["mi"]["dPbc"], mar["pbc"]) and np.array_equal(first["mi"]["dPca"], mar["pca"])
+        assert np.array_equal(st.counts(1), orc.cc_counts_masked(rows, N, pheno))
+        assert np.array_equal(st.counts(0)[:, :3], orc.counts_whole(rows, N)[:, :3])
+        if M >= 2:
+            pi, pj = np.triu_indices(M, 1)
+            pi, pj = pi[:200].astype(np.uint32), pj[:200].astype(np.uint32)
+            for mode in (0, 1, 2, 3):
+                got = st.pair_tables(pi, pj, mode)
+                for q in range(0, len(pi), 17):
+                    ca, co = orc.pair_table(mode, int(pi[q]), int(pj[q]), rows=rows, sel=sel, n_samples=N, pheno=pheno,
+                                            nca=nca, nco=nco, mar=mar)
+                    assert np.array_equal(got[q, :16], ca) and np.array_equal(got[q, 16:], co), (mode, q)
+            hits, stats = st.pairwise_scan(30.0)
+            hi, hj, hs, _ = orc.boost_screen(sel, mar, nca, nco, 30.0)
+            assert stats.pairs_tested == M * (M - 1) // 2
+            assert np.array_equal(hits["i"], hi) and np.array_equal(hits["j"], hj)
+            assert rel_close(hits["stat"], hs, REL_F64)
+
+
 # ------------------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: size-independent properties (the oracle cannot run these in seconds)
 # ------------------------------------------------------------------------------------------------------
