@@ -172,6 +172,9 @@ struct gwasdev_store {
     size_t cap_mm = 0, cap_mma_row = 0, cap_mma_col = 0;
     bool mma_side_valid = false;
     bool any_missing = false, any_clean = false;     // over tiles, valid with side_valid
+    bool pc_valid = false, pc_use_mma = false;       // cached pair / tile counts of the last pairwise scan's shard
+    uint32_t pc_shard = 0, pc_n_shards = 0;
+    uint64_t pc_pairs = 0, pc_tiles = 0, pc_nine = 0;
 
     // grow-only scratch, so that steady-state calls never touch cudaMalloc / cudaFree (both cost
     // milliseconds and cudaFree synchronises the device)

@@ -352,7 +352,7 @@ int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_stor
 static void free_scratch(gwasdev_store::Scratch &sc) { if (sc.p) cudaFree(sc.p); sc.p = nullptr; sc.cap = 0; }
 
 static void invalidate_selection(gwasdev_store *s) {
-    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mma_side_valid = false;
+    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mma_side_valid = s->pc_valid = false;
 }
 
 void gwasdev_destroy(gwasdev_store *s) {
