@@ -69,7 +69,24 @@ int main(int argc, char **argv) {
     std::cout << "Found " << n_individs << " individuals." << std::endl;
     std::cout << "Found " << n_markers << " markers" << std::endl;
     GeneticData gd(n_markers, n_individs, device);
-    if (is_bed) gd.getGenotypeTable()->loadBed(geno);
+    if (is_bed) {
+        // allele letters from the .bim next to the .bed (columns 5 and 6: A1, A2) decide the row header words, i.e. what
+        // getCallAt() spells; rows whose alleles are not two different letters of ACGT keep the default A / C
+        std::vector<unsigned char> alleles;
+        std::ifstream bim((geno.substr(0, geno.size() - 4) + ".bim").c_str());
+        if (bim.is_open()) {
+            std::string chr, id, cm, pos, a1, a2;
+            const std::string acgt = "ACGT";
+            while (bim >> chr >> id >> cm >> pos >> a1 >> a2) {
+                const size_t i1 = a1.size() == 1 ? acgt.find(a1[0]) : std::string::npos, i2 = a2.size() == 1 ? acgt.find(a2[0]) : std::string::npos;
+                const bool ok = i1 != std::string::npos && i2 != std::string::npos && i1 != i2;
+                alleles.push_back(ok ? (unsigned char)i1 : 0);
+                alleles.push_back(ok ? (unsigned char)i2 : 1);
+            }
+            if ((int)alleles.size() != 2 * n_markers) alleles.clear();
+        }
+        gd.getGenotypeTable()->loadBed(geno, alleles);
+    }
     else if (!host_parse) gd.getGenotypeTable()->loadTransposedPlink(geno);
     else {
         std::ifstream f(geno.c_str());

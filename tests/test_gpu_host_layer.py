@@ -149,6 +149,14 @@ def test_cli_reads_gz_and_bed_genotype_files(tmp_path):
     assert run_cli(bed, tfam, "--test-inline-maf", tmp_path) == want
     got = run_cli(bed, tfam, "--test-boost-epi", tmp_path).splitlines()
     assert got[2:] == str(g["boost_text"]).splitlines()[2:]
+    # with a .bim next to it the allele letters decide what getCallAt spells (--dump-api prints calls); counts do not move
+    with open(tmp_path / "c.bim", "w") as f:
+        for r in range(g["codes"].shape[0]):
+            f.write(f"1\trs{r}\t0\t{r}\tG\tT\n")
+    assert run_cli(bed, tfam, "--test-inline-maf", tmp_path) == want
+    spell = {0: "GG", 1: "GT", 2: "TT", 3: "00"}
+    calls = [l.split() for l in run_cli(bed, tfam, "--dump-api", tmp_path).splitlines() if l.startswith("call ")]
+    assert calls and all(c[3] == spell[int(g["codes"][int(c[1]), int(c[2])])] for c in calls)
     # the reference-shaped host loop (one addGenotypeRow per line) stays available and agrees
     out = tmp_path / "hp.txt"
     r = subprocess.run([CLI, "--tplink", "-g", str(tped), "-p", str(tfam), "--host-parse", "--test-inline-maf", "-o", str(out)],
