@@ -241,7 +241,8 @@ __device__ __forceinline__ void accumulate_masked(const uint4 &x, const uint4 &y
     const uint4 ym = make_uint4(y.x & m.x, y.y & m.y, y.z & m.z, y.w & m.w);
     hs_add4(h1, xm.x, xm.y, xm.z, xm.w);
     hs_add4(h2, ym.x, ym.y, ym.z, ym.w);
-    hs_add4(hb, xm.x & y.x, xm.y & y.y, xm.z & y.z, xm.w & y.w);
+    hb.ones += __popc(xm.x & y.x) + __popc(xm.y & y.y);     // plain POPC on the XU pipe: the ALU pipe is the busy one
+    hb.twos += __popc(xm.z & y.z) + __popc(xm.w & y.w);
 }
 
 template <int G, int SLOTS, int MINB>
@@ -290,7 +291,7 @@ marginal_scan_masked_kernel(const uint4 *__restrict__ raw, uint32_t Q, const uin
                     }
                 }
             }
-            uint32_t s1 = hs_total(a1), s2 = hs_total(a2), sb = hs_total(ab), t1 = hs_total(b1), t2 = hs_total(b2), tb = hs_total(bb);
+            uint32_t s1 = hs_total(a1), s2 = hs_total(a2), sb = plain_total(ab), t1 = hs_total(b1), t2 = hs_total(b2), tb = plain_total(bb);
             s1 = __reduce_add_sync(group_mask, s1); s2 = __reduce_add_sync(group_mask, s2);
             sb = __reduce_add_sync(group_mask, sb); t1 = __reduce_add_sync(group_mask, t1);
             t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
