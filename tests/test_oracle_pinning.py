@@ -251,3 +251,35 @@ def test_live_against_reference_build(orc, seed, M, N, ncase, miss):
     hits, located = oracle.parse_boost_output(R.run("computeBoost"))
     hi, hj, hs, st = orc.boost_screen(sel, mar, nca, nco)
     assert located == len(hi)
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_file_reader_pins_the_text_loader_semantics(orc, golden_dir, tmp_path):
+    """The f1 boundary: what the reference's OWN TPED reader + addGenotypeRow (tped_genotype_file.cpp:110-185,
+    compressed_genotype_table5.cpp:277-365) store for a file is what the restated packer stores for the same lines after
+    the reader's collapse (alleles every other character, 1234 -> ACGT). tests/test_gpu_ingest.py holds the device loader
+    to the restated packer, so the chain file -> device rows is pinned to the reference end to end. Also a file with
+    digit alleles, the only spelling the perl fixtures do not use."""
+    def collapsed(line):
+        f = line.split()
+        al = [a.translate(bytes.maketrans(b"1234", b"ACGT")) for a in f[4:]]
+        return b"\t".join(a + b for a, b in zip(al[0::2], al[1::2]))
+
+    files = [(os.path.join(golden_dir, f"perl_{n}.tped"), os.path.join(golden_dir, f"perl_{n}.tfam")) for n in ("simple", "cc")]
+    g = np.load(os.path.join(golden_dir, "cohort_missing.npz"))
+    codes = g["codes"][:30]
+    digit = {0: "1\t1", 1: "1\t3", 2: "3\t3", 3: "0\t0"}
+    tped, tfam = tmp_path / "d.tped", tmp_path / "d.tfam"
+    with open(tped, "w") as f:
+        for r in range(codes.shape[0]):
+            f.write(f"0\trs{r}\t0\t{r}\t" + "\t".join(digit[int(c)] for c in codes[r]) + "\n")
+    with open(tfam, "w") as f:
+        for i, p in enumerate(g["pheno"]):
+            f.write(f"F{i}\tI{i}\t0\t0\t1\t{int(p)}\n")
+    files.append((str(tped), str(tfam)))
+    for tp, tf in files:
+        R = oracle.Ref(tped=tp, tfam=tf, level=5)
+        lines = [l for l in open(tp, "rb").read().splitlines() if l.strip()]
+        assert R.n_snps == len(lines)
+        for r, line in enumerate(lines):
+            assert np.array_equal(R.raw_row(r), orc.pack_text(collapsed(line), R.n_samples)), (tp, r)
