@@ -183,3 +183,27 @@ def test_bed_rows_equal_text_rows(orc, tmp_path, N):
     bad.write_bytes(bytes([0x6C, 0x1B, 0x00]) + bed.tobytes())
     with pytest.raises(gw.GwasDevError, match="individual-major"):
         gw.bed_dims(str(bad), N)
+
+
+def test_configs0_from_tped_text_to_statistics(orc, tmp_path):
+    """BASELINE configs[0] end to end: 1 000 cases / 1 000 controls x 10 000 SNPs as an 80 MB TPED file -> device loader ->
+    case/control selection -> marginal scan, every SNP's counts against the oracle and the allelic chi-square of a
+    sample of SNPs (the configuration the reference itself runs on a CPU)."""
+    M, N, NCASE = 10_000, 2_000, 1_000
+    codes, pheno = orc.simulate(20121127, M, N, NCASE)
+    p = tmp_path / "c0.tped"
+    p.write_bytes(tped_bytes(codes))
+    assert gw.tped_dims(str(p)) == (M, N)
+    with gw.GenoStore(M, N) as st:
+        assert st.load_tped(str(p)) == M
+        rows = st.get_rows()
+        assert np.array_equal(rows, orc.pack_codes(codes))
+        st.select_case_control(pheno)
+        out = st.marginal_scan(mi=False)
+    sel, nca, nco = orc.select(rows, N, pheno)
+    assert (nca, nco) == (NCASE, N - NCASE)
+    assert np.array_equal(out["counts"], orc.cc_counts_selected(sel, nca, nco))
+    for r in range(0, M, 97):
+        x, pv = orc.chi2_allelic(out["counts"][r, :4], out["counts"][r, 4:])
+        s = out["stats"][r]
+        assert abs(s["chi2_allelic"] - x) <= 1e-12 * abs(x) and abs(s["p_allelic"] - pv) <= 1e-10 * abs(pv)
