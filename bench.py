@@ -302,6 +302,7 @@ def gpu_arm(args):
         if not args.no_cpu_baseline and world == 1:
             cb = cpu_baseline_marginal(N, NCASE, threads=1, steps=3)
             out["cpu_baseline"] = cb
+            out["configs0_file_to_statistics"] = configs0_file_to_statistics(gw, local)
             if "pairwise" in out:
                 out["pairwise"]["cpu_baseline"] = cpu_baseline_pairwise(args.pw_samples or PAIRWISE["n_samples"],
                                                                         args.pw_cases or PAIRWISE["n_case"])
@@ -309,6 +310,65 @@ def gpu_arm(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def configs0_file_to_statistics(gw, local):
+    """BASELINE configs[0] -- 1 000 cases / 1 000 controls x 10 000 SNPs, the case the reference runs on a CPU -- from the
+    genotype FILE to the per-SNP statistics on the host: 80 MB of TPED text -> device loader -> selection -> scan -> host
+    results, next to the reference doing the same with its own reader and select_cc_maf on one host core (oracle/_ref)."""
+    import tempfile
+    import oracle
+    M, N, NCASE = 10_000, 2_000, 1_000
+    pheno = gw.simulate_phenotype(SEED, N, NCASE)
+    with gw.GenoStore(M, N, device=local) as st:            # the cohort: device generator -> rows -> text
+        st.simulate(SEED)
+        rows = st.get_rows()
+        st.select_case_control(pheno)
+        want = st.marginal_scan(mi=False)["counts"]
+    P = (rows.shape[1] - 1) // 2
+    p1 = np.unpackbits(np.ascontiguousarray(rows[:, 1:1 + P]).view(np.uint8), axis=1, bitorder="little")[:, :N]
+    p2 = np.unpackbits(np.ascontiguousarray(rows[:, 1 + P:]).view(np.uint8), axis=1, bitorder="little")[:, :N]
+    lut = np.array([np.frombuffer(t, np.uint8).view(np.uint32)[0] for t in (b"0\t0\t", b"A\tA\t", b"A\tC\t", b"C\tC\t")], np.uint32)
+    code = p1 + 2 * p2
+    d = tempfile.mkdtemp()
+    tped, tfam = os.path.join(d, "c0.tped"), os.path.join(d, "c0.tfam")
+    with open(tped, "wb") as f:
+        for r in range(M):
+            f.write(b"0\trs%d\t0\t%d\t" % (r, r) + lut[code[r]].view(np.uint8).tobytes()[:-1] + b"\n")
+    with open(tfam, "w") as f:
+        for i, ph in enumerate(pheno):
+            f.write(f"F{i}\tI{i}\t0\t0\t1\t{int(ph)}\n")
+    res = {"workload": f"configs[0]: {NCASE} cases / {N - NCASE} controls x {M} SNPs, {os.path.getsize(tped) / 1e6:.1f} MB TPED file (page cache) "
+                       "-> per-SNP case/control counts + statistics on the host"}
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        with gw.GenoStore.from_tped(tped, device=local) as st:     # table sized and loaded in one pass over the file
+            t2 = time.perf_counter()
+            st.select_case_control(pheno)
+            got = st.marginal_scan(mi=False)
+            t3 = time.perf_counter()
+        cur = {"create_load_ms": round(1e3 * (t2 - t0), 2), "select_scan_ms": round(1e3 * (t3 - t2), 2),
+               "total_ms": round(1e3 * (t3 - t0), 2)}
+        if best is None or cur["total_ms"] < best["total_ms"]:
+            best = cur
+    assert np.array_equal(got["counts"], want), "counts from the loaded file differ from the generated cohort's"
+    res["b200"] = best
+    if oracle.have_ref():
+        t0 = time.perf_counter()
+        R = oracle.Ref(tped=tped, tfam=tfam, level=5)
+        t1 = time.perf_counter()
+        R.run("select_cc_maf")
+        t2 = time.perf_counter()
+        ref_counts = np.stack([R.cc_dist(r, 1)[0] for r in range(0, M, 101)])
+        assert np.array_equal(ref_counts, want[::101]), "the reference's counts differ"
+        res["reference"] = {"load_ms": round(1e3 * (t1 - t0), 1), "select_cc_maf_ms": round(1e3 * (t2 - t1), 1),
+                            "total_ms": round(1e3 * (t2 - t0), 1), "cores": 1, "kind": "reference",
+                            "what": "TpedGenotypeFile + TfamAnnotationFile readers, compute(select_cc_maf) at --comp-level 5"}
+    for fn in (tped, tfam):
+        os.remove(fn)
+    os.rmdir(d)
+    return res
 
 
 def biobank_gpu(args, gw, torch, local, stream, peaks, peak_src):

@@ -123,6 +123,11 @@ GWASDEV_API int gwasdev_tped_dims(const char *path, uint64_t *n_rows, uint32_t *
  * that reading chunk k+1 overlaps the device work on chunk k. A .gz needs no rewind: dims and load each open it once
  * (the reference's two-pass reader seeks, which its gzstream cannot: individual_genotype_file.cpp:94). */
 GWASDEV_API int gwasdev_load_tped(gwasdev_store *s, const char *path, uint64_t first_row, uint64_t *rows_done);
+/* gwasdev_tped_dims + gwasdev_create + gwasdev_load_tped in ONE pass over a plain file: the sample count comes from the
+ * first genotype line, the row capacity from the file size, and the table is trimmed to the rows found (a .gz still
+ * takes the counting pass first). What `new CompressedGenotypeTable5` + the two-pass reader do in the reference
+ * (genetics/genetic_data.cpp:60-79, individual_genotype_file.cpp:63-106). */
+GWASDEV_API int gwasdev_create_from_tped(const char *path, int device, gwasdev_store **out, uint64_t *n_rows, uint32_t *n_samples);
 /* PLINK .bed rows (SNP-major, ceil(n_samples/4) bytes per SNP, no magic; 0 = hom A1, 1 = missing, 2 = het,
  * 3 = hom A2) into rows [first_row, first_row + n_rows). alleles (may be NULL = A, C) holds the indices of A1 and A2
  * in "ACGT" per row; labels come out as the text loader would give the same calls spelled A1A1 / A1A2 / A2A2 in

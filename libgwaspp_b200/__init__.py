@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "gwasdev_popc_peak", "gwasdev_hbm_read_peak", "gwasdev_set_pair_engine", "gwasdev_mma_tile_counts",
     "gwasdev_ksa_screen_mma_f32", "gwasdev_pack_row_text_block", "gwasdev_simulate_block", "gwasdev_marginal_accumulate",
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
-    "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs",
+    "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs", "gwasdev_create_from_tped",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library():
     L.gwasdev_put_tped_text.argtypes = [vp, u64, vp, C.c_size_t, C.POINTER(u64), C.POINTER(C.c_size_t)]
     L.gwasdev_tped_dims.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u32)]
     L.gwasdev_load_tped.argtypes = [vp, C.c_char_p, u64, C.POINTER(u64)]
+    L.gwasdev_create_from_tped.argtypes = [C.c_char_p, i32, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
     L.gwasdev_put_bed.argtypes = [vp, u64, u64, vp, vp]
     L.gwasdev_bed_dims.argtypes = [C.c_char_p, u32, C.POINTER(u64)]
     L.gwasdev_load_bed.argtypes = [vp, C.c_char_p, vp, u64, C.POINTER(u64)]
@@ -228,6 +229,20 @@ class GenoStore:
         self.n_snps, self.n_samples, self.device = n_snps, n_samples, device
         self.P = plane_blocks(n_samples)
         self.n_case = self.n_ctrl = None
+
+    @classmethod
+    def from_tped(cls, path: str, device: int = 0) -> "GenoStore":
+        """Table sized from and loaded with a TPED file (plain: one pass; .gz: counting pass first), parsed on the device."""
+        self = cls.__new__(cls)
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rows, cols = C.c_uint64(), C.c_uint32()
+        _check(self.L.gwasdev_create_from_tped(os.fsencode(path), device, C.byref(self.h), C.byref(rows), C.byref(cols)),
+               "gwasdev_create_from_tped")
+        self.n_snps, self.n_samples, self.device = int(rows.value), int(cols.value), device
+        self.P = plane_blocks(self.n_samples)
+        self.n_case = self.n_ctrl = None
+        return self
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h:

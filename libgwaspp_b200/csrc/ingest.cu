@@ -12,7 +12,11 @@
 // and the same row assembler takes PLINK .bed rows (SNP-major, 2 bits per genotype), which the reference cannot read.
 // Files are read through zlib, which also reads plain files; a .gz is simply opened twice (dims pass, load pass), the
 // rewind the reference's gzstream cannot do (individual_genotype_file.cpp:94, SURVEY.md inventory row 9).
+#include <errno.h>
+#include <fcntl.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -364,7 +368,45 @@ static void invalidate(gwasdev_store *s) {
 
 static size_t chunk_bytes() {
     if (const char *e = getenv("GWASDEV_INGEST_CHUNK")) { const long long v = atoll(e); if (v >= 64) return (size_t)v; }
-    return 16ull << 20;
+    return 4ull << 20;   // pinning host memory costs ~1.5 ms per MB: small buffers, grown only for lines that do not fit
+}
+
+// Plain files are read with read() straight into the caller's (pinned) buffer; gzip files (magic 1f 8b) through zlib.
+struct TextFile {
+    int fd = -1;
+    gzFile gz = nullptr;
+    bool open(const char *path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        unsigned char magic[2] = {0, 0};
+        const ssize_t got = ::pread(fd, magic, 2, 0);
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            gz = gzdopen(fd, "rb");
+            if (!gz) { ::close(fd); fd = -1; return false; }
+            gzbuffer(gz, 1 << 20);
+        }
+        return true;
+    }
+    bool compressed() const { return gz != nullptr; }
+    long long size() const { struct stat st; return (!gz && fd >= 0 && fstat(fd, &st) == 0) ? (long long)st.st_size : -1; }
+    long long read(char *buf, size_t n) {   // bytes read, 0 at end of file, < 0 on error
+        if (gz) return gzread(gz, buf, (unsigned)std::min<size_t>(n, 1u << 30));
+        for (;;) { const ssize_t r = ::read(fd, buf, std::min<size_t>(n, 1u << 30)); if (r < 0 && errno == EINTR) continue; return r; }
+    }
+    void close() { if (gz) gzclose(gz); else if (fd >= 0) ::close(fd); gz = nullptr; fd = -1; }
+    ~TextFile() { close(); }
+};
+
+static bool is_blank(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+// genotype columns of a TPED line, counted like the reference sizes its row buffer (tped_genotype_file.cpp:132-136)
+static uint32_t tped_line_columns(const char *line, size_t len) {
+    size_t b = 0, e = len;
+    while (b < e && is_blank(line[b])) ++b;
+    while (e > b && is_blank(line[e - 1])) --e;
+    int delims = 0;
+    while (b < e && delims < 4) { if (line[b] == ' ' || line[b] == '\t') ++delims; ++b; }
+    return delims == 4 ? (uint32_t)((e - b + 1) >> 2) : 0;
 }
 
 }  // namespace gwasdev
@@ -409,21 +451,20 @@ int gwasdev_put_tped_text(gwasdev_store *s, uint64_t first_row, const char *text
 
 int gwasdev_tped_dims(const char *path, uint64_t *n_rows, uint32_t *n_samples) {
     GW_REQUIRE(path && n_rows && n_samples, "gwasdev_tped_dims: NULL argument");
-    gzFile f = gzopen(path, "rb");
-    GW_REQUIRE(f != nullptr, "gwasdev_tped_dims: cannot open %s", path);
-    gzbuffer(f, 1 << 20);
+    TextFile f;
+    GW_REQUIRE(f.open(path), "gwasdev_tped_dims: cannot open %s", path);
     std::vector<char> buf(8u << 20);
     std::string first;
     bool first_done = false, line_has_text = false;
     uint64_t rows = 0;
-    int n;
-    while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) {
-        for (int i = 0; i < n;) {
-            const char *nlp = (const char *)memchr(buf.data() + i, '\n', n - i);
-            const int e = nlp ? (int)(nlp - buf.data()) : n;
-            if (!first_done) first.append(buf.data() + i, e - i);
+    long long n;
+    while ((n = f.read(buf.data(), buf.size())) > 0) {
+        for (long long i = 0; i < n;) {
+            const char *nlp = (const char *)memchr(buf.data() + i, '\n', (size_t)(n - i));
+            const long long e = nlp ? (long long)(nlp - buf.data()) : n;
+            if (!first_done) first.append(buf.data() + i, (size_t)(e - i));
             if (!line_has_text)
-                for (int q = i; q < e; ++q) if (!(buf[q] == ' ' || (buf[q] >= '\t' && buf[q] <= '\r'))) { line_has_text = true; break; }
+                for (long long q = i; q < e; ++q) if (!is_blank(buf[q])) { line_has_text = true; break; }
             if (nlp) {
                 rows += line_has_text;
                 if (!first_done) { if (line_has_text) first_done = true; else first.clear(); }
@@ -433,46 +474,34 @@ int gwasdev_tped_dims(const char *path, uint64_t *n_rows, uint32_t *n_samples) {
             else i = n;
         }
     }
-    const bool bad = n < 0;
-    gzclose(f);
-    GW_REQUIRE(!bad, "gwasdev_tped_dims: read error in %s", path);
+    GW_REQUIRE(n == 0, "gwasdev_tped_dims: read error in %s", path);
     rows += line_has_text;   // last line without a newline
-    // columns of the first line, counted like the reference sizes its buffer (tped_genotype_file.cpp:132-136)
-    size_t b = 0, e = first.size();
-    while (b < e && (first[b] == ' ' || (first[b] >= '\t' && first[b] <= '\r'))) ++b;
-    while (e > b && (first[e - 1] == ' ' || (first[e - 1] >= '\t' && first[e - 1] <= '\r'))) --e;
-    int delims = 0;
-    while (b < e && delims < 4) { if (first[b] == ' ' || first[b] == '\t') ++delims; ++b; }
     *n_rows = rows;
-    *n_samples = delims == 4 ? (uint32_t)((e - b + 1) >> 2) : 0;
+    *n_samples = tped_line_columns(first.data(), first.size());
     return GWASDEV_OK;
 }
 
-int gwasdev_load_tped(gwasdev_store *s, const char *path, uint64_t first_row, uint64_t *rows_done) {
-    GW_REQUIRE(s && path, "gwasdev_load_tped: NULL argument");
-    GW_REQUIRE(first_row <= s->M, "gwasdev_load_tped: first row outside the table");
-    if (rows_done) *rows_done = 0;
-    GW_CUDA(cudaSetDevice(s->device));
-    gzFile f = gzopen(path, "rb");
-    GW_REQUIRE(f != nullptr, "gwasdev_load_tped: cannot open %s", path);
-    gzbuffer(f, 1 << 20);
-    const size_t CH = chunk_bytes();
+// the rest of an open text file (after `head`, bytes already read from it) into rows first_row.. of the store
+static int load_text_file(gwasdev_store *s, TextFile &f, const char *path, const char *head, size_t head_len, uint64_t first_row,
+                          uint64_t *rows_done) {
+    size_t CH = std::max(chunk_bytes(), head_len + 1);
     Ingest *g = nullptr;
     int rc = ingest_get(s, &g);
     if (rc == GWASDEV_OK) rc = reserve_text(g, CH + 1, true);
     if (rc == GWASDEV_OK) rc = ingest_begin(s, g, first_row);
-    if (rc != GWASDEV_OK) { gzclose(f); return rc; }
+    if (rc != GWASDEV_OK) return rc;
     // two pinned buffers: the file is read into one while the device works on the other
-    size_t carry = 0;
+    size_t carry = head_len;
+    if (head_len) memcpy(g->h_pin[0], head, head_len);
     int b = 0;
     bool eof = false, used_buf[2] = {false, false};
     while (!eof || carry) {
-        if (used_buf[b]) { cudaError_t e = cudaEventSynchronize(g->done[b]); if (e != cudaSuccess) { gzclose(f); GW_CUDA(e); } }
+        if (used_buf[b]) GW_CUDA(cudaEventSynchronize(g->done[b]));
         char *buf = g->h_pin[b];
         size_t have = carry;
         while (!eof && have < CH) {
-            const int n = gzread(f, buf + have, (unsigned)std::min<size_t>(CH - have, 1u << 30));
-            if (n < 0) { gzclose(f); set_error("gwasdev_load_tped: read error in %s", path); return GWASDEV_EINVAL; }
+            const long long n = f.read(buf + have, CH - have);
+            GW_REQUIRE(n >= 0, "gwasdev_load_tped: read error in %s", path);
             if (n == 0) eof = true;
             have += (size_t)n;
         }
@@ -481,26 +510,90 @@ int gwasdev_load_tped(gwasdev_store *s, const char *path, uint64_t first_row, ui
         while (used > 0 && buf[used - 1] != '\n') --used;
         if (used == 0) {
             if (have == 0) break;
-            gzclose(f);
-            set_error("gwasdev_load_tped: a line of %s is longer than the %zu-byte chunk (GWASDEV_INGEST_CHUNK)", path, CH);
-            return GWASDEV_EINVAL;
+            // a line longer than the buffers: quadruple them (the device may still be reading the other one) and go on
+            GW_REQUIRE(CH < (1ull << 30), "gwasdev_load_tped: a line of %s is longer than 1 GiB", path);
+            GW_CUDA(cudaStreamSynchronize(s->stream));
+            std::vector<char> keep(buf, buf + have);
+            CH *= 4;
+            if ((rc = reserve_text(g, CH + 1, true)) != GWASDEV_OK) return rc;
+            memcpy(g->h_pin[b], keep.data(), have);
+            used_buf[0] = used_buf[1] = false;
+            carry = have;
+            continue;
         }
-        cudaError_t e = cudaMemcpyAsync(g->d_text[b], buf, used, cudaMemcpyHostToDevice, s->stream);
-        if (e != cudaSuccess) { gzclose(f); GW_CUDA(e); }
-        rc = ingest_text_chunk(s, g, b, used);
-        if (rc != GWASDEV_OK) { gzclose(f); return rc; }
-        cudaEventRecord(g->done[b], s->stream);
+        GW_CUDA(cudaMemcpyAsync(g->d_text[b], buf, used, cudaMemcpyHostToDevice, s->stream));
+        if ((rc = ingest_text_chunk(s, g, b, used)) != GWASDEV_OK) return rc;
+        GW_CUDA(cudaEventRecord(g->done[b], s->stream));
         used_buf[b] = true;
         carry = have - used;
         if (carry) {
-            if (used_buf[b ^ 1]) cudaEventSynchronize(g->done[b ^ 1]);
+            if (used_buf[b ^ 1]) GW_CUDA(cudaEventSynchronize(g->done[b ^ 1]));
             memcpy(g->h_pin[b ^ 1], buf + used, carry);
         }
         b ^= 1;
     }
-    gzclose(f);
     invalidate(s);
     return ingest_finish(s, g, "gwasdev_load_tped", first_row, rows_done);
+}
+
+int gwasdev_load_tped(gwasdev_store *s, const char *path, uint64_t first_row, uint64_t *rows_done) {
+    GW_REQUIRE(s && path, "gwasdev_load_tped: NULL argument");
+    GW_REQUIRE(first_row <= s->M, "gwasdev_load_tped: first row outside the table");
+    if (rows_done) *rows_done = 0;
+    GW_CUDA(cudaSetDevice(s->device));
+    TextFile f;
+    GW_REQUIRE(f.open(path), "gwasdev_load_tped: cannot open %s", path);
+    return load_text_file(s, f, path, nullptr, 0, first_row, rows_done);
+}
+
+int gwasdev_create_from_tped(const char *path, int device, gwasdev_store **out, uint64_t *n_rows, uint32_t *n_samples) {
+    GW_REQUIRE(path && out, "gwasdev_create_from_tped: NULL argument");
+    *out = nullptr;
+    uint64_t rows_cap = 0;
+    uint32_t cols = 0;
+    TextFile f;
+    GW_REQUIRE(f.open(path), "gwasdev_create_from_tped: cannot open %s", path);
+    std::string head;
+    if (f.compressed()) {   // size unknown before inflating: the counting pass, then a second open
+        f.close();
+        int rc = gwasdev_tped_dims(path, &rows_cap, &cols);
+        if (rc != GWASDEV_OK) return rc;
+        GW_REQUIRE(f.open(path), "gwasdev_create_from_tped: cannot open %s", path);
+    } else {
+        // one pass: the first non-blank line gives the sample count, the file size an upper bound of the rows (a line is at
+        // least 8 bytes of marker fields and 4 bytes per sample); the table is trimmed to the rows actually found
+        std::vector<char> buf(1u << 20);
+        size_t line_begin = 0;
+        bool found = false;
+        while (!found) {
+            const long long n = f.read(buf.data(), buf.size());
+            GW_REQUIRE(n >= 0, "gwasdev_create_from_tped: read error in %s", path);
+            if (n == 0) break;
+            head.append(buf.data(), (size_t)n);
+            for (;;) {
+                const size_t nl = head.find('\n', line_begin);
+                if (nl == std::string::npos) break;
+                if ((cols = tped_line_columns(head.data() + line_begin, nl - line_begin)) > 0) { found = true; break; }
+                line_begin = nl + 1;
+            }
+        }
+        if (!found) cols = tped_line_columns(head.data() + line_begin, head.size() - line_begin);
+        if (cols) rows_cap = (uint64_t)f.size() / (4ull * cols + 7) + 1;
+    }
+    GW_REQUIRE(cols > 0 && rows_cap > 0, "gwasdev_create_from_tped: %s holds no genotype line with four marker fields", path);
+    gwasdev_store *s = nullptr;
+    int rc = gwasdev_create(rows_cap, cols, device, &s);
+    if (rc != GWASDEV_OK) return rc;
+    uint64_t rows = 0;
+    rc = load_text_file(s, f, path, head.data(), head.size(), 0, &rows);
+    if (rc == GWASDEV_OK && rows == 0) { set_error("gwasdev_create_from_tped: %s holds no genotype rows", path); rc = GWASDEV_EINVAL; }
+    if (rc != GWASDEV_OK) { gwasdev_destroy(s); return rc; }
+    s->M = rows;                                   // rows beyond are allocated but not part of the table
+    s->Mpad = (rows + TILE - 1) / TILE * TILE;
+    *out = s;
+    if (n_rows) *n_rows = rows;
+    if (n_samples) *n_samples = cols;
+    return GWASDEV_OK;
 }
 
 int gwasdev_put_bed(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, const uint8_t *bed, const uint8_t *alleles) {

@@ -57,6 +57,14 @@ def test_load_tped_equals_reference_rows(orc, tmp_path, name):
     with gw.GenoStore(M, N) as st:
         assert st.load_tped(str(pz)) == M
         assert np.array_equal(st.get_rows(), g["raw_rows"])
+    for path in (p, pz):
+        with gw.GenoStore.from_tped(str(path)) as st:
+            assert (st.n_snps, st.n_samples) == (M, N)
+            assert np.array_equal(st.get_rows(), g["raw_rows"])
+            st.select_case_control(g["pheno"])                         # the trimmed table behaves like one created with M rows
+            assert np.array_equal(st.marginal_scan()["counts"], g["cc_selected"])
+            hits, stats = st.pairwise_scan(30.0)
+            assert stats.pairs_tested == M * (M - 1) // 2 and len(hits) == int(g["boost_located"])
 
 
 @pytest.mark.parametrize("name", ["simple", "cc"])
@@ -93,11 +101,15 @@ def test_messy_text_and_chunk_boundaries(orc, tmp_path, monkeypatch):
     p = tmp_path / "m.tped"
     p.write_bytes(text)
     assert gw.tped_dims(str(p)) == (M, N)
-    for chunk in (None, 9000, 4097 * 3):                                # lines straddle chunks, newline blocks, both
+    for chunk in (None, 9000, 4097 * 3, 1000):                          # lines straddle chunks, newline blocks, both; 1000: shorter
+                                                                        # than a line, the loader has to grow its buffers
         if chunk:
             monkeypatch.setenv("GWASDEV_INGEST_CHUNK", str(chunk))
         with gw.GenoStore(M, N) as st:
             assert st.load_tped(str(p)) == M
+            assert np.array_equal(st.get_rows(), want)
+        with gw.GenoStore.from_tped(str(p)) as st:                      # table sized by the loader itself, one pass
+            assert (st.n_snps, st.n_samples) == (M, N)
             assert np.array_equal(st.get_rows(), want)
     monkeypatch.delenv("GWASDEV_INGEST_CHUNK")
     # the same through the in-memory entry point, in three calls; an unterminated tail is left to the caller
