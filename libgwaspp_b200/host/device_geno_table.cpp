@@ -65,6 +65,19 @@ DeviceGenoTable::DeviceGenoTable(int n_markers, int n_individuals, int device)
     call_buf[0] = call_buf[1] = call_buf[2] = 0;
 }
 
+// table sized from and loaded with a transposed-PLINK genotype file in one pass (plain) or two (.gz), parsed on the device
+DeviceGenoTable::DeviceGenoTable(const std::string &tped_path, int device)
+    : max_row(0), max_column(0), store(nullptr), pending_first(0), pending_count(0), selected_rev(0), selected_set(nullptr) {
+    uint64_t rows = 0;
+    uint32_t cols = 0;
+    GW_MUST(gwasdev_create_from_tped(tped_path.c_str(), device, &store, &rows, &cols));
+    max_row = (int)rows;
+    max_column = (int)cols;
+    plane_blocks = gwasdev_plane_blocks(cols);
+    cell_row.resize(2 * plane_blocks + 1);
+    call_buf[0] = call_buf[1] = call_buf[2] = 0;
+}
+
 DeviceGenoTable::~DeviceGenoTable() { gwasdev_destroy(store); }
 
 void DeviceGenoTable::flush() {

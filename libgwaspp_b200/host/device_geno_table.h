@@ -20,6 +20,7 @@ namespace genetics {
 class DeviceGenoTable {
 public:
     DeviceGenoTable(int n_markers, int n_individuals, int device = 0);
+    explicit DeviceGenoTable(const std::string &tped_path, int device = 0);   // dimensions and rows from the file, one pass
     virtual ~DeviceGenoTable();
 
     // ---- util::Table<DataBlock> (src/util/table/table.h:48-74)

@@ -22,92 +22,7 @@ static void usage() {
                  "--contin-debug | --contin-perform | --contin-cc-perform | --epi-debug | --epi-perform)\n";
 }
 
-int main(int argc, char **argv) {
-    std::string geno, pheno, outfile, test;
-    int device = 0;
-    bool host_parse = false;
-    for (int a = 1; a < argc; ++a) {
-        std::string s = argv[a];
-        if ((s == "-g" || s == "--geno") && a + 1 < argc) geno = argv[++a];
-        else if ((s == "-p" || s == "--pheno") && a + 1 < argc) pheno = argv[++a];
-        else if ((s == "-o" || s == "--output") && a + 1 < argc) outfile = argv[++a];
-        else if (s == "--device" && a + 1 < argc) device = atoi(argv[++a]);
-        else if (s == "--comp-level" && a + 1 < argc) ++a;          // accepted for command-line compatibility
-        else if (s == "--tplink") {}
-        else if (s == "--host-parse") host_parse = true;
-        else if (s.rfind("--", 0) == 0) test = s.substr(2);
-    }
-    if (geno.empty() || pheno.empty() || test.empty()) { usage(); return 1; }
-
-    std::set<int> cases, controls;
-    int n_individs = 0;
-    {
-        std::ifstream f(pheno.c_str());
-        if (!f.is_open()) { std::cerr << "cannot open " << pheno << std::endl; return 1; }
-        std::string line;
-        while (std::getline(f, line)) {
-            if (line.empty()) continue;
-            size_t pos = 0;
-            for (int col = 0; col < 5 && pos != std::string::npos; ++col) pos = line.find_first_of("\t ", pos) == std::string::npos ? std::string::npos : line.find_first_of("\t ", pos) + 1;
-            if (pos != std::string::npos && pos < line.size()) {
-                if (line[pos] == '1') cases.insert(n_individs);
-                else if (line[pos] == '0') controls.insert(n_individs);
-            }
-            ++n_individs;
-        }
-    }
-    // Genotypes: the whole file is parsed, labelled and packed on the device (gwasdev_load_tped; .gz works, a .bed is
-    // taken as SNP-major PLINK binary). --host-parse keeps the reference-shaped loop -- one addGenotypeRow per line
-    // with the host packer -- as a cross-check.
-    const bool is_bed = geno.size() > 4 && geno.compare(geno.size() - 4, 4, ".bed") == 0;
-    uint64_t n_rows64 = 0;
-    uint32_t n_cols = 0;
-    if (is_bed) {
-        if (gwasdev_bed_dims(geno.c_str(), (uint32_t)n_individs, &n_rows64) != GWASDEV_OK) { std::cerr << gwasdev_last_error() << std::endl; return 1; }
-    } else if (gwasdev_tped_dims(geno.c_str(), &n_rows64, &n_cols) != GWASDEV_OK) { std::cerr << gwasdev_last_error() << std::endl; return 1; }
-    const int n_markers = (int)n_rows64;
-    std::cout << "Found " << n_individs << " individuals." << std::endl;
-    std::cout << "Found " << n_markers << " markers" << std::endl;
-    GeneticData gd(n_markers, n_individs, device);
-    if (is_bed) {
-        // allele letters from the .bim next to the .bed (columns 5 and 6: A1, A2) decide the row header words, i.e. what
-        // getCallAt() spells; rows whose alleles are not two different letters of ACGT keep the default A / C
-        std::vector<unsigned char> alleles;
-        std::ifstream bim((geno.substr(0, geno.size() - 4) + ".bim").c_str());
-        if (bim.is_open()) {
-            std::string chr, id, cm, pos, a1, a2;
-            const std::string acgt = "ACGT";
-            while (bim >> chr >> id >> cm >> pos >> a1 >> a2) {
-                const size_t i1 = a1.size() == 1 ? acgt.find(a1[0]) : std::string::npos, i2 = a2.size() == 1 ? acgt.find(a2[0]) : std::string::npos;
-                const bool ok = i1 != std::string::npos && i2 != std::string::npos && i1 != i2;
-                alleles.push_back(ok ? (unsigned char)i1 : 0);
-                alleles.push_back(ok ? (unsigned char)i2 : 1);
-            }
-            if ((int)alleles.size() != 2 * n_markers) alleles.clear();
-        }
-        gd.getGenotypeTable()->loadBed(geno, alleles);
-    }
-    else if (!host_parse) gd.getGenotypeTable()->loadTransposedPlink(geno);
-    else {
-        std::ifstream f(geno.c_str());
-        std::string line, buf;
-        int row = 0;
-        while (std::getline(f, line)) {
-            if (line.empty()) continue;
-            size_t pos = 0;
-            for (int col = 0; col < 4; ++col) pos = line.find_first_of("\t ", pos) + 1;
-            buf.clear();
-            bool second = false;
-            for (size_t q = pos; q < line.size(); q += 2) {
-                char c = line[q];
-                c = c == '1' ? 'A' : c == '2' ? 'C' : c == '3' ? 'G' : c == '4' ? 'T' : c;
-                buf.push_back(c);
-                if (second) buf.push_back('\t');
-                second = !second;
-            }
-            gd.addGenotypeRow(row++, buf.data(), buf.data() + buf.size(), '\t');
-        }
-    }
+static int run_test(GeneticData &gd, const std::set<int> &cases, const std::set<int> &controls, const std::string &test, const std::string &outfile) {
     gd.setCaseControlSet(cases, controls);
     std::cout << "Setting " << cases.size() << " cases." << std::endl;
     std::cout << "Setting " << controls.size() << " controls." << std::endl;
@@ -159,4 +74,102 @@ int main(int argc, char **argv) {
     else { usage(); return 1; }
     std::cout << "DONE" << std::endl;
     return 0;
+}
+
+int main(int argc, char **argv) {
+    std::string geno, pheno, outfile, test;
+    int device = 0;
+    bool host_parse = false;
+    for (int a = 1; a < argc; ++a) {
+        std::string s = argv[a];
+        if ((s == "-g" || s == "--geno") && a + 1 < argc) geno = argv[++a];
+        else if ((s == "-p" || s == "--pheno") && a + 1 < argc) pheno = argv[++a];
+        else if ((s == "-o" || s == "--output") && a + 1 < argc) outfile = argv[++a];
+        else if (s == "--device" && a + 1 < argc) device = atoi(argv[++a]);
+        else if (s == "--comp-level" && a + 1 < argc) ++a;          // accepted for command-line compatibility
+        else if (s == "--tplink") {}
+        else if (s == "--host-parse") host_parse = true;
+        else if (s.rfind("--", 0) == 0) test = s.substr(2);
+    }
+    if (geno.empty() || pheno.empty() || test.empty()) { usage(); return 1; }
+
+    std::set<int> cases, controls;
+    int n_individs = 0;
+    {
+        std::ifstream f(pheno.c_str());
+        if (!f.is_open()) { std::cerr << "cannot open " << pheno << std::endl; return 1; }
+        std::string line;
+        while (std::getline(f, line)) {
+            if (line.empty()) continue;
+            size_t pos = 0;
+            for (int col = 0; col < 5 && pos != std::string::npos; ++col) pos = line.find_first_of("\t ", pos) == std::string::npos ? std::string::npos : line.find_first_of("\t ", pos) + 1;
+            if (pos != std::string::npos && pos < line.size()) {
+                if (line[pos] == '1') cases.insert(n_individs);
+                else if (line[pos] == '0') controls.insert(n_individs);
+            }
+            ++n_individs;
+        }
+    }
+    // Genotypes: the whole file is parsed, labelled and packed on the device (gwasdev_load_tped; .gz works, a .bed is
+    // taken as SNP-major PLINK binary). --host-parse keeps the reference-shaped loop -- one addGenotypeRow per line
+    // with the host packer -- as a cross-check.
+    const bool is_bed = geno.size() > 4 && geno.compare(geno.size() - 4, 4, ".bed") == 0;
+    std::cout << "Found " << n_individs << " individuals." << std::endl;
+    if (!is_bed && !host_parse) {   // table sized from the file and filled in the same pass
+        GeneticData gd_file(geno, device);
+        if (gd_file.getGenotypedIndividualsCount() != n_individs) {
+            std::cerr << geno << " has " << gd_file.getGenotypedIndividualsCount() << " genotype columns, " << pheno << " lists " << n_individs << " individuals" << std::endl;
+            return 1;
+        }
+        std::cout << "Found " << gd_file.getGenotypedMarkersCount() << " markers" << std::endl;
+        return run_test(gd_file, cases, controls, test, outfile);
+    }
+    uint64_t n_rows64 = 0;
+    uint32_t n_cols = 0;
+    if (is_bed) {
+        if (gwasdev_bed_dims(geno.c_str(), (uint32_t)n_individs, &n_rows64) != GWASDEV_OK) { std::cerr << gwasdev_last_error() << std::endl; return 1; }
+    } else if (gwasdev_tped_dims(geno.c_str(), &n_rows64, &n_cols) != GWASDEV_OK) { std::cerr << gwasdev_last_error() << std::endl; return 1; }
+    const int n_markers = (int)n_rows64;
+    std::cout << "Found " << n_markers << " markers" << std::endl;
+    GeneticData gd(n_markers, n_individs, device);
+    if (is_bed) {
+        // allele letters from the .bim next to the .bed (columns 5 and 6: A1, A2) decide the row header words, i.e. what
+        // getCallAt() spells; rows whose alleles are not two different letters of ACGT keep the default A / C
+        std::vector<unsigned char> alleles;
+        std::ifstream bim((geno.substr(0, geno.size() - 4) + ".bim").c_str());
+        if (bim.is_open()) {
+            std::string chr, id, cm, pos, a1, a2;
+            const std::string acgt = "ACGT";
+            while (bim >> chr >> id >> cm >> pos >> a1 >> a2) {
+                const size_t i1 = a1.size() == 1 ? acgt.find(a1[0]) : std::string::npos, i2 = a2.size() == 1 ? acgt.find(a2[0]) : std::string::npos;
+                const bool ok = i1 != std::string::npos && i2 != std::string::npos && i1 != i2;
+                alleles.push_back(ok ? (unsigned char)i1 : 0);
+                alleles.push_back(ok ? (unsigned char)i2 : 1);
+            }
+            if ((int)alleles.size() != 2 * n_markers) alleles.clear();
+        }
+        gd.getGenotypeTable()->loadBed(geno, alleles);
+    }
+    else if (!host_parse) gd.getGenotypeTable()->loadTransposedPlink(geno);
+    else {
+        std::ifstream f(geno.c_str());
+        std::string line, buf;
+        int row = 0;
+        while (std::getline(f, line)) {
+            if (line.empty()) continue;
+            size_t pos = 0;
+            for (int col = 0; col < 4; ++col) pos = line.find_first_of("\t ", pos) + 1;
+            buf.clear();
+            bool second = false;
+            for (size_t q = pos; q < line.size(); q += 2) {
+                char c = line[q];
+                c = c == '1' ? 'A' : c == '2' ? 'C' : c == '3' ? 'G' : c == '4' ? 'T' : c;
+                buf.push_back(c);
+                if (second) buf.push_back('\t');
+                second = !second;
+            }
+            gd.addGenotypeRow(row++, buf.data(), buf.data() + buf.size(), '\t');
+        }
+    }
+    return run_test(gd, cases, controls, test, outfile);
 }

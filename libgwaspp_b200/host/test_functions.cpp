@@ -10,6 +10,12 @@ namespace genetics {
 
 GeneticData::GeneticData(int m, int n, int device)
     : n_markers(m), n_individs(n), geno_tbl(new DeviceGenoTable(m, n, device)), ccs(new CaseControlSet(n)) {}
+GeneticData::GeneticData(const std::string &tped_path, int device)
+    : n_markers(0), n_individs(0), geno_tbl(new DeviceGenoTable(tped_path, device)), ccs(nullptr) {
+    n_markers = geno_tbl->row_size();
+    n_individs = geno_tbl->column_size();
+    ccs = new CaseControlSet(n_individs);
+}
 GeneticData::~GeneticData() { delete geno_tbl; delete ccs; }
 
 void GeneticData::setCaseControlSet(const std::set<int> &cases, const std::set<int> &controls) {

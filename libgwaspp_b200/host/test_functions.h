@@ -22,6 +22,7 @@ namespace genetics {
 class GeneticData {
 public:
     GeneticData(int n_markers, int n_individuals, int device = 0);
+    GeneticData(const std::string &tped_path, int device);   // genotype table sized from and loaded with the file
     ~GeneticData();
     int getGenotypedIndividualsCount() const { return n_individs; }
     int getGenotypedMarkersCount() const { return n_markers; }
