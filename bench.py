@@ -447,17 +447,15 @@ def pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max
     st.select_case_control(case_mask=case_mask, ctrl_mask=ctrl_mask)
     cap = 1 << 20
     d_hits = torch.empty((cap, 2), dtype=torch.int64, device="cuda")     # 16-byte gwasdev_hit records
+    from libgwaspp_b200 import multi_gpu as mg
 
     def step():
         n, stats = st.pairwise_scan(30.0, shard=rank, n_shards=world, capacity=cap, hits=d_hits, on_device=True)
-        if world > 1:   # top-k / hit gather over NCCL: counts, then the padded hit buffers
-            cnt = torch.tensor([n], dtype=torch.int64, device="cuda")
-            cnts = [torch.zeros_like(cnt) for _ in range(world)]
-            dist.all_gather(cnts, cnt)
-            mx = max(1, int(max(c.item() for c in cnts)))
-            bufs = [torch.empty((mx, 2), dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(bufs, d_hits[:mx].contiguous())
-            n = int(sum(c.item() for c in cnts))
+        if world > 1:   # top-k / hit gather over NCCL: counts, then the padded hit buffers (one collective each)
+            counts = mg.gather_counts(int(n), world, torch.device("cuda", local))
+            mx = max(1, max(counts))
+            mg.gather_records(d_hits[:mx], world)
+            n = int(sum(counts))
         return n, stats
 
     for _ in range(W):

@@ -54,15 +54,39 @@ def gather_hits(local_hits: np.ndarray, group=None, device=None) -> np.ndarray:
     world = dist.get_world_size(group)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    cnt = torch.tensor([len(local_hits)], dtype=torch.int64, device=device)
-    cnts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(cnts, cnt, group=group)
-    counts = [int(c.item()) for c in cnts]
+    counts = gather_counts(len(local_hits), world, device, group)
     cap = max(1, max(counts))
     mine = hits_to_tensor(local_hits, cap, device)
-    bufs = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(bufs, mine, group=group)
-    return merge_hits([tensor_to_hits(b, n) for b, n in zip(bufs, counts)])
+    allb = gather_records(mine, world, group)
+    return merge_hits([tensor_to_hits(allb[r], n) for r, n in enumerate(counts)])
+
+
+def gather_counts(n_local: int, world: int, device, group=None) -> list:
+    """Every rank's hit count: one collective and ONE device-to-host read (a .item() per rank is a synchronisation each)."""
+    import torch
+    import torch.distributed as dist
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=device)
+    if dist.get_backend(group) != "nccl":          # gloo (host-logic tests) has no all_gather_into_tensor
+        parts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(parts, cnt, group=group)
+        return [int(c.item()) for c in parts]
+    out = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, cnt, group=group)
+    return out.tolist()
+
+
+def gather_records(mine, world: int, group=None):
+    """(cap, 2) int64 hit records of every rank -> (world, cap, 2), one collective into one buffer."""
+    import torch
+    import torch.distributed as dist
+    mine = mine.contiguous()
+    if dist.get_backend(group) != "nccl":
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        return torch.stack(parts)
+    out = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out
 
 
 def shard_tiles(n_snps: int, shard: int, n_shards: int, tile: int = 64):
