@@ -294,6 +294,8 @@ def gpu_arm(args):
     if not args.no_pairwise:
         out["pairwise"] = pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks,
                                        sum_over_ranks, sampler)
+        if world == 1 and not args.pw_snps and not args.no_missing:
+            out["pairwise_missing_calls"] = pairwise_missing_gpu(gw, local, stream)
         if world > 1 and not args.no_cfg3 and not args.pw_snps:
             # BASELINE.json configs[3]: the north star's target problem, sharded by tile pairs over the ranks
             out["pairwise_configs3"] = pairwise_gpu(args, gw, torch, dist, rank, world, local, stream, barrier, max_over_ranks,
@@ -429,6 +431,34 @@ def biobank_gpu(args, gw, torch, local, stream, peaks, peak_src):
                        "snps": Ms, "sample_blocks": len(blocks), "block_samples": B, "seconds": round(t, 4),
                        "h2d_bytes": h2d, "h2d_gbs": round(h2d / t / 1e9, 2),
                        "check": "summed counts bit-identical to the resident scan"}
+    return res
+
+
+def pairwise_missing_gpu(gw, local, stream):
+    """configs[2] with 1 % of the calls missing (what real genotype data looks like): every 64-SNP block has missing calls,
+    so the whole screen takes the reference's 9-cell branch -- here the four-plane tensor-core kernel; the 9-cell AND+POPC
+    kernel it replaces is timed beside it."""
+    M, N, NCASE = PAIRWISE["n_snps"], PAIRWISE["n_samples"], PAIRWISE["n_case"]
+    res = {"workload": f"configs[2] shape with 1 % missing calls: {NCASE}/{N - NCASE} samples x {M} SNPs ({M * (M - 1) // 2} pairs), "
+                       "9-cell tables (compressed_genotype_table5.cpp:1000-1067) + KSA statistic, threshold 30"}
+    with gw.GenoStore(M, N, device=local) as st:
+        st.set_stream(stream.cuda_stream)
+        st.simulate(SEED, missing_rate=0.01)
+        st.select_case_control(gw.simulate_phenotype(SEED, N, NCASE))
+        for name, engine in (("tensor_cores_four_planes", 0), ("and_popc_nine_cells", 1)):
+            st.set_pair_engine(engine)
+            ms, hits = [], None
+            for it in range(4):
+                hits, s = st.pairwise_scan(30.0)
+                if it:
+                    ms.append(s.screen_ms)
+            k_ms = float(np.mean(ms))
+            res[name] = {"value": round(s.pairs_tested / (k_ms * 1e-3), 1), "unit": "pairs/s", "kernel_ms": round(k_ms, 3),
+                         "tiles_with_missing_calls": int(s.tiles_nine_cell), "hits": int(len(hits))}
+        cells = 9 * ((NCASE + 31) // 32 + (N - NCASE + 31) // 32)
+        peak, _ = gw.popc_peak(local)
+        res["and_popc_nine_cells"]["frac_of_popc_roofline"] = round(res["and_popc_nine_cells"]["value"] * cells / peak, 4)
+        res["tensor_cores_four_planes"]["x_popc_roofline"] = round(res["tensor_cores_four_planes"]["value"] * cells / peak, 4)
     return res
 
 
@@ -664,6 +694,7 @@ def main():
     ap.add_argument("--pw-cases", type=int, default=0)
     ap.add_argument("--pw-steps", type=int, default=5)
     ap.add_argument("--no-pairwise", action="store_true")
+    ap.add_argument("--no-missing", action="store_true", help="skip the section on a cohort with missing calls")
     ap.add_argument("--no-cfg3", action="store_true", help="N > 1: skip the configs[3] (5k/5k x 500k SNPs) pairwise section")
     ap.add_argument("--biobank", action="store_true", help="add the configs[4] biobank-scale section (needs ~110 GB of HBM)")
     ap.add_argument("--bb-snps", type=int, default=1_000_000)

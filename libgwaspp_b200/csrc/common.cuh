@@ -166,13 +166,20 @@ struct gwasdev_store {
     void *tmap_mm = nullptr;      // host copies of the two CUtensorMaps (A box, B box)
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
+    // four-plane operands (aa, bb, xx, padding) for the tiles with missing calls (pair_screen_mma4_kernel)
+    bool mm4_built = false;
+    int8_t *d_mm4 = nullptr;
+    size_t cap_mm4 = 0;
+    uint64_t mm4_rows = 0, mm4_tiles = 0;
+    void *tmap_mm4 = nullptr;
     float mma_qc = 0.f, mma_q0 = 0.f;   // constants of the upper-bound pre-filter (pairwise_mma.cu)
     uint32_t mma_bound_ncase = 0xffffffffu, mma_bound_n = 0;   // class split they were computed for
     std::vector<uint8_t> h_tile_missing;   // host copy of d_tile_missing (valid with side_valid)
     size_t cap_mm = 0, cap_mma_row = 0, cap_mma_col = 0;
     bool mma_side_valid = false;
     bool any_missing = false, any_clean = false;     // over tiles, valid with side_valid
-    bool pc_valid = false, pc_use_mma = false;       // cached pair / tile counts of the last pairwise scan's shard
+    bool pc_valid = false;                           // cached pair / tile counts of the last pairwise scan's shard
+    int pc_engines = 0;
     uint32_t pc_shard = 0, pc_n_shards = 0;
     uint64_t pc_pairs = 0, pc_tiles = 0, pc_nine = 0;
 

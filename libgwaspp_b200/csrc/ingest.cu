@@ -363,7 +363,7 @@ static int reserve_text(Ingest *g, size_t bytes, bool pinned) {
 }
 
 static void invalidate(gwasdev_store *s) {
-    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mma_side_valid = s->pc_valid = false;
+    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mm4_built = s->mma_side_valid = s->pc_valid = false;
 }
 
 static size_t chunk_bytes() {

@@ -43,4 +43,34 @@ int get_encode_tiled(encode_tiled_fn *out);
 
 __device__ __forceinline__ float u2f(uint32_t n) { return __uint_as_float(0x4B000000u | n) - 8388608.0f; }   // n < 2^23
 
+// fp32 KSA screen value of a 3x3x2 table with the per-SNP records of both SNPs (see pairwise.cu for the algebra)
+__device__ __forceinline__ float g_nlogn(float n) { return n * __logf(fmaxf(n, 1.0f)); }
+
+__device__ __forceinline__ float ksa_screen_f32(const uint32_t (&n)[2][3][3], const PairSide &A, const PairSide &B,
+                                                float N, float lnN) {
+    float S = 0.f, tau = 0.f, total = 0.f;
+    float row[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, col[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const float c0 = u2f(n[0][a][b]), c1 = u2f(n[1][a][b]), cab = c0 + c1;
+            const float W = fmaf(B.w[0][b], A.pca[0][a], B.w[1][b] * A.pca[1][a]);
+            tau = fmaf(cab, W, tau);
+            S += g_nlogn(c0) + g_nlogn(c1) - g_nlogn(cab);
+            row[0][a] += c0; row[1][a] += c1; col[0][b] += c0; col[1][b] += c1;
+            total += cab;
+        }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            S = fmaf(-row[k][g], A.lpca[k][g], S);
+            S = fmaf(-col[k][g], B.lw[k][g], S);
+        }
+    S = fmaf(-total, lnN, S);
+    return 2.0f * fmaf(N, logf(tau), S);
+}
+
+
 }  // namespace gwasdev

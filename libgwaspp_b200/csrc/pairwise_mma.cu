@@ -640,6 +640,268 @@ __global__ void expand_mma_kernel(const uint32_t *__restrict__ sel, uint32_t sel
     }
 }
 
+// =====================================================================================================
+// Tiles WITH missing calls on the tensor cores (four planes per SNP).
+//
+// The four counted corners stay exact when calls are missing; what fails is the margin shortcut for the five cells
+// that involve the heterozygote, because "not aa, not bb" is then "ab or missing". With a third one-hot plane per SNP --
+// xx, the class members without a call -- the GEMM also yields |aa_A & xx_B|, |bb_A & xx_B|, |xx_A & aa_B|, |xx_A & bb_B|
+// and |xx_A & xx_B|, and the nine core cells follow exactly (the reference's other branch,
+// compressed_genotype_table5.cpp:1000-1067, counts them with nine AND+POPC streams):
+//     AA_Bb = c_A[aa] - AA_BB - AA_bb - AA_xx        aa_Bb likewise          Aa_BB = c_B[aa] - AA_BB - aa_BB - xx_BB
+//     Aa_bb likewise        Aa_Bb = c_A[ab] - Aa_BB - Aa_bb - (c_B[xx] - AA_xx - aa_xx - xx_xx)
+// with c_X[g] the per-SNP class counts. Operand rows 4s+p: p = 0 aa, 1 bb, 2 xx, 3 zero padding (a power of two keeps
+// the pipeline of the two-plane kernel byte for byte: 256 x 256 row tiles, the same TMA boxes, descriptors and barriers;
+// a tile is now 64 x 64 SNPs, i.e. one 64-SNP missing-call block against another). The epilogue has no margin shortcut
+// and no bound pass: the four lanes that hold the planes of one A-SNP exchange their products so that each owns two of
+// the eight pairs of a 32-column load, builds the 3x3x2 table and evaluates ksa_screen_f32 (the epilogue of the
+// AND+POPC kernel it replaces). Only tiles with a missing call in either block are computed; the others belong to
+// pair_screen_mma_kernel.
+constexpr int M4_PLANES = 4;
+constexpr int M4_A_SNPS = 2 * MMA_A_SNPS / M4_PLANES;        // 32 A-SNPs per CTA (128 rows)
+constexpr int M4_BLK = MMA_N / M4_PLANES;                    // 64 SNPs per schedule block = B-SNPs of a tile
+static_assert(M4_BLK == TILE, "the four-plane tiles coincide with the 64-SNP missing-call blocks");
+
+struct Mma4Params {
+    uint32_t TB, NKB, n_bands;
+    uint64_t M, n_tiles;
+    uint32_t shard, n_shards;
+    const PairSide *side;
+    const uint8_t *tile_missing;   // per 64-SNP block
+    float thr, N, lnN;
+    Candidate *cand;
+    unsigned long long *n_cand;
+    uint64_t cap;
+};
+
+__device__ __forceinline__ uint32_t sel4(uint32_t k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t lo = (k & 1u) ? b : a, hi = (k & 1u) ? d : c;
+    return (k & 2u) ? hi : lo;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
+pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
+    unsigned char *col_sm = sm + MMA_STAGES * STAGE_BYTES_MMA;                 // per epilogue warp: PairSide records of its 16 B-SNPs
+    uint64_t *full = reinterpret_cast<uint64_t *>(col_sm + EPI_WARPS * COL_STAGE_BYTES);
+    uint64_t *empty = full + MMA_STAGES;
+    uint64_t *tfull = empty + MMA_STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint64_t u_first = pair_id, u_step = n_pairs;
+    const uint64_t first = shard_tile(u_first, p.shard, p.n_shards), last = p.n_tiles;
+    // all three roles walk the same tile sequence and skip the tiles without missing calls the same way
+    auto wanted = [&](uint32_t I2, uint32_t J) -> bool { return (p.tile_missing[I2] | p.tile_missing[J]) != 0; };
+
+    if (warp == TMA_WARP) {
+        if (lane == 0) {
+            uint64_t it = 0;
+            TileCursor cur; cur.locate(first, p.TB, p.n_bands);
+            for (uint64_t t = first, u = u_first; t < last;) {
+                uint32_t I2, J;
+                cur.decode(p.TB, I2, J);
+                { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
+                if (!wanted(I2, J)) continue;
+                const int a_row = (int)((2 * I2 + rank) * (2 * MMA_A_SNPS)), b_row = (int)(J * MMA_N + rank * MMA_B_SNPS);
+                for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
+                    const int st = (int)(it % MMA_STAGES);
+                    const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
+                    mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
+                    unsigned char *dst = sm + st * STAGE_BYTES_MMA;
+                    if (rank == 0) mbar_expect_tx(&full[st], nk * 2 * KB_BYTES);
+                    else mbar_arrive_remote(&full[st], 0);
+                    for (uint32_t k2 = 0; k2 < nk; ++k2) {
+                        tma_load_2d_pair(dst + k2 * KB_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), a_row, &full[st]);
+                        tma_load_2d_pair(dst + k2 * KB_BYTES + A_STAGE_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), b_row, &full[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        if (lane == 0 && rank == 0) {
+            uint64_t it = 0, tile_it = 0;
+            TileCursor cur; cur.locate(first, p.TB, p.n_bands);
+            for (uint64_t t = first, u = u_first; t < last;) {
+                uint32_t I2, J;
+                cur.decode(p.TB, I2, J);
+                { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
+                if (!wanted(I2, J)) continue;
+                const uint32_t buf = (uint32_t)(tile_it & 1);
+                mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + buf * ACC_COLS;
+                for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
+                    const int st = (int)(it % MMA_STAGES);
+                    const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
+                    mbar_wait_wd(&full[st], (uint32_t)((it / MMA_STAGES) & 1));
+                    tc_fence_after();
+                    for (uint32_t k2 = 0; k2 < nk; ++k2) {
+                        const uint32_t a_addr = base + st * STAGE_BYTES_MMA + k2 * KB_BYTES, b_addr = a_addr + A_STAGE_BYTES;
+                        const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+#pragma unroll
+                        for (int k = 0; k < MMA_KB / UMMA_K; ++k)
+                            tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb | k2 | (uint32_t)k) != 0);
+                    }
+                    tc_commit_mc(&empty[st], 3);
+                }
+                tc_commit_mc(&tfull[buf], 3);
+                ++tile_it;
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs: own 32 A-SNPs x the tile's 64 B-SNPs) =====
+        const int ew = warp;
+        const int q = warp & 3;                       // TMEM lane quadrant: rows 32q.. = A-SNPs 8q..8q+7 of this CTA
+        const int g = ew >> 2;                        // column group: 64 accumulator columns = 16 B-SNPs
+        const int a_loc = 8 * q + (lane >> 2);        // A-SNP of this lane inside the CTA's 32
+        const uint32_t pl = (uint32_t)lane & 3u;      // plane held by this lane's TMEM row (0 aa, 1 bb, 2 xx, 3 padding)
+        const unsigned qbase = (unsigned)lane & ~3u;
+        uint64_t tile_it = 0;
+        TileCursor cur; cur.locate(first, p.TB, p.n_bands);
+        for (uint64_t t = first, u = u_first; t < last;) {
+            uint32_t I2, J;
+            cur.decode(p.TB, I2, J);
+            { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
+            if (!wanted(I2, J)) continue;
+            const uint32_t buf = (uint32_t)(tile_it & 1);
+            const uint64_t gi = (uint64_t)I2 * M4_BLK + rank * M4_A_SNPS + a_loc;
+            // this warp's 16 column-role records (PairSide, 128 bytes each): 2 KiB contiguous -> its shared-memory slot
+            unsigned char *my_col = col_sm + ew * COL_STAGE_BYTES;
+            {
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.side + ((uint64_t)J * M4_BLK + 16 * g));
+                uint4 *dst = reinterpret_cast<uint4 *>(my_col);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst[32 * k + lane] = __ldg(src + 32 * k + lane);
+                __syncwarp();
+            }
+            const PairSide &A = p.side[gi < p.M ? gi : 0];   // read through L1: 8 records per warp, reused for 16 B-SNPs
+            if (lane == 0) mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 64 * g + 32 * h, v);
+                tc_wait_ld();
+                // columns 4s..4s+3 = planes (aa, bb, xx, pad) of B-SNP s of this load (s < 8). Lane o of the quad owns the
+                // pairs (a, s) for s = o and o + 4. In rotation r every lane reads from quad lane (o + r) & 3 the three
+                // products that lane holds for the reader's two pairs: D[e][r][c] = product (plane (o + r) & 3 of A,
+                // plane c of B-SNP o + 4e).
+                uint32_t D[2][4][3];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t d = (pl - (uint32_t)r) & 3u;          // the lane that reads from me in this rotation
+                    const unsigned src = qbase | ((pl + (uint32_t)r) & 3u);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const uint32_t mine = sel4(d, v[16 * e + 0 + c], v[16 * e + 4 + c], v[16 * e + 8 + c], v[16 * e + 12 + c]);
+                            D[e][r][c] = __shfl_sync(0xffffffffu, mine, src);
+                        }
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int b_loc = 16 * g + 8 * h + 4 * e + (int)pl;
+                    const uint64_t gj = (uint64_t)J * M4_BLK + b_loc;
+                    if (!(gi < gj && gj < p.M)) continue;
+                    // plane P of A is what arrived in rotation (P - o) & 3
+                    uint32_t prod[3][3];
+#pragma unroll
+                    for (int P = 0; P < 3; ++P) {
+                        const uint32_t r = ((uint32_t)P - pl) & 3u;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) prod[P][c] = sel4(r, D[e][0][c], D[e][1][c], D[e][2][c], D[e][3][c]);
+                    }
+                    const PairSide &B = *reinterpret_cast<const PairSide *>(my_col + (8 * h + 4 * e + (int)pl) * 128);
+                    uint32_t n[2][3][3];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        uint32_t x[3][3];   // x[P][c]: class-k count of (plane P of A) & (plane c of B); planes aa, bb, xx
+#pragma unroll
+                        for (int P = 0; P < 3; ++P)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) x[P][c] = k ? (prod[P][c] >> CTRL_SHIFT) : (prod[P][c] & 0x3fffu);
+                        const uint32_t *ca = A.cnt[k], *cb = B.cnt[k];     // aa, ab, bb, xx
+                        n[k][0][0] = x[0][0]; n[k][0][2] = x[0][1]; n[k][2][0] = x[1][0]; n[k][2][2] = x[1][1];
+                        n[k][0][1] = ca[0] - x[0][0] - x[0][1] - x[0][2];
+                        n[k][2][1] = ca[2] - x[1][0] - x[1][1] - x[1][2];
+                        n[k][1][0] = cb[0] - x[0][0] - x[1][0] - x[2][0];
+                        n[k][1][2] = cb[2] - x[0][1] - x[1][1] - x[2][1];
+                        n[k][1][1] = ca[1] - n[k][1][0] - n[k][1][2] - (cb[3] - x[0][2] - x[1][2] - x[2][2]);
+                    }
+                    const float stat = ksa_screen_f32(n, A, B, p.N, p.lnN);
+                    if (stat > p.thr) {
+                        const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
+                        if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tempty[buf], 0);
+            ++tile_it;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// operand rows of the four-plane engine: one thread per (SNP, 32-sample word), 32 bytes of each of aa, bb, xx
+// (the padding row 4s+3 stays zero from the memset)
+__global__ void expand_mma4_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Kc, uint32_t Kt,
+                                   uint32_t n_case, uint32_t n_ctrl, uint32_t case_bytes, uint32_t kbytes, uint64_t M,
+                                   int8_t *__restrict__ mm) {
+    const uint32_t K = Kc + Kt;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t snp = idx / K;
+    if (snp >= M) return;
+    const uint32_t k = (uint32_t)(idx - snp * K);
+    const uint32_t *row = sel + snp * (uint64_t)sel_stride;
+    uint32_t p1, p2, off, shift, left;
+    if (k < Kc) { p1 = row[sel_word(0, 0, k)]; p2 = row[sel_word(0, 1, k)]; off = 32 * k; shift = 0; left = n_case - 32 * k; }
+    else { p1 = row[sel_word(2 * Wc, 0, k - Kc)]; p2 = row[sel_word(2 * Wc, 1, k - Kc)]; off = case_bytes + 32 * (k - Kc); shift = 7; left = n_ctrl - 32 * (k - Kc); }
+    const uint32_t members = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);     // class members among the word's 32 positions
+    const uint32_t bb = p1 & p2, aa = p1 ^ bb, xx = ~(p1 | p2) & members;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+        const uint32_t x = pl == 0 ? aa : (pl == 1 ? bb : xx);
+        uint4 *dst = reinterpret_cast<uint4 *>(mm + (4 * snp + pl) * (uint64_t)kbytes + off);
+        uint4 lo, hi;
+        lo.x = spread4(x & 15u) << shift;         lo.y = spread4((x >> 4) & 15u) << shift;
+        lo.z = spread4((x >> 8) & 15u) << shift;  lo.w = spread4((x >> 12) & 15u) << shift;
+        hi.x = spread4((x >> 16) & 15u) << shift; hi.y = spread4((x >> 20) & 15u) << shift;
+        hi.z = spread4((x >> 24) & 15u) << shift; hi.w = spread4((x >> 28) & 15u) << shift;
+        dst[0] = lo; dst[1] = hi;
+    }
+}
+
 __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__ mi, uint64_t M, uint64_t Mrec, uint32_t n_ind,
                                 MmaRow *__restrict__ row, MmaCol *__restrict__ col, MmaRowF *__restrict__ rowf, MmaColF *__restrict__ colf) {
     const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -920,6 +1182,91 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
     p.qc = s->mma_qc; p.q0 = s->mma_q0; p.thr2 = 0.f;
     p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0; p.prof = nullptr;
     p.dbg = getenv("GWASDEV_MMA_DEBUG") ? (uint32_t)atoi(getenv("GWASDEV_MMA_DEBUG")) : 0u;
+}
+
+// ---- four-plane engine: host side ---------------------------------------------------------------------
+static uint32_t m4_blocks(const gwasdev_store *s) { return (uint32_t)((s->M + M4_BLK - 1) / M4_BLK); }
+
+static uint64_t m4_schedule_tiles(uint32_t TB) {
+    const uint32_t n_bands = (TB + BAND - 1) / BAND;
+    uint64_t tiles = band_offset(TB, n_bands - 1);
+    const uint32_t na = band_height(TB, n_bands - 1);
+    for (uint32_t J = BAND * (n_bands - 1); J < TB; ++J) tiles += column_height(na, J - BAND * (n_bands - 1));
+    return tiles;
+}
+
+static int ensure_mma4_inputs(gwasdev_store *s) {
+    if (s->mm4_built) return GWASDEV_OK;
+    const uint32_t TB = m4_blocks(s);
+    const uint32_t case_bytes = round_up(s->n_case, MMA_KB), ctrl_bytes = round_up(s->n_ctrl, MMA_KB);
+    s->mm_kbytes = case_bytes + ctrl_bytes;                 // the same row geometry as the two-plane matrix
+    s->mm4_rows = (uint64_t)M4_PLANES * TB * M4_BLK;
+    const size_t bytes = (size_t)s->mm4_rows * s->mm_kbytes;
+    GW_CUDA(reserve_raw(s->d_mm4, s->cap_mm4, bytes));
+    GW_CUDA(cudaMemsetAsync(s->d_mm4, 0, bytes, s->stream));
+    const uint32_t K = s->Kc + s->Kt;
+    const uint64_t work = s->M * K;
+    expand_mma4_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, s->n_case,
+                                                                              s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4);
+    GW_LAUNCHED();
+    if (!s->tmap_mm4 && posix_memalign(&s->tmap_mm4, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm4 = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
+    encode_tiled_fn encode = nullptr;
+    { int rc = get_encode_tiled(&encode); if (rc != GWASDEV_OK) return rc; }
+    cuuint64_t gdim[2] = {s->mm_kbytes, s->mm4_rows};
+    cuuint64_t gstride[1] = {s->mm_kbytes};
+    cuuint32_t box[2] = {(cuuint32_t)MMA_KB, (cuuint32_t)(2 * MMA_A_SNPS)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode((CUtensorMap *)s->tmap_mm4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s->d_mm4, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (four-plane operand matrix) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
+    s->mm4_tiles = m4_schedule_tiles(TB);
+    s->mm4_built = true;
+    return GWASDEV_OK;
+}
+
+// pairs (i < j < M) and tiles of the shard among the tiles with missing calls, in the four-plane schedule
+uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags, uint64_t *tiles_out) {
+    const uint32_t TB = m4_blocks(s), n_bands = (TB + BAND - 1) / BAND;
+    const uint64_t M = s->M;
+    uint64_t pairs = 0, tiles = 0, t = 0;
+    for (uint32_t b = 0; b < n_bands; ++b) {
+        const uint32_t na = band_height(TB, b);
+        for (uint32_t J = BAND * b; J < TB; ++J) {
+            const uint32_t h = column_height(na, J - BAND * b);
+            for (uint32_t ii = 0; ii < h; ++ii, ++t) {
+                const uint32_t I2 = BAND * b + ii;
+                if (!tile_in_shard(t, shard, n_shards) || !(flags[I2] | flags[J])) continue;
+                ++tiles;
+                if (I2 < J && (uint64_t)(J + 1) * M4_BLK <= M) pairs += (uint64_t)M4_BLK * M4_BLK;     // full off-diagonal block
+                else pairs += rect_pairs(M, (uint64_t)I2 * M4_BLK, (uint64_t)(I2 + 1) * M4_BLK, (uint64_t)J * M4_BLK, (uint64_t)(J + 1) * M4_BLK);
+            }
+        }
+    }
+    if (tiles_out) *tiles_out = tiles;
+    return pairs;
+}
+
+// Launches the four-plane tensor-core screen over this shard's tiles with missing calls. thr carries the fp32 margin.
+int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, void *cand,
+                                 unsigned long long *n_cand, uint64_t cap) {
+    int rc = ensure_mma4_inputs(s);
+    if (rc != GWASDEV_OK) return rc;
+    Mma4Params p;
+    p.TB = m4_blocks(s); p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M; p.n_tiles = s->mm4_tiles;
+    p.shard = shard; p.n_shards = n_shards; p.side = s->d_side; p.tile_missing = s->d_tile_missing;
+    const uint32_t n_ind = s->n_case + s->n_ctrl;
+    p.thr = thr; p.N = (float)n_ind; p.lnN = (float)std::log((double)n_ind);
+    p.cand = (Candidate *)cand; p.n_cand = n_cand; p.cap = cap;
+    const uint64_t my_tiles = shard_tiles_before(p.n_tiles, shard, n_shards);
+    if (my_tiles == 0) return GWASDEV_OK;
+    int sms = 0;
+    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const size_t smem = mma_smem_bytes();
+    GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));
+    pair_screen_mma4_kernel<<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);
+    GW_LAUNCHED();
+    return GWASDEV_OK;
 }
 
 // Launches the tensor-core screen for this shard's clean tiles. thr already carries the fp32 margin.

@@ -352,7 +352,7 @@ int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_stor
 static void free_scratch(gwasdev_store::Scratch &sc) { if (sc.p) cudaFree(sc.p); sc.p = nullptr; sc.cap = 0; }
 
 static void invalidate_selection(gwasdev_store *s) {
-    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mma_side_valid = s->pc_valid = false;
+    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mm4_built = s->mma_side_valid = s->pc_valid = false;
 }
 
 void gwasdev_destroy(gwasdev_store *s) {
@@ -361,8 +361,8 @@ void gwasdev_destroy(gwasdev_store *s) {
     gwasdev_internal_free_ingest(s);
     cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_ctrl_sel_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
     cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
-    free(s->tmap); free(s->tmap_mm);
-    cudaFree(s->d_mm); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col);
+    free(s->tmap); free(s->tmap_mm); free(s->tmap_mm4);
+    cudaFree(s->d_mm); cudaFree(s->d_mm4); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col);
     for (gwasdev_store::Scratch *sc : {&s->sc_out_counts, &s->sc_out_stats, &s->sc_out_mi, &s->sc_cnt, &s->sc_cand, &s->sc_keys,
                                       &s->sc_keys2, &s->sc_vals, &s->sc_vals2, &s->sc_sort, &s->sc_hits, &s->sc_pi, &s->sc_pj,
                                       &s->sc_a, &s->sc_b, &s->sc_stage})
