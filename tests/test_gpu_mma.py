@@ -103,3 +103,29 @@ def test_engine_selection_errors(orc):
         st.set_pair_engine(2)
         hits, stats = st.pairwise_scan(30.0)
         assert stats.engine == 2 and stats.pairs_tested == 64 * 63 // 2
+
+
+def test_four_plane_engine_on_a_cohort_where_every_block_has_missing_calls(orc):
+    """Real genotype data: every 64-SNP block has missing calls, so the whole screen is the reference's 9-cell branch
+    (compressed_genotype_table5.cpp:1000-1067). The four-plane tensor-core kernel (planes aa, bb, xx) must return the
+    AND+POPC kernel's records bit for bit and the oracle's hit set, also sharded."""
+    M, N, ncase = 700, 1500, 640
+    codes, pheno = planted_cohort(orc, 77, M, N, ncase, 0.02, 6)
+    with make_store(orc, codes, pheno) as st:
+        h4, s4 = st.pairwise_scan(30.0)                      # default engine: tensor cores
+        assert s4.engine == 2 and s4.tiles_nine_cell == s4.tiles > 0 and s4.pairs_tested == M * (M - 1) // 2
+        st.set_pair_engine(1)
+        h1, s1 = st.pairwise_scan(30.0)
+        assert s1.engine == 1 and np.array_equal(h1, h4)
+        st.set_pair_engine(0)
+        sel = st.get_selected_rows()
+        mar = orc.margins(sel, st.n_case, st.n_ctrl)
+        hi, hj, hs, _ = orc.boost_screen(sel, mar, st.n_case, st.n_ctrl, 30.0)
+        assert len(hi) >= 3 and np.array_equal(h4["i"], hi) and np.array_equal(h4["j"], hj) and rel_close(h4["stat"], hs, 1e-12)
+        parts = [st.pairwise_scan(30.0, shard=k, n_shards=5) for k in range(5)]
+        assert sum(p[1].pairs_tested for p in parts) == M * (M - 1) // 2
+        assert np.array_equal(np.sort(np.concatenate([p[0] for p in parts]), order=["i", "j"]), h4)
+        l4, _ = st.pairwise_scan(-1e9)                       # every pair with a finite statistic goes through epilogue and re-score
+        st.set_pair_engine(1)
+        l1, _ = st.pairwise_scan(-1e9)
+        assert len(l4) > 100 * len(h4) and np.array_equal(l1, l4)
