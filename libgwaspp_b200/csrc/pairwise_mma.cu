@@ -679,6 +679,13 @@ __device__ __forceinline__ uint32_t sel4(uint32_t k, uint32_t a, uint32_t b, uin
     return (k & 2u) ? hi : lo;
 }
 
+// SPLIT = false: planes (aa, bb, xx, padding) with the signed case/control bytes, tiles WITH missing calls (above).
+// SPLIT = true : planes (aa of the cases, bb of the cases, aa of the controls, bb of the controls), every byte +1, tiles
+//                WITHOUT missing calls of cohorts whose class sizes do not fit the packed accumulator of the two-plane
+//                kernel (n_case >= 16384 or n_ctrl >= 131072): the two classes land in different products, each a full
+//                int32 count, and the five other cells follow from the per-SNP class counts as in the reference's shortcut
+//                (compressed_genotype_table5.cpp:1084-1092, :1133-1141). Same pipeline, same 4x MACs.
+template <bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
 pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Params p) {
     extern __shared__ unsigned char smem_raw[];
@@ -712,7 +719,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
     const uint64_t u_first = pair_id, u_step = n_pairs;
     const uint64_t first = shard_tile(u_first, p.shard, p.n_shards), last = p.n_tiles;
     // all three roles walk the same tile sequence and skip the tiles without missing calls the same way
-    auto wanted = [&](uint32_t I2, uint32_t J) -> bool { return (p.tile_missing[I2] | p.tile_missing[J]) != 0; };
+    auto wanted = [&](uint32_t I2, uint32_t J) -> bool { return ((p.tile_missing[I2] | p.tile_missing[J]) != 0) != SPLIT; };
 
     if (warp == TMA_WARP) {
         if (lane == 0) {
@@ -808,7 +815,8 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                 // pairs (a, s) for s = o and o + 4. In rotation r every lane reads from quad lane (o + r) & 3 the three
                 // products that lane holds for the reader's two pairs: D[e][r][c] = product (plane (o + r) & 3 of A,
                 // plane c of B-SNP o + 4e).
-                uint32_t D[2][4][3];
+                constexpr int NC = SPLIT ? 4 : 3;       // B planes a pair needs (the padding plane of the missing-call layout is never read)
+                uint32_t D[2][4][NC];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const uint32_t d = (pl - (uint32_t)r) & 3u;          // the lane that reads from me in this rotation
@@ -816,7 +824,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
 #pragma unroll
                     for (int e = 0; e < 2; ++e)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
+                        for (int c = 0; c < NC; ++c) {
                             const uint32_t mine = sel4(d, v[16 * e + 0 + c], v[16 * e + 4 + c], v[16 * e + 8 + c], v[16 * e + 12 + c]);
                             D[e][r][c] = __shfl_sync(0xffffffffu, mine, src);
                         }
@@ -827,29 +835,39 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                     const uint64_t gj = (uint64_t)J * M4_BLK + b_loc;
                     if (!(gi < gj && gj < p.M)) continue;
                     // plane P of A is what arrived in rotation (P - o) & 3
-                    uint32_t prod[3][3];
+                    uint32_t prod[NC][NC];
 #pragma unroll
-                    for (int P = 0; P < 3; ++P) {
+                    for (int P = 0; P < NC; ++P) {
                         const uint32_t r = ((uint32_t)P - pl) & 3u;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) prod[P][c] = sel4(r, D[e][0][c], D[e][1][c], D[e][2][c], D[e][3][c]);
+                        for (int c = 0; c < NC; ++c) prod[P][c] = sel4(r, D[e][0][c], D[e][1][c], D[e][2][c], D[e][3][c]);
                     }
                     const PairSide &B = *reinterpret_cast<const PairSide *>(my_col + (8 * h + 4 * e + (int)pl) * 128);
                     uint32_t n[2][3][3];
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        uint32_t x[3][3];   // x[P][c]: class-k count of (plane P of A) & (plane c of B); planes aa, bb, xx
-#pragma unroll
-                        for (int P = 0; P < 3; ++P)
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) x[P][c] = k ? (prod[P][c] >> CTRL_SHIFT) : (prod[P][c] & 0x3fffu);
                         const uint32_t *ca = A.cnt[k], *cb = B.cnt[k];     // aa, ab, bb, xx
-                        n[k][0][0] = x[0][0]; n[k][0][2] = x[0][1]; n[k][2][0] = x[1][0]; n[k][2][2] = x[1][1];
-                        n[k][0][1] = ca[0] - x[0][0] - x[0][1] - x[0][2];
-                        n[k][2][1] = ca[2] - x[1][0] - x[1][1] - x[1][2];
-                        n[k][1][0] = cb[0] - x[0][0] - x[1][0] - x[2][0];
-                        n[k][1][2] = cb[2] - x[0][1] - x[1][1] - x[2][1];
-                        n[k][1][1] = ca[1] - n[k][1][0] - n[k][1][2] - (cb[3] - x[0][2] - x[1][2] - x[2][2]);
+                        if (SPLIT) {
+                            const uint32_t AB = prod[2 * k][2 * k], Ab = prod[2 * k][2 * k + 1], aB = prod[2 * k + 1][2 * k], ab = prod[2 * k + 1][2 * k + 1];
+                            n[k][0][0] = AB; n[k][0][2] = Ab; n[k][2][0] = aB; n[k][2][2] = ab;
+                            n[k][0][1] = ca[0] - AB - Ab;
+                            n[k][2][1] = ca[2] - aB - ab;
+                            n[k][1][0] = cb[0] - AB - aB;
+                            n[k][1][2] = cb[2] - Ab - ab;
+                            n[k][1][1] = cb[1] - n[k][0][1] - n[k][2][1];
+                        } else {
+                            uint32_t x[3][3];   // x[P][c]: class-k count of (plane P of A) & (plane c of B); planes aa, bb, xx
+#pragma unroll
+                            for (int P = 0; P < 3; ++P)
+#pragma unroll
+                                for (int c = 0; c < 3; ++c) x[P][c] = k ? (prod[P][c] >> CTRL_SHIFT) : (prod[P][c] & 0x3fffu);
+                            n[k][0][0] = x[0][0]; n[k][0][2] = x[0][1]; n[k][2][0] = x[1][0]; n[k][2][2] = x[1][1];
+                            n[k][0][1] = ca[0] - x[0][0] - x[0][1] - x[0][2];
+                            n[k][2][1] = ca[2] - x[1][0] - x[1][1] - x[1][2];
+                            n[k][1][0] = cb[0] - x[0][0] - x[1][0] - x[2][0];
+                            n[k][1][2] = cb[2] - x[0][1] - x[1][1] - x[2][1];
+                            n[k][1][1] = ca[1] - n[k][1][0] - n[k][1][2] - (cb[3] - x[0][2] - x[1][2] - x[2][2]);
+                        }
                     }
                     const float stat = ksa_screen_f32(n, A, B, p.N, p.lnN);
                     if (stat > p.thr) {
@@ -875,6 +893,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
 
 // operand rows of the four-plane engine: one thread per (SNP, 32-sample word), 32 bytes of each of aa, bb, xx
 // (the padding row 4s+3 stays zero from the memset)
+template <bool SPLIT>
 __global__ void expand_mma4_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Kc, uint32_t Kt,
                                    uint32_t n_case, uint32_t n_ctrl, uint32_t case_bytes, uint32_t kbytes, uint64_t M,
                                    int8_t *__restrict__ mm) {
@@ -889,10 +908,12 @@ __global__ void expand_mma4_kernel(const uint32_t *__restrict__ sel, uint32_t se
     else { p1 = row[sel_word(2 * Wc, 0, k - Kc)]; p2 = row[sel_word(2 * Wc, 1, k - Kc)]; off = case_bytes + 32 * (k - Kc); shift = 7; left = n_ctrl - 32 * (k - Kc); }
     const uint32_t members = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);     // class members among the word's 32 positions
     const uint32_t bb = p1 & p2, aa = p1 ^ bb, xx = ~(p1 | p2) & members;
+    if (SPLIT) shift = 0;                                    // every byte +1: the classes are told apart by the plane
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl) {
+    for (int pl = 0; pl < (SPLIT ? 2 : 3); ++pl) {
         const uint32_t x = pl == 0 ? aa : (pl == 1 ? bb : xx);
-        uint4 *dst = reinterpret_cast<uint4 *>(mm + (4 * snp + pl) * (uint64_t)kbytes + off);
+        const int plane = SPLIT ? (k < Kc ? pl : 2 + pl) : pl;   // split: rows 0,1 hold the cases' aa / bb, rows 2,3 the controls'
+        uint4 *dst = reinterpret_cast<uint4 *>(mm + (4 * snp + plane) * (uint64_t)kbytes + off);
         uint4 lo, hi;
         lo.x = spread4(x & 15u) << shift;         lo.y = spread4((x >> 4) & 15u) << shift;
         lo.z = spread4((x >> 8) & 15u) << shift;  lo.w = spread4((x >> 12) & 15u) << shift;
@@ -1195,8 +1216,8 @@ static uint64_t m4_schedule_tiles(uint32_t TB) {
     return tiles;
 }
 
-static int ensure_mma4_inputs(gwasdev_store *s) {
-    if (s->mm4_built) return GWASDEV_OK;
+static int ensure_mma4_inputs(gwasdev_store *s, bool split) {
+    if (s->mm4_built && s->mm4_split == split) return GWASDEV_OK;
     const uint32_t TB = m4_blocks(s);
     const uint32_t case_bytes = round_up(s->n_case, MMA_KB), ctrl_bytes = round_up(s->n_ctrl, MMA_KB);
     s->mm_kbytes = case_bytes + ctrl_bytes;                 // the same row geometry as the two-plane matrix
@@ -1206,8 +1227,10 @@ static int ensure_mma4_inputs(gwasdev_store *s) {
     GW_CUDA(cudaMemsetAsync(s->d_mm4, 0, bytes, s->stream));
     const uint32_t K = s->Kc + s->Kt;
     const uint64_t work = s->M * K;
-    expand_mma4_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, s->n_case,
-                                                                              s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4);
+    if (split) expand_mma4_kernel<true><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, s->n_case,
+                                                                                          s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4);
+    else expand_mma4_kernel<false><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, s->n_case,
+                                                                                     s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4);
     GW_LAUNCHED();
     if (!s->tmap_mm4 && posix_memalign(&s->tmap_mm4, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm4 = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
     encode_tiled_fn encode = nullptr;
@@ -1221,11 +1244,12 @@ static int ensure_mma4_inputs(gwasdev_store *s) {
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (four-plane operand matrix) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
     s->mm4_tiles = m4_schedule_tiles(TB);
     s->mm4_built = true;
+    s->mm4_split = split;
     return GWASDEV_OK;
 }
 
 // pairs (i < j < M) and tiles of the shard among the tiles with missing calls, in the four-plane schedule
-uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags, uint64_t *tiles_out) {
+uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags, bool split, uint64_t *tiles_out) {
     const uint32_t TB = m4_blocks(s), n_bands = (TB + BAND - 1) / BAND;
     const uint64_t M = s->M;
     uint64_t pairs = 0, tiles = 0, t = 0;
@@ -1235,7 +1259,7 @@ uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uin
             const uint32_t h = column_height(na, J - BAND * b);
             for (uint32_t ii = 0; ii < h; ++ii, ++t) {
                 const uint32_t I2 = BAND * b + ii;
-                if (!tile_in_shard(t, shard, n_shards) || !(flags[I2] | flags[J])) continue;
+                if (!tile_in_shard(t, shard, n_shards) || ((flags[I2] | flags[J]) != 0) == split) continue;   // split mode: the clean tiles
                 ++tiles;
                 if (I2 < J && (uint64_t)(J + 1) * M4_BLK <= M) pairs += (uint64_t)M4_BLK * M4_BLK;     // full off-diagonal block
                 else pairs += rect_pairs(M, (uint64_t)I2 * M4_BLK, (uint64_t)(I2 + 1) * M4_BLK, (uint64_t)J * M4_BLK, (uint64_t)(J + 1) * M4_BLK);
@@ -1247,9 +1271,9 @@ uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uin
 }
 
 // Launches the four-plane tensor-core screen over this shard's tiles with missing calls. thr carries the fp32 margin.
-int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, void *cand,
+int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, bool split, void *cand,
                                  unsigned long long *n_cand, uint64_t cap) {
-    int rc = ensure_mma4_inputs(s);
+    int rc = ensure_mma4_inputs(s, split);
     if (rc != GWASDEV_OK) return rc;
     Mma4Params p;
     p.TB = m4_blocks(s); p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M; p.n_tiles = s->mm4_tiles;
@@ -1262,9 +1286,14 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, ui
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const size_t smem = mma_smem_bytes();
-    GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));
-    pair_screen_mma4_kernel<<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);
+    if (split) {
+        GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_screen_mma4_kernel<true><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);
+    } else {
+        GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pair_screen_mma4_kernel<false><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);
+    }
     GW_LAUNCHED();
     return GWASDEV_OK;
 }

@@ -129,3 +129,30 @@ def test_four_plane_engine_on_a_cohort_where_every_block_has_missing_calls(orc):
         st.set_pair_engine(1)
         l1, _ = st.pairwise_scan(-1e9)
         assert len(l4) > 100 * len(h4) and np.array_equal(l1, l4)
+
+
+@pytest.mark.parametrize("M,N,ncase,popc_ok", [(200, 40_000, 20_000, True), (130, 150_000, 70_000, False)])
+def test_split_class_planes_for_cohorts_beyond_the_packed_accumulator(orc, M, N, ncase, popc_ok):
+    """n_case >= 16384: the two-plane kernel's int32 accumulator (n_case + 2^14 n_ctrl) no longer fits; the four-plane kernel
+    with one pair of planes per class counts both classes as full int32 products. Records must equal the AND+POPC engine's
+    (while that one still applies: classes below 65536) and the oracle's hit set."""
+    codes, pheno = planted_cohort(orc, 91, M, N, ncase, 0.0, 5)
+    with make_store(orc, codes, pheno) as st:
+        h, s = st.pairwise_scan(30.0)
+        assert s.engine == 2 and s.pairs_tested == M * (M - 1) // 2
+        sel = st.get_selected_rows()
+        mar = orc.margins(sel, st.n_case, st.n_ctrl)
+        hi, hj, hs, _ = orc.boost_screen(sel, mar, st.n_case, st.n_ctrl, 30.0)
+        assert len(hi) >= 3 and np.array_equal(h["i"], hi) and np.array_equal(h["j"], hj) and rel_close(h["stat"], hs, 1e-12)
+        parts = [st.pairwise_scan(30.0, shard=k, n_shards=2) for k in range(2)]
+        assert np.array_equal(np.sort(np.concatenate([p[0] for p in parts]), order=["i", "j"]), h)
+        low, _ = st.pairwise_scan(-1e9)
+        assert len(low) == M * (M - 1) // 2 or len(low) > 100 * len(h)
+        st.set_pair_engine(1)
+        if popc_ok:
+            h1, s1 = st.pairwise_scan(30.0)
+            l1, _ = st.pairwise_scan(-1e9)
+            assert s1.engine == 1 and np.array_equal(h1, h) and np.array_equal(l1, low)
+        else:
+            with pytest.raises(gw.GwasDevError, match="65535"):
+                st.pairwise_scan(30.0)
