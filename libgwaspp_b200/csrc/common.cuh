@@ -167,7 +167,8 @@ struct gwasdev_store {
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
     // four-plane operands (aa, bb, xx, padding) for the tiles with missing calls (pair_screen_mma4_kernel)
-    bool mm4_built = false, mm4_split = false;   // split: planes per class (cohorts beyond the packed accumulator) instead of aa/bb/xx
+    bool mm4_built = false;
+    int mm4_mode = 0;             // 0: aa/bb/xx planes, packed classes; 1: per-class planes; 2: aa/bb/xx planes, one accumulator per class
     int8_t *d_mm4 = nullptr;
     size_t cap_mm4 = 0;
     uint64_t mm4_rows = 0, mm4_tiles = 0;

@@ -664,6 +664,7 @@ static_assert(M4_BLK == TILE, "the four-plane tiles coincide with the 64-SNP mis
 
 struct Mma4Params {
     uint32_t TB, NKB, n_bands;
+    uint32_t case_kb;              // 128-byte sample blocks of the case range of a row (two-accumulator mode)
     uint64_t M, n_tiles;
     uint32_t shard, n_shards;
     const PairSide *side;
@@ -685,9 +686,14 @@ __device__ __forceinline__ uint32_t sel4(uint32_t k, uint32_t a, uint32_t b, uin
 //                kernel (n_case >= 16384 or n_ctrl >= 131072): the two classes land in different products, each a full
 //                int32 count, and the five other cells follow from the per-SNP class counts as in the reference's shortcut
 //                (compressed_genotype_table5.cpp:1084-1092, :1133-1141). Same pipeline, same 4x MACs.
-template <bool SPLIT>
+// MODE 2  : planes (aa, bb, xx, padding), every byte +1, cases and controls accumulated into SEPARATE TMEM accumulators (the
+//                K range of a row is class-pure: the MMAs of the case sample blocks go to one, those of the control blocks
+//                to the other). Any class sizes with missing calls; the price is the accumulator double buffering (the
+//                epilogue of a tile no longer overlaps the MMAs of the next). All tiles of such a cohort take it.
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
 pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Params p) {
+    constexpr bool SPLIT = MODE == 1, TWOACC = MODE == 2;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
@@ -719,7 +725,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
     const uint64_t u_first = pair_id, u_step = n_pairs;
     const uint64_t first = shard_tile(u_first, p.shard, p.n_shards), last = p.n_tiles;
     // all three roles walk the same tile sequence and skip the tiles without missing calls the same way
-    auto wanted = [&](uint32_t I2, uint32_t J) -> bool { return ((p.tile_missing[I2] | p.tile_missing[J]) != 0) != SPLIT; };
+    auto wanted = [&](uint32_t I2, uint32_t J) -> bool { return TWOACC || ((p.tile_missing[I2] | p.tile_missing[J]) != 0) != SPLIT; };
 
     if (warp == TMA_WARP) {
         if (lane == 0) {
@@ -754,8 +760,9 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                 cur.decode(p.TB, I2, J);
                 { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
                 if (!wanted(I2, J)) continue;
-                const uint32_t buf = (uint32_t)(tile_it & 1);
-                mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
+                // two accumulators per tile (TWOACC): buffer 0 = cases, buffer 1 = controls, one tile in flight
+                const uint32_t buf = TWOACC ? 0u : (uint32_t)(tile_it & 1);
+                mbar_wait_wd(&tempty[buf], TWOACC ? (uint32_t)((tile_it & 1) ^ 1) : (uint32_t)(((tile_it >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + buf * ACC_COLS;
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
@@ -766,9 +773,13 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                     for (uint32_t k2 = 0; k2 < nk; ++k2) {
                         const uint32_t a_addr = base + st * STAGE_BYTES_MMA + k2 * KB_BYTES, b_addr = a_addr + A_STAGE_BYTES;
                         const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
+                        const uint32_t blk = kb + k2;                                      // 128-byte sample block of the row
+                        const bool ctrl = TWOACC && blk >= p.case_kb;
+                        const uint32_t d_blk = ctrl ? d_addr + ACC_COLS : d_addr;
+                        const uint32_t first_blk = ctrl ? p.case_kb : 0u;
 #pragma unroll
                         for (int k = 0; k < MMA_KB / UMMA_K; ++k)
-                            tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb | k2 | (uint32_t)k) != 0);
+                            tc_mma_i8(d_blk, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (blk != first_blk) || k != 0);
                     }
                     tc_commit_mc(&empty[st], 3);
                 }
@@ -791,7 +802,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
             cur.decode(p.TB, I2, J);
             { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
             if (!wanted(I2, J)) continue;
-            const uint32_t buf = (uint32_t)(tile_it & 1);
+            const uint32_t buf = TWOACC ? 0u : (uint32_t)(tile_it & 1);
             const uint64_t gi = (uint64_t)I2 * M4_BLK + rank * M4_A_SNPS + a_loc;
             // this warp's 16 column-role records (PairSide, 128 bytes each): 2 KiB contiguous -> its shared-memory slot
             unsigned char *my_col = col_sm + ew * COL_STAGE_BYTES;
@@ -803,12 +814,29 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                 __syncwarp();
             }
             const PairSide &A = p.side[gi < p.M ? gi : 0];   // read through L1: 8 records per warp, reused for 16 B-SNPs
-            if (lane == 0) mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
+            if (lane == 0) mbar_wait_wd(&tfull[buf], TWOACC ? (uint32_t)(tile_it & 1) : (uint32_t)((tile_it >> 1) & 1));
             __syncwarp();
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 uint32_t v[32];
+                uint32_t Dctl[2][4][3];                  // TWOACC: the control accumulator's products, exchanged first
+                if (TWOACC) {
+                    tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + ACC_COLS + 64 * g + 32 * h, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const uint32_t d = (pl - (uint32_t)r) & 3u;
+                        const unsigned src = qbase | ((pl + (uint32_t)r) & 3u);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const uint32_t mine = sel4(d, v[16 * e + 0 + c], v[16 * e + 4 + c], v[16 * e + 8 + c], v[16 * e + 12 + c]);
+                                Dctl[e][r][c] = __shfl_sync(0xffffffffu, mine, src);
+                            }
+                    }
+                }
                 tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 64 * g + 32 * h, v);
                 tc_wait_ld();
                 // columns 4s..4s+3 = planes (aa, bb, xx, pad) of B-SNP s of this load (s < 8). Lane o of the quad owns the
@@ -835,12 +863,16 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                     const uint64_t gj = (uint64_t)J * M4_BLK + b_loc;
                     if (!(gi < gj && gj < p.M)) continue;
                     // plane P of A is what arrived in rotation (P - o) & 3
-                    uint32_t prod[NC][NC];
+                    uint32_t prod[NC][NC], prod_ctl[3][3];
 #pragma unroll
                     for (int P = 0; P < NC; ++P) {
                         const uint32_t r = ((uint32_t)P - pl) & 3u;
 #pragma unroll
                         for (int c = 0; c < NC; ++c) prod[P][c] = sel4(r, D[e][0][c], D[e][1][c], D[e][2][c], D[e][3][c]);
+                        if (TWOACC && P < 3) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) prod_ctl[P][c] = sel4(r, Dctl[e][0][c], Dctl[e][1][c], Dctl[e][2][c], Dctl[e][3][c]);
+                        }
                     }
                     const PairSide &B = *reinterpret_cast<const PairSide *>(my_col + (8 * h + 4 * e + (int)pl) * 128);
                     uint32_t n[2][3][3];
@@ -860,7 +892,8 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
 #pragma unroll
                             for (int P = 0; P < 3; ++P)
 #pragma unroll
-                                for (int c = 0; c < 3; ++c) x[P][c] = k ? (prod[P][c] >> CTRL_SHIFT) : (prod[P][c] & 0x3fffu);
+                                for (int c = 0; c < 3; ++c)
+                                    x[P][c] = TWOACC ? (k ? prod_ctl[P][c] : prod[P][c]) : (k ? (prod[P][c] >> CTRL_SHIFT) : (prod[P][c] & 0x3fffu));
                             n[k][0][0] = x[0][0]; n[k][0][2] = x[0][1]; n[k][2][0] = x[1][0]; n[k][2][2] = x[1][1];
                             n[k][0][1] = ca[0] - x[0][0] - x[0][1] - x[0][2];
                             n[k][2][1] = ca[2] - x[1][0] - x[1][1] - x[1][2];
@@ -893,7 +926,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
 
 // operand rows of the four-plane engine: one thread per (SNP, 32-sample word), 32 bytes of each of aa, bb, xx
 // (the padding row 4s+3 stays zero from the memset)
-template <bool SPLIT>
+template <int MODE>
 __global__ void expand_mma4_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Kc, uint32_t Kt,
                                    uint32_t n_case, uint32_t n_ctrl, uint32_t case_bytes, uint32_t kbytes, uint64_t M,
                                    int8_t *__restrict__ mm) {
@@ -908,7 +941,8 @@ __global__ void expand_mma4_kernel(const uint32_t *__restrict__ sel, uint32_t se
     else { p1 = row[sel_word(2 * Wc, 0, k - Kc)]; p2 = row[sel_word(2 * Wc, 1, k - Kc)]; off = case_bytes + 32 * (k - Kc); shift = 7; left = n_ctrl - 32 * (k - Kc); }
     const uint32_t members = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);     // class members among the word's 32 positions
     const uint32_t bb = p1 & p2, aa = p1 ^ bb, xx = ~(p1 | p2) & members;
-    if (SPLIT) shift = 0;                                    // every byte +1: the classes are told apart by the plane
+    constexpr bool SPLIT = MODE == 1;
+    if (MODE != 0) shift = 0;                                // every byte +1: the classes are told apart by the plane / the accumulator
 #pragma unroll
     for (int pl = 0; pl < (SPLIT ? 2 : 3); ++pl) {
         const uint32_t x = pl == 0 ? aa : (pl == 1 ? bb : xx);
@@ -1216,8 +1250,8 @@ static uint64_t m4_schedule_tiles(uint32_t TB) {
     return tiles;
 }
 
-static int ensure_mma4_inputs(gwasdev_store *s, bool split) {
-    if (s->mm4_built && s->mm4_split == split) return GWASDEV_OK;
+static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
+    if (s->mm4_built && s->mm4_mode == mode) return GWASDEV_OK;
     const uint32_t TB = m4_blocks(s);
     const uint32_t case_bytes = round_up(s->n_case, MMA_KB), ctrl_bytes = round_up(s->n_ctrl, MMA_KB);
     s->mm_kbytes = case_bytes + ctrl_bytes;                 // the same row geometry as the two-plane matrix
@@ -1227,10 +1261,10 @@ static int ensure_mma4_inputs(gwasdev_store *s, bool split) {
     GW_CUDA(cudaMemsetAsync(s->d_mm4, 0, bytes, s->stream));
     const uint32_t K = s->Kc + s->Kt;
     const uint64_t work = s->M * K;
-    if (split) expand_mma4_kernel<true><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, s->n_case,
-                                                                                          s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4);
-    else expand_mma4_kernel<false><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, s->n_case,
-                                                                                     s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4);
+#define EXPAND4(MODE_) expand_mma4_kernel<MODE_><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, \
+                                                            s->n_case, s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4)
+    if (mode == 1) EXPAND4(1); else if (mode == 2) EXPAND4(2); else EXPAND4(0);
+#undef EXPAND4
     GW_LAUNCHED();
     if (!s->tmap_mm4 && posix_memalign(&s->tmap_mm4, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm4 = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
     encode_tiled_fn encode = nullptr;
@@ -1244,12 +1278,13 @@ static int ensure_mma4_inputs(gwasdev_store *s, bool split) {
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (four-plane operand matrix) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
     s->mm4_tiles = m4_schedule_tiles(TB);
     s->mm4_built = true;
-    s->mm4_split = split;
+    s->mm4_mode = mode;
     return GWASDEV_OK;
 }
 
 // pairs (i < j < M) and tiles of the shard among the tiles with missing calls, in the four-plane schedule
-uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags, bool split, uint64_t *tiles_out) {
+// mode 0: tiles with missing calls; 1: tiles without; 2: all tiles
+uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags, int mode, uint64_t *tiles_out) {
     const uint32_t TB = m4_blocks(s), n_bands = (TB + BAND - 1) / BAND;
     const uint64_t M = s->M;
     uint64_t pairs = 0, tiles = 0, t = 0;
@@ -1259,7 +1294,7 @@ uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uin
             const uint32_t h = column_height(na, J - BAND * b);
             for (uint32_t ii = 0; ii < h; ++ii, ++t) {
                 const uint32_t I2 = BAND * b + ii;
-                if (!tile_in_shard(t, shard, n_shards) || ((flags[I2] | flags[J]) != 0) == split) continue;   // split mode: the clean tiles
+                if (!tile_in_shard(t, shard, n_shards) || (mode != 2 && ((flags[I2] | flags[J]) != 0) == (mode == 1))) continue;
                 ++tiles;
                 if (I2 < J && (uint64_t)(J + 1) * M4_BLK <= M) pairs += (uint64_t)M4_BLK * M4_BLK;     // full off-diagonal block
                 else pairs += rect_pairs(M, (uint64_t)I2 * M4_BLK, (uint64_t)(I2 + 1) * M4_BLK, (uint64_t)J * M4_BLK, (uint64_t)(J + 1) * M4_BLK);
@@ -1271,12 +1306,13 @@ uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uin
 }
 
 // Launches the four-plane tensor-core screen over this shard's tiles with missing calls. thr carries the fp32 margin.
-int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, bool split, void *cand,
+int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, int mode, void *cand,
                                  unsigned long long *n_cand, uint64_t cap) {
-    int rc = ensure_mma4_inputs(s, split);
+    int rc = ensure_mma4_inputs(s, mode);
     if (rc != GWASDEV_OK) return rc;
     Mma4Params p;
     p.TB = m4_blocks(s); p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M; p.n_tiles = s->mm4_tiles;
+    p.case_kb = round_up(s->n_case, MMA_KB) / MMA_KB;
     p.shard = shard; p.n_shards = n_shards; p.side = s->d_side; p.tile_missing = s->d_tile_missing;
     const uint32_t n_ind = s->n_case + s->n_ctrl;
     p.thr = thr; p.N = (float)n_ind; p.lnN = (float)std::log((double)n_ind);
@@ -1287,13 +1323,13 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, ui
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const size_t smem = mma_smem_bytes();
     const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));
-    if (split) {
-        GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pair_screen_mma4_kernel<true><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);
-    } else {
-        GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        pair_screen_mma4_kernel<false><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);
-    }
+#define SCREEN4(MODE_)                                                                                                         \
+    do {                                                                                                                       \
+        GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        pair_screen_mma4_kernel<MODE_><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);      \
+    } while (0)
+    if (mode == 1) SCREEN4(1); else if (mode == 2) SCREEN4(2); else SCREEN4(0);
+#undef SCREEN4
     GW_LAUNCHED();
     return GWASDEV_OK;
 }

@@ -131,12 +131,14 @@ def test_four_plane_engine_on_a_cohort_where_every_block_has_missing_calls(orc):
         assert len(l4) > 100 * len(h4) and np.array_equal(l1, l4)
 
 
-@pytest.mark.parametrize("M,N,ncase,popc_ok", [(200, 40_000, 20_000, True), (130, 150_000, 70_000, False)])
-def test_split_class_planes_for_cohorts_beyond_the_packed_accumulator(orc, M, N, ncase, popc_ok):
-    """n_case >= 16384: the two-plane kernel's int32 accumulator (n_case + 2^14 n_ctrl) no longer fits; the four-plane kernel
-    with one pair of planes per class counts both classes as full int32 products. Records must equal the AND+POPC engine's
-    (while that one still applies: classes below 65536) and the oracle's hit set."""
-    codes, pheno = planted_cohort(orc, 91, M, N, ncase, 0.0, 5)
+@pytest.mark.parametrize("M,N,ncase,miss,popc_ok", [(200, 40_000, 20_000, 0.0, True), (130, 150_000, 70_000, 0.0, False),
+                                                     (200, 40_000, 20_000, 0.01, True), (130, 150_000, 70_000, 0.005, False)])
+def test_split_class_planes_for_cohorts_beyond_the_packed_accumulator(orc, M, N, ncase, miss, popc_ok):
+    """n_case >= 16384: the two-plane kernel's int32 accumulator (n_case + 2^14 n_ctrl) no longer fits. Complete cohorts: the
+    four-plane kernel with one pair of planes per class counts both classes as full int32 products. Cohorts with missing
+    calls: planes aa, bb, xx with cases and controls accumulated into separate TMEM accumulators. Records must equal the
+    AND+POPC engine's (while that one still applies: classes below 65536) and the oracle's hit set."""
+    codes, pheno = planted_cohort(orc, 91, M, N, ncase, miss, 5)
     with make_store(orc, codes, pheno) as st:
         h, s = st.pairwise_scan(30.0)
         assert s.engine == 2 and s.pairs_tested == M * (M - 1) // 2
