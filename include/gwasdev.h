@@ -220,8 +220,9 @@ GWASDEV_API int gwasdev_pairwise_scan(gwasdev_store *s, double threshold, uint32
  * one-hot bytes, pairwise_mma.cu) when n_case < 16384 and n_ctrl < 131072, else AND+POPC tiles; 1: AND+POPC
  * tiles; 2: tensor cores or GWASDEV_EINVAL. Tile pairs with missing calls (the reference's other branch,
  * compressed_genotype_table5.cpp:1000-1067) take the four-plane tensor-core kernel under the same conditions and the
- * 9-cell AND+POPC kernel otherwise. Cohorts with larger classes (below 2^23 samples each) run their complete tile
- * pairs on the four-plane kernel with one pair of planes per class. Results are identical. */
+ * 9-cell AND+POPC kernel otherwise. Cohorts with larger classes (below 2^23 samples each) run on the four-plane kernel
+ * with one pair of planes per class (no missing calls) or one accumulator per class (missing calls). Results are
+ * identical. */
 GWASDEV_API int gwasdev_set_pair_engine(gwasdev_store *s, int engine);
 /* Parity probe of the tensor-core engine: raw corner counts of one tile pair of its schedule (A-block I of 64
  * SNPs, B-block J of 128 SNPs, I/2 <= J): out[(a*128 + b)*8 + {0,1,2,3}] = cases AA_BB, AA_bb, aa_BB, aa_bb
