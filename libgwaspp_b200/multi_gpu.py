@@ -89,6 +89,29 @@ def gather_records(mine, world: int, group=None):
     return out
 
 
+def snp_range(n_snps: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous SNP range of `rank` for the marginal scan: balanced to one SNP, in rank order, so that the
+    concatenation of the ranks' outputs is the whole-table output."""
+    return n_snps * rank // world, n_snps * (rank + 1) // world
+
+
+def marginal_scan_distributed(store, group=None, gather: bool = False, **kw):
+    """This rank's SNP range of the marginal scan on a store that holds the whole table (replicated, as for the pairwise
+    screen). Outputs stay sharded -- no data-path collective -- unless gather=True, in which case every rank receives the
+    whole-table arrays (one all_gather_object of the numpy outputs: 96 to 288 bytes per SNP)."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    b, e = snp_range(store.n_snps, rank, world)
+    out = store.marginal_scan(b, e, **kw)
+    if not gather or world == 1:
+        return (b, e), out
+    parts = [None] * world
+    dist.all_gather_object(parts, out, group=group)
+    return (0, store.n_snps), {k: np.concatenate([p[k] for p in parts]) for k in out}
+
+
 def shard_tiles(n_snps: int, shard: int, n_shards: int, tile: int = 64):
     """Tile pairs (I <= J) handled by `shard`: linear upper-triangular index t with t % n_shards == shard --
     the same enumeration the screen kernel uses. Returns (list of (I, J), pairs covered)."""

@@ -87,3 +87,49 @@ def test_merge_rejects_duplicates_and_orders_top_k():
     with pytest.raises(ValueError):
         mg.merge_hits([a, a])
     assert len(mg.merge_hits([])) == 0
+
+
+class _FakeStore:
+    """Stands in for GenoStore on the CPU: marginal_scan(b, e) returns recognisable per-SNP rows."""
+    def __init__(self, n_snps):
+        self.n_snps = n_snps
+
+    def marginal_scan(self, b, e, **kw):
+        idx = np.arange(b, e, dtype=np.uint32)
+        return {"counts": np.stack([idx * 8 + k for k in range(8)], 1), "stats": idx.astype(np.float64) * 0.5}
+
+
+def _marginal_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    (b, e), part = mg.marginal_scan_distributed(_FakeStore(1003))
+    (b2, e2), whole = mg.marginal_scan_distributed(_FakeStore(1003), gather=True)
+    q.put((rank, (b, e, len(part["counts"]), b2, e2, whole["counts"].tobytes(), whole["stats"].tobytes())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_marginal_scan_ranges_and_gather(world):
+    """Marginal scan over ranks: contiguous balanced SNP ranges, outputs sharded by default, whole table after a gather."""
+    for n in (1, 7, 1003, 500_000):
+        r = [mg.snp_range(n, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+        assert max(e - b for b, e in r) - min(e - b for b, e in r) <= 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_marginal_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _FakeStore(1003).marginal_scan(0, 1003)
+    for r in range(world):
+        b, e, n_part, b2, e2, counts, stats = got[r]
+        assert (b, e) == mg.snp_range(1003, r, world) and n_part == e - b and (b2, e2) == (0, 1003)
+        assert counts == want["counts"].tobytes() and stats == want["stats"].tobytes()
