@@ -694,18 +694,18 @@ int gwasdev_load_bed(gwasdev_store *s, const char *bed_path, const uint8_t *alle
     if (rc != GWASDEV_OK) return rc;
     GW_REQUIRE(first_row + rows <= s->M, "gwasdev_load_bed: %llu rows do not fit the table of %llu from row %llu", (unsigned long long)rows,
                (unsigned long long)s->M, (unsigned long long)first_row);
-    FILE *f = fopen(bed_path, "rb");
-    GW_REQUIRE(f != nullptr, "gwasdev_load_bed: cannot open %s", bed_path);
-    fseek(f, 3, SEEK_SET);
-    const uint64_t bps = (s->N + 3) / 4, chunk = std::max<uint64_t>(1, (64ull << 20) / bps);
-    std::vector<uint8_t> buf(std::min(chunk, std::max<uint64_t>(rows, 1)) * bps);
-    for (uint64_t r = 0; r < rows; r += chunk) {
-        const uint64_t n = std::min(chunk, rows - r);
-        if (fread(buf.data(), bps, n, f) != n) { fclose(f); set_error("gwasdev_load_bed: short read in %s", bed_path); return GWASDEV_EINVAL; }
-        rc = gwasdev_put_bed(s, first_row + r, n, buf.data(), alleles ? alleles + 2 * r : nullptr);
-        if (rc != GWASDEV_OK) { fclose(f); return rc; }
+    // the file is mapped and its rows go to the device in 64 MB pieces as pageable memory (staged by the driver)
+    const int fd = ::open(bed_path, O_RDONLY);
+    GW_REQUIRE(fd >= 0, "gwasdev_load_bed: cannot open %s", bed_path);
+    const uint64_t bps = (s->N + 3) / 4, size = 3 + rows * bps;
+    const uint8_t *map = rows ? (const uint8_t *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE | (size <= (1ull << 30) ? MAP_POPULATE : 0), fd, 0) : nullptr;
+    ::close(fd);
+    GW_REQUIRE(rows == 0 || map != MAP_FAILED, "gwasdev_load_bed: cannot map %s", bed_path);
+    if (rows) {
+        rc = gwasdev_put_bed(s, first_row, rows, map + 3, alleles);
+        munmap((void *)map, size);
+        if (rc != GWASDEV_OK) return rc;
     }
-    fclose(f);
     if (rows_done) *rows_done = rows;
     return GWASDEV_OK;
 }
