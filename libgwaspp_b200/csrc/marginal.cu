@@ -523,7 +523,8 @@ int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
         for (cudaEvent_t &e : s->ev_piece) GW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     const uint64_t out_bytes = n * ((counts ? 32 : 0) + (stats ? sizeof(gwasdev_snp_stats) : 0) + (mi ? sizeof(gwasdev_marginal_information) : 0));
-    const int pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(gwasdev_store::MAX_PIECES, out_bytes / (4ull << 20)));
+    int pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(gwasdev_store::MAX_PIECES, out_bytes / (12ull << 20)));   // ~12 MB per piece (tools/sweep_pieces.py)
+    if (const char *e = getenv("GWASDEV_SCAN_PIECES")) pieces = std::max(1, std::min((int)gwasdev_store::MAX_PIECES, atoi(e)));
     cudaError_t e = cudaSuccess;
     for (int p = 0; p < pieces && e == cudaSuccess; ++p) {
         const uint64_t b = snp_begin + n * p / pieces, en = snp_begin + n * (p + 1) / pieces, o = b - snp_begin, k = en - b;
