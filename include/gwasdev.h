@@ -53,6 +53,21 @@ typedef struct {
     double chi2_allelic, p_allelic, chi2_genotypic, p_genotypic;
 } gwasdev_snp_stats;
 
+/* Compact per-SNP result for host consumers (32 bytes instead of the 96 of counts + gwasdev_snp_stats): the eight genotype
+ * counts as 16-bit integers (both classes below 65 536 samples) and the four test results in fp32 (north star: fp32
+ * p-values, 1e-5 relative on significant hits). p-values below the fp32 range flush towards 0; such SNPs are in the
+ * significant list of gwasdev_marginal_scan_compact with all their statistics in fp64. */
+typedef struct {
+    uint16_t cases[4], controls[4];   /* {aa, ab, bb, xx} per class */
+    float chi2_allelic, p_allelic, chi2_genotypic, p_genotypic;
+} gwasdev_snp_compact;
+
+/* One SNP whose allelic or genotypic p-value is below the caller's threshold (48 bytes). */
+typedef struct {
+    uint32_t snp, df_genotypic;
+    double maf_pooled, chi2_allelic, p_allelic, chi2_genotypic, p_genotypic;
+} gwasdev_sig_snp;
+
 /* One screened SNP pair: SNPInteractionPair of algorithms/epistasis_func.h:59-60. */
 typedef struct {
     uint32_t i, j;   /* i < j, table row indices */
@@ -83,6 +98,21 @@ GWASDEV_API int gwasdev_set_stream(gwasdev_store *s, void *cuda_stream);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 GWASDEV_API uint64_t gwasdev_launch_count(void);
 GWASDEV_API int gwasdev_synchronize(gwasdev_store *s);
+
+/* Explicit knobs of a store. The library reads no environment variables: everything that changes which kernel runs is
+ * set here, per store, and defaults (0) are the measured best. Used by the tests to force the alternative code paths
+ * on small fixtures and by the timing scripts under tools/. */
+#define GWASDEV_OPT_SELECT_KERNEL 0  /* K0: 0 auto (register form up to 32 768 samples), 1 table-driven form */
+#define GWASDEV_OPT_LANES_PER_ROW 1  /* K1 / K1': 0 auto, or 8 / 16 / 32 lanes cooperating on one row */
+#define GWASDEV_OPT_INGEST_CHUNK 2   /* file loaders: bytes of text per device chunk (0: 32 MiB mapped / 4 MiB .gz) */
+#define GWASDEV_OPT_SCAN_PIECES 3    /* host-output scans: pieces whose D2H copies overlap the next piece (0 auto, 1..8) */
+#define GWASDEV_OPT_MASKED_SCAN 4    /* 0 auto (first scan after a selection counts through the masks); 1 always compact first */
+#define GWASDEV_OPT_TRACE 5          /* 1: phase timings of the pairwise scan / compaction / G-test on stderr */
+#define GWASDEV_OPT_FOUR_PLANE 6     /* 0 auto; 1: tiles with missing calls stay on the 9-cell AND+POPC kernel */
+#define GWASDEV_OPT_ROW_TOTALS 7     /* K1': 0 auto (row totals cached per table when the classes partition the cohort); 1 never */
+#define GWASDEV_OPT_CAND_CAPACITY 8  /* pairwise screen: candidate buffer entries (0 auto); small values exercise the overflow paths */
+#define GWASDEV_OPT_COUNT 16
+GWASDEV_API int gwasdev_set_option(gwasdev_store *s, int option, long long value);
 
 /* ---- geometry ------------------------------------------------------------------------------- */
 /* 16-bit blocks per bit-plane for n samples: pad4(n/16 + 1) (compressed_genotype_table5.cpp:55-64). */
@@ -154,12 +184,17 @@ GWASDEV_API int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, ui
  * SNP-tiled pairwise store) on the device; the raw store stays resident, so this can be called
  * again with other masks. */
 GWASDEV_API int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask);
-/* Compaction is lazy by default: the call above uploads the masks and the compaction tables, and the compacted rows
- * are built (kernel K0) when something first needs them -- the pairwise screen, the layout probes, or a second
- * marginal scan; a single marginal scan after a selection counts through the masks on the raw rows instead, which
- * is the reference's mask-on-the-fly overload (:609-657) and gives identical counts. eager != 0 runs K0 inside
- * gwasdev_select_case_control. */
+/* Compaction is lazy by default: the call above uploads the masks, and the compacted rows are built (kernel K0) when
+ * something first needs them -- the layout probes, the AND+POPC engine, the per-pair probes, or the second marginal scan of a
+ * cohort with samples outside both classes; marginal scans after a selection count through the masks on the raw rows
+ * instead, which is the reference's mask-on-the-fly overload (:609-657) and gives identical counts. eager != 0 runs K0
+ * inside gwasdev_select_case_control. */
 GWASDEV_API int gwasdev_set_select_mode(gwasdev_store *s, int eager);
+/* Stream masks for the mask-on-the-fly overloads only -- getCaseControlGenotypeDistribution(r, ccs, ccgd) (:609-657,
+ * gwasdev_counts mode 1) and getCaseControlContingencyTable(i, j, ccs, ccct) (:806-895, gwasdev_pair_tables mode 1). As in
+ * the reference, they do not touch the pre-selected store: selection, compacted rows, margins and pairwise layouts stay
+ * valid. gwasdev_select_case_control sets them too (to its own masks). */
+GWASDEV_API int gwasdev_set_stream_masks(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask);
 GWASDEV_API int gwasdev_case_control_counts(gwasdev_store *s, uint32_t *n_case, uint32_t *n_ctrl);
 /* Compacted rows in the reference's layout [case p1: Pca][case p2: Pca][ctrl p1: Pco][ctrl p2: Pco]
  * (16-bit blocks, Pca = gwasdev_plane_blocks(n_case)) -- layout-parity probe. */
@@ -174,6 +209,13 @@ GWASDEV_API int gwasdev_get_selected_rows(gwasdev_store *s, uint64_t first_row, 
  * on_device = 0: outputs are host buffers (copied back inside the call); 1: device buffers. */
 GWASDEV_API int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *counts,
                           gwasdev_marginal_information *mi, gwasdev_snp_stats *stats, int on_device);
+/* The same scan with compact outputs, for callers on the far side of PCIe (select_cc_maf needs the two frequency tables
+ * per SNP, algorithms/maf_func.cpp:256-267; a chi-square scan needs four numbers): `out` (may be NULL) receives one 32-byte
+ * record per SNP; SNPs with min(p_allelic, p_genotypic) < p_threshold are also appended to sig[0..*n_sig) in fp64, sorted
+ * by SNP index (sig may be NULL when p_threshold <= 0; more than sig_capacity significant SNPs -> GWASDEV_EOVERFLOW with
+ * *n_sig = the number found). Needs both classes below 65 536 samples when out != NULL. Host or device buffers as above. */
+GWASDEV_API int gwasdev_marginal_scan_compact(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, gwasdev_snp_compact *out,
+                                  double p_threshold, gwasdev_sig_snp *sig, uint64_t sig_capacity, uint64_t *n_sig, int on_device);
 /* Streaming in sample blocks (BASELINE configs[4]): genotype counts are additive over disjoint sample blocks, which the
  * reference cannot exploit (its rows are always whole: compressed_genotype_table5.cpp:703-747 walks one compacted row).
  * A store holding one block of samples (loaded with label state carried over, or gwasdev_simulate_block) adds its

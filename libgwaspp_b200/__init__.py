@@ -17,7 +17,8 @@ import numpy as np
 from .maf_spectrum import MAF_SPECTRUM, PANELS  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgwasdev.so")
+# GWASDEV_LIB selects another build of the same library (the -DGWASDEV_SWEEP build the tuning scripts under tools/ use)
+LIB_PATH = os.environ.get("GWASDEV_LIB") or os.path.join(HERE, "libgwasdev.so")
 
 # genetics/genotype/common_genotype.h:101-106 of the reference (192 bytes)
 MI_DTYPE = np.dtype([("margins", "<u4", 4), ("cases", "<u4", 4), ("controls", "<u4", 4),
@@ -25,7 +26,16 @@ MI_DTYPE = np.dtype([("margins", "<u4", 4), ("cases", "<u4", 4), ("controls", "<
 STATS_DTYPE = np.dtype([("maf_ref_case", "<f8"), ("maf_ref_ctrl", "<f8"), ("maf_pooled", "<f8"), ("df_genotypic", "<f8"),
                         ("chi2_allelic", "<f8"), ("p_allelic", "<f8"), ("chi2_genotypic", "<f8"), ("p_genotypic", "<f8")])
 HIT_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("stat", "<f8")])
+COMPACT_DTYPE = np.dtype([("cases", "<u2", 4), ("controls", "<u2", 4), ("chi2_allelic", "<f4"), ("p_allelic", "<f4"),
+                          ("chi2_genotypic", "<f4"), ("p_genotypic", "<f4")])
+SIG_DTYPE = np.dtype([("snp", "<u4"), ("df_genotypic", "<u4"), ("maf_pooled", "<f8"), ("chi2_allelic", "<f8"), ("p_allelic", "<f8"),
+                      ("chi2_genotypic", "<f8"), ("p_genotypic", "<f8")])
 assert MI_DTYPE.itemsize == 192 and STATS_DTYPE.itemsize == 64 and HIT_DTYPE.itemsize == 16
+assert COMPACT_DTYPE.itemsize == 32 and SIG_DTYPE.itemsize == 48
+
+# gwasdev_set_option keys (include/gwasdev.h)
+OPT_SELECT_KERNEL, OPT_LANES_PER_ROW, OPT_INGEST_CHUNK, OPT_SCAN_PIECES, OPT_MASKED_SCAN, OPT_TRACE, OPT_FOUR_PLANE, \
+    OPT_ROW_TOTALS, OPT_CAND_CAPACITY = range(9)
 
 
 class PairStats(C.Structure):
@@ -52,6 +62,7 @@ ABI_SYMBOLS = [
     "gwasdev_ksa_screen_mma_f32", "gwasdev_pack_row_text_block", "gwasdev_simulate_block", "gwasdev_marginal_accumulate",
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
     "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs", "gwasdev_create_from_tped",
+    "gwasdev_set_option", "gwasdev_set_stream_masks", "gwasdev_marginal_scan_compact",
 ]
 
 
@@ -76,6 +87,9 @@ def load_library():
     L.gwasdev_destroy.restype = None
     L.gwasdev_set_stream.argtypes = [vp, vp]
     L.gwasdev_synchronize.argtypes = [vp]
+    L.gwasdev_set_option.argtypes = [vp, i32, C.c_longlong]
+    L.gwasdev_set_stream_masks.argtypes = [vp, vp, vp]
+    L.gwasdev_marginal_scan_compact.argtypes = [vp, u64, u64, vp, C.c_double, vp, u64, C.POINTER(u64), i32]
     L.gwasdev_pack_row_text.argtypes = [C.c_char_p, C.c_size_t, u32, vp]
     L.gwasdev_put_rows.argtypes = [vp, u64, u64, vp]
     L.gwasdev_get_rows.argtypes = [vp, u64, u64, vp]
@@ -268,6 +282,10 @@ class GenoStore:
     def synchronize(self):
         _check(self.L.gwasdev_synchronize(self.h), "gwasdev_synchronize")
 
+    def set_option(self, option: int, value: int):
+        """Explicit knob of this store (OPT_* constants; include/gwasdev.h). The library reads no environment variables."""
+        _check(self.L.gwasdev_set_option(self.h, option, value), "gwasdev_set_option")
+
     def put_rows(self, rows: np.ndarray, first_row: int = 0):
         rows = np.ascontiguousarray(rows, np.uint16)
         assert rows.ndim == 2 and rows.shape[1] == 2 * self.P + 1, rows.shape
@@ -341,6 +359,15 @@ class GenoStore:
         _check(self.L.gwasdev_case_control_counts(self.h, C.byref(a), C.byref(b)), "gwasdev_case_control_counts")
         self.n_case, self.n_ctrl = a.value, b.value
 
+    def set_stream_masks(self, pheno=None, *, case_mask=None, ctrl_mask=None):
+        """Masks of the mask-on-the-fly overloads only (counts mode 1, pair_tables mode 1); the selection stays as it is."""
+        if pheno is not None:
+            case_mask, ctrl_mask = stream_masks(pheno)
+        case_mask = np.ascontiguousarray(case_mask, np.uint16)
+        ctrl_mask = np.ascontiguousarray(ctrl_mask, np.uint16)
+        assert len(case_mask) == self.P and len(ctrl_mask) == self.P
+        _check(self.L.gwasdev_set_stream_masks(self.h, _ptr(case_mask), _ptr(ctrl_mask)), "gwasdev_set_stream_masks")
+
     def get_selected_rows(self, first_row: int = 0, n_rows: int | None = None) -> np.ndarray:
         n_rows = self.n_snps - first_row if n_rows is None else n_rows
         S = 2 * (plane_blocks(self.n_case) + plane_blocks(self.n_ctrl))
@@ -368,6 +395,28 @@ class GenoStore:
         """Raw-pointer call: buffers are torch tensors / numpy arrays / int addresses (device when on_device)."""
         _check(self.L.gwasdev_marginal_scan(self.h, snp_begin, snp_end, _ptr(counts), _ptr(mi), _ptr(stats),
                                             1 if on_device else 0), "gwasdev_marginal_scan")
+
+    def marginal_scan_compact(self, snp_begin: int = 0, snp_end: int | None = None, *, records=True, p_threshold: float = 0.0,
+                              sig_capacity: int = 1 << 16):
+        """Host-buffer call with compact outputs: (records[COMPACT_DTYPE] or None, significant[SIG_DTYPE] sorted by SNP)."""
+        snp_end = self.n_snps if snp_end is None else snp_end
+        n = snp_end - snp_begin
+        rec = np.zeros(n, COMPACT_DTYPE) if records else None
+        sig = np.zeros(sig_capacity, SIG_DTYPE) if p_threshold > 0 else None
+        n_sig = C.c_uint64()
+        rc = self.L.gwasdev_marginal_scan_compact(self.h, snp_begin, snp_end, _ptr(rec), p_threshold, _ptr(sig), sig_capacity if sig is not None else 0,
+                                                  C.byref(n_sig), 0)
+        if rc == 4:   # GWASDEV_EOVERFLOW: grow and retry once
+            return self.marginal_scan_compact(snp_begin, snp_end, records=records, p_threshold=p_threshold, sig_capacity=int(n_sig.value))
+        _check(rc, "gwasdev_marginal_scan_compact")
+        return rec, (sig[: n_sig.value].copy() if sig is not None else None)
+
+    def marginal_scan_compact_into(self, snp_begin, snp_end, records=None, p_threshold=0.0, sig=None, sig_capacity=0, on_device=True) -> int:
+        """Raw-pointer call of gwasdev_marginal_scan_compact; returns the number of significant SNPs."""
+        n_sig = C.c_uint64()
+        _check(self.L.gwasdev_marginal_scan_compact(self.h, snp_begin, snp_end, _ptr(records), p_threshold, _ptr(sig), sig_capacity, C.byref(n_sig),
+                                                    1 if on_device else 0), "gwasdev_marginal_scan_compact")
+        return int(n_sig.value)
 
     def marginal_accumulate(self, acc, snp_begin: int = 0, snp_end: int | None = None, on_device: bool = False):
         """acc[8 per SNP] += this sample block's case/control genotype counts (streaming in sample blocks)."""

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgwasdev.so")
+SWEEP_LIB = os.path.join(HERE, "libgwasdev_sweep.so")
 HOST_LIB = os.path.join(HERE, "libgwaspp_host.so")
 HOST_CLI = os.path.join(HERE, "gwas_b200")
 SOURCES = ["store.cu", "ingest.cu", "marginal.cu", "pairwise.cu", "pairwise_mma.cu"]
@@ -36,15 +37,26 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, sweep: bool = False) -> str:
+    """sweep=True builds libgwasdev_sweep.so instead: the same sources with -DGWASDEV_SWEEP, i.e. with the extra kernel
+    configurations, the GWASDEV_*_CFG environment parsing and the role timers that the tuning scripts under tools/ use
+    (load it with GWASDEV_LIB=<path>). The product library has none of them."""
+    if sweep:
+        return _build_lib(SWEEP_LIB, ["-DGWASDEV_SWEEP"], "build_sweep", verbose)
     if not force and not needs_build():
         return LIB
+    _build_lib(LIB, [], "build", verbose)
+    build_host()
+    return LIB
+
+
+def _build_lib(lib: str, extra: list, objdir: str, verbose: bool) -> str:
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, objdir), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", "g++", "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(HERE, objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc(), *NVCC_FLAGS, *extra, "-ccbin", "g++", "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -55,10 +67,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if pr.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc(), "-shared", "-ccbin", "g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lz"]
+    link = [nvcc(), "-shared", "-ccbin", "g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lz", "-ldl"]
     subprocess.check_call(link)
-    build_host()
-    return LIB
+    return lib
 
 
 def build_host() -> str:
@@ -75,4 +86,4 @@ def build_host() -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, sweep="--sweep" in sys.argv))

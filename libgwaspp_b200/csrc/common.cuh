@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -12,7 +13,7 @@ namespace gwasdev {
 
 // ---- error plumbing ------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
-extern unsigned long long g_launches;   // kernels launched by this library (gwasdev_launch_count)
+extern std::atomic<unsigned long long> g_launches;   // kernels launched by this library (gwasdev_launch_count); stores may be driven from several host threads
 
 #define GW_CUDA(call)                                                                              \
     do {                                                                                           \
@@ -136,11 +137,20 @@ struct gwasdev_store {
     uint32_t Pca = 0, Pco = 0;    // reference geometry of the compacted streams (16-bit blocks)
     uint32_t Wc = 0, Wt = 0;      // words per plane per class in the scan layout (multiples of 4)
     uint32_t Kc = 0, Kt = 0;      // tight word counts ceil(n/32) (pairwise layout)
-    uint32_t *d_case_mask = nullptr, *d_ctrl_mask = nullptr;   // [Wr] stream masks as given (a sample may be in both)
-    uint32_t *d_ctrl_sel_mask = nullptr;                       // [Wr] controls of the compaction: ctrl & ~case
+    // class masks over the raw sample positions, [4][Wr] in one allocation (gwasdev_create):
+    uint32_t *d_masks = nullptr;
+    uint32_t *d_case_mask = nullptr, *d_ctrl_mask = nullptr;           // stream masks of the mask-on-the-fly overloads, as given (a sample may be in both)
+    uint32_t *d_case_sel_mask = nullptr, *d_ctrl_sel_mask = nullptr;   // classes of the selection: cases, controls-and-not-cases
+    bool fly_valid = false;                                            // on-the-fly masks uploaded (by a selection or gwasdev_set_stream_masks)
+    uint32_t n_fly_case = 0, n_fly_ctrl = 0;                           // members of the on-the-fly masks as given (reference: ccs.getCaseCount() / getControlCount())
+    std::vector<uint32_t> h_sel_masks;                                 // host copy of the selection masks [2][Wr]: K0's tables are built from it on demand
+    // per-SNP totals over ALL samples (|p1|, |p2|, |p1 & p2|, 0), independent of the phenotype: when the classes partition the
+    // cohort the control counts are totals - case counts, so a re-selection's scan needs three masked popcount streams only
+    uint4 *d_row_tot = nullptr;
+    bool tot_valid = false;
     uint32_t *d_case_idx = nullptr, *d_ctrl_idx = nullptr;     // sample index of the k-th case / control
     uint32_t *d_sel = nullptr;    // scan layout [M][cases: Wc/4 x (p1 chunk, p2 chunk)][controls: Wt/4 x (p1 chunk, p2 chunk)]
-    size_t cap_sel = 0, cap_case_idx = 0, cap_ctrl_idx = 0, cap_mask = 0;   // bytes allocated (grow-only)
+    size_t cap_sel = 0, cap_case_idx = 0, cap_ctrl_idx = 0;   // bytes allocated (grow-only)
 
     // pairwise layout: one-hot planes, word-major so that a 64-SNP tile row is 256 contiguous bytes
     bool pw_built = false;
@@ -194,6 +204,8 @@ struct gwasdev_store {
     unsigned long long *h_cnt = nullptr;                     // pinned host counters
     void *ingest = nullptr;                                  // file / text ingestion state (ingest.cu)
 
+    long long opt[GWASDEV_OPT_COUNT] = {};                   // gwasdev_set_option (explicit knobs; the library reads no environment variables)
+
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     static constexpr int MAX_PIECES = 8;                     // host-output scans: pieces whose copies overlap the next piece's scan
     cudaStream_t copy_stream = nullptr;
@@ -202,6 +214,7 @@ struct gwasdev_store {
 };
 
 void gwasdev_internal_free_ingest(gwasdev_store *s);
+void gwasdev_internal_rows_changed(gwasdev_store *s);      // raw rows were (re)written: everything derived from them is stale (store.cu)
 int gwasdev_internal_ensure_compacted(gwasdev_store *s);   // K0 on demand (store.cu)
 
 namespace gwasdev {

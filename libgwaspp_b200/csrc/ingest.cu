@@ -363,12 +363,10 @@ static int reserve_text(Ingest *g, size_t bytes, bool pinned) {
     return GWASDEV_OK;
 }
 
-static void invalidate(gwasdev_store *s) {
-    s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mm4_built = s->mma_side_valid = s->pc_valid = false;
-}
+static void invalidate(gwasdev_store *s) { gwasdev_internal_rows_changed(s); }
 
-static size_t chunk_bytes() {
-    if (const char *e = getenv("GWASDEV_INGEST_CHUNK")) { const long long v = atoll(e); if (v >= 64) return (size_t)v; }
+static size_t chunk_bytes(const gwasdev_store *s) {
+    if (s->opt[GWASDEV_OPT_INGEST_CHUNK] >= 64) return (size_t)s->opt[GWASDEV_OPT_INGEST_CHUNK];
     return 4ull << 20;   // pinning host memory costs ~1.5 ms per MB: small buffers, grown only for lines that do not fit
 }
 
@@ -485,7 +483,7 @@ int gwasdev_tped_dims(const char *path, uint64_t *n_rows, uint32_t *n_samples) {
 // the rest of an open text file (after `head`, bytes already read from it) into rows first_row.. of the store
 static int load_text_file(gwasdev_store *s, TextFile &f, const char *path, const char *head, size_t head_len, uint64_t first_row,
                           uint64_t *rows_done) {
-    size_t CH = std::max(chunk_bytes(), head_len + 1);
+    size_t CH = std::max(chunk_bytes(s), head_len + 1);
     Ingest *g = nullptr;
     int rc = ingest_get(s, &g);
     if (rc == GWASDEV_OK) rc = reserve_text(g, CH + 1, true);
@@ -549,7 +547,7 @@ static int load_mapped_file(gwasdev_store *s, int fd, size_t size, const char *p
     const char *map = (const char *)mmap(nullptr, size, PROT_READ, MAP_PRIVATE | (size <= (1ull << 30) ? MAP_POPULATE : 0), fd, 0);   // small files: no page fault per 4 KiB
     GW_REQUIRE(map != MAP_FAILED, "gwasdev_load_tped: cannot map %s", path);
     madvise((void *)map, size, MADV_SEQUENTIAL);
-    const size_t CH = getenv("GWASDEV_INGEST_CHUNK") ? chunk_bytes() : (32ull << 20);
+    const size_t CH = s->opt[GWASDEV_OPT_INGEST_CHUNK] ? chunk_bytes(s) : (32ull << 20);
     int b = 0;
     for (size_t off = 0; off < size && rc == GWASDEV_OK;) {
         size_t end = std::min(size, off + CH);

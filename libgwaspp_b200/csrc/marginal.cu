@@ -143,20 +143,53 @@ __device__ __noinline__ void fill_stats(const uint32_t ca[4], const uint32_t co[
     else { o.chi2_genotypic = x; o.p_genotypic = chisq_upper(x, df); }
 }
 
+// Where one scan writes. Every pointer may be NULL; outputs are indexed from out_base (the first SNP of the call).
+struct ScanOut {
+    uint32_t *counts;
+    gwasdev_marginal_information *mi;
+    gwasdev_snp_stats *stats;
+    gwasdev_snp_compact *compact;          // 32-byte records for host consumers
+    gwasdev_sig_snp *sig;                  // SNPs with min(p_allelic, p_genotypic) < p_thr, appended through n_sig
+    unsigned long long *n_sig;
+    uint64_t sig_cap;
+    double p_thr;
+    uint4 *row_tot;                        // K1': per-SNP totals over all samples, indexed by the absolute SNP (written or read)
+    uint64_t out_base;
+};
+
 // One SNP's epilogue, kept out of line so that the streaming loop stays small in the instruction cache.
 __device__ __noinline__ void finish_snp(uint32_t m1c, uint32_t m2c, uint32_t mbc, uint32_t m1t, uint32_t m2t, uint32_t mbt,
-                                        uint32_t n_case, uint32_t n_ctrl, uint64_t o, uint32_t *__restrict__ counts,
-                                        gwasdev_marginal_information *__restrict__ mi, gwasdev_snp_stats *__restrict__ stats) {
+                                        uint32_t n_case, uint32_t n_ctrl, uint64_t snp, const ScanOut &out) {
+    const uint64_t o = snp - out.out_base;
     uint32_t ca[4], co[4];
     ca[0] = m1c - mbc; ca[1] = m2c - mbc; ca[2] = mbc; ca[3] = n_case - ca[0] - ca[1] - ca[2];
     co[0] = m1t - mbt; co[1] = m2t - mbt; co[2] = mbt; co[3] = n_ctrl - co[0] - co[1] - co[2];
-    if (counts) {
-        uint4 *dst = reinterpret_cast<uint4 *>(counts + 8 * o);
+    if (out.counts) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out.counts + 8 * o);
         dst[0] = make_uint4(ca[0], ca[1], ca[2], ca[3]);
         dst[1] = make_uint4(co[0], co[1], co[2], co[3]);
     }
-    if (mi) fill_marginal_information(ca, co, n_case + n_ctrl, mi[o]);
-    if (stats) fill_stats(ca, co, stats[o]);
+    if (out.mi) fill_marginal_information(ca, co, n_case + n_ctrl, out.mi[o]);
+    if (out.stats || out.compact || out.sig) {
+        gwasdev_snp_stats st;
+        fill_stats(ca, co, st);
+        if (out.stats) out.stats[o] = st;
+        if (out.compact) {
+            uint4 *dst = reinterpret_cast<uint4 *>(out.compact + o);
+            dst[0] = make_uint4(ca[0] | (ca[1] << 16), ca[2] | (ca[3] << 16), co[0] | (co[1] << 16), co[2] | (co[3] << 16));
+            dst[1] = make_uint4(__float_as_uint((float)st.chi2_allelic), __float_as_uint((float)st.p_allelic),
+                                __float_as_uint((float)st.chi2_genotypic), __float_as_uint((float)st.p_genotypic));
+        }
+        if (out.sig && (st.p_allelic < out.p_thr || st.p_genotypic < out.p_thr)) {
+            const unsigned long long slot = atomicAdd(out.n_sig, 1ull);
+            if (slot < out.sig_cap) {
+                gwasdev_sig_snp g;
+                g.snp = (uint32_t)snp; g.df_genotypic = (uint32_t)st.df_genotypic; g.maf_pooled = st.maf_pooled;
+                g.chi2_allelic = st.chi2_allelic; g.p_allelic = st.p_allelic; g.chi2_genotypic = st.chi2_genotypic; g.p_genotypic = st.p_genotypic;
+                out.sig[slot] = g;
+            }
+        }
+    }
 }
 
 // SLOTS = chunk pairs a lane loads back to back (2*SLOTS 128-bit loads in flight per lane)
@@ -179,24 +212,34 @@ __device__ __forceinline__ void scan_class(const uint4 *__restrict__ base, uint3
     s1 = hs_total(h1); s2 = hs_total(h2); sb = plain_total(hb);
 }
 
-// grid: persistent, MINB CTAs of 256 threads per SM; each warp takes one contiguous, balanced range of rows.
-template <int G, int SLOTS, int MINB>
-__global__ void __launch_bounds__(256, MINB)
-marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
-                     uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end,
-                     uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
-                     gwasdev_snp_stats *__restrict__ stats, uint64_t out_base, int interleave) {
-    const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
-    const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
+// The batch loop both scan kernels share: full rounds of 32-row batches dealt round-robin over the warps (neighbouring
+// warps stream neighbouring rows), then the rows that do not fill a round split evenly, so that no warp runs a whole
+// batch longer than the rest.
+template <class Batch>
+__device__ __forceinline__ void for_each_batch(uint64_t snp_begin, uint64_t snp_end, Batch batch) {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_snps = snp_end - snp_begin;
+    const uint64_t rounds = n_snps / (n_warps * 32);
+    for (uint64_t r = 0; r < rounds; ++r) batch(snp_begin + (r * n_warps + warp) * 32, 32u);
+    const uint64_t rem_begin = snp_begin + rounds * n_warps * 32, rem = snp_end - rem_begin;
+    const uint64_t b0 = rem_begin + warp * rem / n_warps, b1 = rem_begin + (warp + 1) * rem / n_warps;
+    for (uint64_t base = b0; base < b1; base += 32) batch(base, (uint32_t)min((uint64_t)32, b1 - base));
+}
+
+// grid: persistent, MINB CTAs of 256 threads per SM.
+template <int G, int SLOTS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
+                     uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end, const ScanOut out) {
+    const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
+    const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     // One batch: up to 32 consecutive rows; in pass `it` the 32/G lane groups work on rows it*(32/G) .. +32/G-1 (so a short
     // batch needs proportionally fewer passes), lane `it` of group g keeps the totals of row it*(32/G) + g, and after the
     // passes every lane finishes one SNP.
     constexpr uint32_t NG = 32 / G;
     const uint32_t my_row = l * NG + g;
-    auto batch = [&](uint64_t base, uint32_t in_batch) {
+    for_each_batch(snp_begin, snp_end, [&](uint64_t base, uint32_t in_batch) {
         const uint32_t passes = (in_batch + NG - 1) / NG;
         uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;   // totals of row (base + my_row)
         for (uint32_t it = 0; it < passes; ++it) {
@@ -211,31 +254,16 @@ marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Q
             t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
             if (l == it) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
         }
-        if (my_row < in_batch)
-            finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + my_row - out_base, counts, mi, stats);
-    };
-    if (interleave) {
-        // full rounds of 32-row batches dealt round-robin over the warps (neighbouring warps stream neighbouring rows),
-        // then the rows that do not fill a round split evenly, so that no warp runs a whole batch longer than the rest
-        const uint64_t rounds = n_snps / (n_warps * 32);
-        for (uint64_t r = 0; r < rounds; ++r) batch(snp_begin + (r * n_warps + warp) * 32, 32);
-        const uint64_t rem_begin = snp_begin + rounds * n_warps * 32, rem = snp_end - rem_begin;
-        const uint64_t b0 = rem_begin + warp * rem / n_warps, b1 = rem_begin + (warp + 1) * rem / n_warps;
-        for (uint64_t base = b0; base < b1; base += 32) batch(base, (uint32_t)min((uint64_t)32, b1 - base));
-    } else {
-        // contiguous balanced ranges
-        const uint64_t b0 = snp_begin + warp * n_snps / n_warps, b1 = snp_begin + (warp + 1) * n_snps / n_warps;
-        for (uint64_t base = b0; base < b1; base += 32) batch(base, (uint32_t)min((uint64_t)32, b1 - base));
-    }
+        if (my_row < in_batch) finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + my_row, out);
+    });
 }
 
-// ---- select + scan in one pass --------------------------------------------------------------------------------
+// ---- select + scan in one pass (K1') ----------------------------------------------------------------------------
 // The same scan on the RAW rows with the class masks applied on the fly: the reference's
-// getCaseControlGenotypeDistribution(rIdx, ccs, ccgd) (compressed_genotype_table5.cpp:609-657), which is what
-// select_cc_maf needs when the compacted rows are used once. A row is [plane 1: Q chunks][plane 2: Q chunks]; the
-// masks (case, control-and-not-case: the compaction's classes) sit in shared memory. Six popcount streams per
-// chunk pair instead of three, no K0 and no second copy of the table: algorithmic bytes are again n_samples / 4
-// per SNP.
+// getCaseControlGenotypeDistribution(rIdx, ccs, ccgd) (compressed_genotype_table5.cpp:609-657), which is all that
+// select_cc_maf, a permutation or another trait over the resident table needs: no K0, no second copy of the table,
+// algorithmic bytes again n_samples / 4 per SNP. A row is [plane 1: Q chunks][plane 2: Q chunks]; the masks (case,
+// control-and-not-case: the compaction's classes) sit in shared memory.
 __device__ __forceinline__ void accumulate_masked(const uint4 &x, const uint4 &y, const uint4 &m, HS &h1, HS &h2, HS &hb) {
     const uint4 xm = make_uint4(x.x & m.x, x.y & m.y, x.z & m.z, x.w & m.w);
     const uint4 ym = make_uint4(y.x & m.x, y.y & m.y, y.z & m.z, y.w & m.w);
@@ -245,28 +273,30 @@ __device__ __forceinline__ void accumulate_masked(const uint4 &x, const uint4 &y
     hb.twos += __popc(xm.z & y.z) + __popc(xm.w & y.w);
 }
 
-// PARTITION: every sample is a case or a control (no sample outside both classes), the usual cohort. The control counts
-// are then the row totals minus the case counts, and the totals need no mask: three masked and three plain streams
-// instead of six masked ones (54 instead of 66 ALU-pipe instructions per chunk pair on the pipe that bounds this kernel).
-template <int G, int SLOTS, int MINB, bool PARTITION>
+// MODE 0 (general): six masked popcount streams, any two disjoint classes (samples may belong to neither).
+// MODE 1 (partition, first scan of a table): every sample is a case or a control, so the control counts are the row
+//         totals minus the case counts and the totals need no mask (three masked + three plain streams); the totals --
+//         which depend on the table alone, not on the phenotype -- are written to row_tot on the way.
+// MODE 2 (partition, totals cached): three masked streams; the row totals come from row_tot (16 bytes per SNP instead of
+//         a second pass over the words). This is what every re-selection over a resident table runs: the ALU work of the
+//         compacted scan plus the mask ANDs, without K0 ever having run.
+template <int G, int SLOTS, int MINB, int MODE>
 __global__ void __launch_bounds__(256, MINB)
 marginal_scan_masked_kernel(const uint4 *__restrict__ raw, uint32_t Q, const uint4 *__restrict__ mask_case,
                             const uint4 *__restrict__ mask_ctrl, uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin,
-                            uint64_t snp_end, uint32_t *__restrict__ counts, gwasdev_marginal_information *__restrict__ mi,
-                            gwasdev_snp_stats *__restrict__ stats, uint64_t out_base) {
-    extern __shared__ uint4 sm_mask[];   // [Q] case, [Q] control
-    for (uint32_t q = threadIdx.x; q < 2 * Q; q += blockDim.x) sm_mask[q] = q < Q ? mask_case[q] : mask_ctrl[q - Q];
+                            uint64_t snp_end, const ScanOut out) {
+    extern __shared__ uint4 sm_mask[];   // [Q] case, then (MODE 0) [Q] control
+    for (uint32_t q = threadIdx.x; q < (MODE == 0 ? 2 * Q : Q); q += blockDim.x) sm_mask[q] = q < Q ? mask_case[q] : mask_ctrl[q - Q];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
     const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t n_snps = snp_end - snp_begin;
     constexpr uint32_t NG = 32 / G;
     const uint32_t my_row = l * NG + g;
-    auto batch = [&](uint64_t base, uint32_t in_batch) {
+    for_each_batch(snp_begin, snp_end, [&](uint64_t base, uint32_t in_batch) {
         const uint32_t passes = (in_batch + NG - 1) / NG;
         uint32_t m1c = 0, m2c = 0, mbc = 0, m1t = 0, m2t = 0, mbt = 0;
+        uint4 tot = make_uint4(0, 0, 0, 0);
+        if (MODE == 2 && my_row < in_batch) tot = __ldg(out.row_tot + base + my_row);   // in flight during the passes
         for (uint32_t it = 0; it < passes; ++it) {
             const uint32_t brow = it * NG + g;
             const bool valid = brow < in_batch;
@@ -290,26 +320,28 @@ marginal_scan_masked_kernel(const uint4 *__restrict__ raw, uint32_t Q, const uin
                     const uint32_t q = q0 + u * G;
                     if (q < Q) {
                         accumulate_masked(x[u], y[u], sm_mask[q], a1, a2, ab);
-                        if (PARTITION) { ChunkPair c; c.x = x[u]; c.y = y[u]; accumulate_pair(c, b1, b2, bb); }   // row totals (padding bits are zero)
-                        else accumulate_masked(x[u], y[u], sm_mask[Q + q], b1, b2, bb);
+                        if (MODE == 1) { ChunkPair c; c.x = x[u]; c.y = y[u]; accumulate_pair(c, b1, b2, bb); }   // row totals (bits beyond sample N are zero)
+                        else if (MODE == 0) accumulate_masked(x[u], y[u], sm_mask[Q + q], b1, b2, bb);
                     }
                 }
             }
-            uint32_t s1 = hs_total(a1), s2 = hs_total(a2), sb = plain_total(ab), t1 = hs_total(b1), t2 = hs_total(b2), tb = plain_total(bb);
+            uint32_t s1 = hs_total(a1), s2 = hs_total(a2), sb = plain_total(ab), t1 = 0, t2 = 0, tb = 0;
             s1 = __reduce_add_sync(group_mask, s1); s2 = __reduce_add_sync(group_mask, s2);
-            sb = __reduce_add_sync(group_mask, sb); t1 = __reduce_add_sync(group_mask, t1);
-            t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
-            if (PARTITION) { t1 -= s1; t2 -= s2; tb -= sb; }
+            sb = __reduce_add_sync(group_mask, sb);
+            if (MODE != 2) {
+                t1 = hs_total(b1); t2 = hs_total(b2); tb = plain_total(bb);
+                t1 = __reduce_add_sync(group_mask, t1); t2 = __reduce_add_sync(group_mask, t2); tb = __reduce_add_sync(group_mask, tb);
+            }
             if (l == it) { m1c = s1; m2c = s2; mbc = sb; m1t = t1; m2t = t2; mbt = tb; }
         }
-        if (my_row < in_batch)
-            finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + my_row - out_base, counts, mi, stats);
-    };
-    const uint64_t rounds = n_snps / (n_warps * 32);
-    for (uint64_t r = 0; r < rounds; ++r) batch(snp_begin + (r * n_warps + warp) * 32, 32);
-    const uint64_t rem_begin = snp_begin + rounds * n_warps * 32, rem = snp_end - rem_begin;
-    const uint64_t b0 = rem_begin + warp * rem / n_warps, b1 = rem_begin + (warp + 1) * rem / n_warps;
-    for (uint64_t base = b0; base < b1; base += 32) batch(base, (uint32_t)min((uint64_t)32, b1 - base));
+        if (my_row < in_batch) {
+            if (MODE == 1) {
+                if (out.row_tot) out.row_tot[base + my_row] = make_uint4(m1t, m2t, mbt, 0);
+                m1t -= m1c; m2t -= m2c; mbt -= mbc;
+            } else if (MODE == 2) { m1t = tot.x - m1c; m2t = tot.y - m2c; mbt = tot.z - mbc; }
+            finish_snp(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, base + my_row, out);
+        }
+    });
 }
 
 // Streaming in sample blocks: counts are additive over disjoint sample blocks of one cohort.
@@ -361,123 +393,203 @@ __global__ void raw_counts_kernel(const uint32_t *__restrict__ raw, uint32_t Wr,
 
 using namespace gwasdev;
 
-// Launch the scan with DEVICE output pointers (any may be NULL). Outputs are indexed from snp_begin.
-static int scan_compacted(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
-                          gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats) {
-    int sms = 0;
-    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    const uint32_t Qc = s->Wc / 4, Qt = s->Wt / 4, stride4 = 2 * (Qc + Qt);
-    // lanes per row: the width that wastes the fewest lane slots for this cohort, narrower on ties
+static int lanes_per_row(const gwasdev_store *s, std::initializer_list<uint32_t> class_chunks) {
+    if (s->opt[GWASDEV_OPT_LANES_PER_ROW]) return (int)s->opt[GWASDEV_OPT_LANES_PER_ROW];
+    // the width that wastes the fewest lane slots for this cohort, narrower on ties
     int G = 8;
     double best = 1e30;
     for (int cand : {8, 16, 32}) {
-        const double used = (double)((Qc + cand - 1) / cand + (Qt + cand - 1) / cand) * cand;
-        const double waste = used / (double)(Qc + Qt);
+        double used = 0, have = 0;
+        for (uint32_t Q : class_chunks) { used += (double)((Q + cand - 1) / cand) * cand; have += Q; }
+        const double waste = used / have;
         if (waste < best - 1e-9) { best = waste; G = cand; }
     }
+    return G;
+}
+
+// Launch the compacted scan [snp_begin, snp_end) with DEVICE output pointers.
+static int scan_compacted(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, const ScanOut &out) {
+    int sms = 0;
+    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    const uint32_t Qc = s->Wc / 4, Qt = s->Wt / 4, stride4 = 2 * (Qc + Qt);
+    int G = lanes_per_row(s, {Qc, Qt});
     const uint64_t n = snp_end - snp_begin;
     const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
-    // tuning knob (loads in flight per lane, resident CTAs per SM); defaults measured on B200, see DESIGN.md
-    int slots = 5, minb = 3, interleave = 1;
-    if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d,%d,%d", &slots, &minb, &G, &interleave);
+    // loads in flight per lane and resident CTAs per SM: 5 chunk pairs, 3 CTAs (B200 sweep)
+    int slots = 5, minb = 3;
+#ifdef GWASDEV_SWEEP
+    if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d,%d", &slots, &minb, &G);
+#endif
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * minb, (n + 255) / 256));
 #define SCAN_LAUNCH(GG, SS, BB)                                                                                          \
-    marginal_scan_kernel<GG, SS, BB><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, \
-                                                                    snp_end, d_counts, d_mi, d_stats, snp_begin, interleave)
+    marginal_scan_kernel<GG, SS, BB><<<blocks, 256, 0, s->stream>>>(sel, stride4, Qc, Qt, s->n_case, s->n_ctrl, snp_begin, snp_end, out)
+#ifdef GWASDEV_SWEEP
 #define SCAN_CFG(GG)                                                                                   \
     do {                                                                                               \
         if (slots == 6 && minb == 3) SCAN_LAUNCH(GG, 6, 3);                                            \
         else if (slots == 5 && minb == 3) SCAN_LAUNCH(GG, 5, 3);                                       \
         else if (slots == 4 && minb == 4) SCAN_LAUNCH(GG, 4, 4);                                       \
         else if (slots == 3 && minb == 4) SCAN_LAUNCH(GG, 3, 4);                                       \
-        else if (slots == 5 && minb == 4) SCAN_LAUNCH(GG, 5, 4);                                       \
         else if (slots == 8 && minb == 2) SCAN_LAUNCH(GG, 8, 2);                                       \
-        else if (slots == 2 && minb == 5) SCAN_LAUNCH(GG, 2, 5);                                       \
         else { set_error("GWASDEV_SCAN_CFG=%d,%d is not an instantiated configuration", slots, minb); return GWASDEV_EINVAL; } \
     } while (0)
+#else
+#define SCAN_CFG(GG) SCAN_LAUNCH(GG, 5, 3)
+#endif
     if (G == 8) SCAN_CFG(8);
     else if (G == 16) SCAN_CFG(16);
     else SCAN_CFG(32);
 #undef SCAN_CFG
 #undef SCAN_LAUNCH
+    (void)slots; (void)minb;
     GW_LAUNCHED();
     return GWASDEV_OK;
 }
 
-// Compacted scan for the other translation units (margins of the pairwise screen, probes): builds the compacted
-// layout when it is missing and times the kernel for gwasdev_last_scan_ms.
-int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
-                          gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats) {
-    { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
-    GW_CUDA(cudaEventRecord(s->ev0, s->stream));
-    const int rc = scan_compacted(s, snp_begin, snp_end, d_counts, d_mi, d_stats);
-    if (rc != GWASDEV_OK) return rc;
-    GW_CUDA(cudaEventRecord(s->ev1, s->stream));
-    return GWASDEV_OK;
-}
+static size_t masked_smem_bytes(const gwasdev_store *s, int mode) { return (mode == 0 ? 2ull : 1ull) * (s->Wr / 4) * sizeof(uint4); }
+static bool partitioned(const gwasdev_store *s) { return s->n_case + s->n_ctrl == s->N; }   // nobody outside the two classes
+// can this selection be scanned through the masks (the masks must fit in shared memory)
+static bool masked_fits(const gwasdev_store *s) { return masked_smem_bytes(s, partitioned(s) ? 1 : 0) <= 200 * 1024; }
 
-// The masked scan over the raw rows (no compacted store needed). Same outputs as gwasdev_internal_scan.
-static int scan_masked(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
-                       gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats, uint64_t out_base) {
+// The masked scan over the raw rows (no compacted store needed).
+static int scan_masked(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, ScanOut out) {
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const uint32_t Q = s->Wr / 4;
-    int G = 8;
-    double best = 1e30;
-    for (int cand : {8, 16, 32}) {
-        const double waste = (double)((Q + cand - 1) / cand) * cand / (double)Q;
-        if (waste < best - 1e-9) { best = waste; G = cand; }
-    }
-    int slots = 2, minb = 4;   // B200 sweep (tools/sweep_mscan.py): the kernel is ALU-bound, occupancy pays more than loads in flight
+    int G = lanes_per_row(s, {Q});
+    const bool use_tot = partitioned(s) && s->opt[GWASDEV_OPT_ROW_TOTALS] == 0;
+    const int mode = !partitioned(s) ? 0 : (use_tot && s->tot_valid ? 2 : 1);
+    if (mode == 1 && use_tot) {
+        if (!s->d_row_tot) GW_CUDA(cudaMalloc((void **)&s->d_row_tot, s->M * sizeof(uint4)));
+        out.row_tot = s->d_row_tot;
+    } else out.row_tot = mode == 2 ? s->d_row_tot : nullptr;
+    // loads in flight per lane, resident CTAs per SM (B200 sweeps, tools/sweep_mscan.py): modes 0 and 1 are bound by the
+    // ALU pipe (occupancy pays more than loads in flight); mode 2 has the compacted scan's instruction mix
+    int slots = mode == 2 ? 4 : 2, minb = mode == 2 ? 3 : 4;
+#ifdef GWASDEV_SWEEP
     if (const char *cfg = getenv("GWASDEV_MSCAN_CFG")) sscanf(cfg, "%d,%d,%d", &slots, &minb, &G);
+#endif
     const uint64_t n = snp_end - snp_begin;
-    const size_t smem = 2ull * Q * sizeof(uint4);
+    const size_t smem = masked_smem_bytes(s, mode);
     GW_REQUIRE(smem <= 200 * 1024, "masked scan: %u samples exceed the shared-memory mask buffer", s->N);
     const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms * minb, (n + 255) / 256));
     const uint4 *raw = reinterpret_cast<const uint4 *>(s->d_raw);
-    const uint4 *mca = reinterpret_cast<const uint4 *>(s->d_case_mask), *mco = reinterpret_cast<const uint4 *>(s->d_ctrl_sel_mask);
-    const bool partition = s->n_case + s->n_ctrl == s->N && !getenv("GWASDEV_MSCAN_NO_PARTITION");   // nobody outside the two classes
-#define MSCAN1(GG, SS, BB, PP)                                                                                                     \
+    const uint4 *mca = reinterpret_cast<const uint4 *>(s->d_case_sel_mask), *mco = reinterpret_cast<const uint4 *>(s->d_ctrl_sel_mask);
+#define MSCAN1(GG, SS, BB, MM)                                                                                                     \
     do {                                                                                                                           \
-        if (smem > 48 * 1024) GW_CUDA(cudaFuncSetAttribute(marginal_scan_masked_kernel<GG, SS, BB, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        marginal_scan_masked_kernel<GG, SS, BB, PP><<<blocks, 256, smem, s->stream>>>(raw, Q, mca, mco, s->n_case, s->n_ctrl, snp_begin, \
-                                                                                     snp_end, d_counts, d_mi, d_stats, out_base);  \
+        if (smem > 48 * 1024) GW_CUDA(cudaFuncSetAttribute(marginal_scan_masked_kernel<GG, SS, BB, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        marginal_scan_masked_kernel<GG, SS, BB, MM><<<blocks, 256, smem, s->stream>>>(raw, Q, mca, mco, s->n_case, s->n_ctrl, snp_begin, snp_end, out); \
     } while (0)
 #define MSCAN(GG, SS, BB)                                                                                                          \
-    do { if (partition) MSCAN1(GG, SS, BB, true); else MSCAN1(GG, SS, BB, false); } while (0)
+    do { if (mode == 2) MSCAN1(GG, SS, BB, 2); else if (mode == 1) MSCAN1(GG, SS, BB, 1); else MSCAN1(GG, SS, BB, 0); } while (0)
+#ifdef GWASDEV_SWEEP
 #define MSCAN_G(GG)                                                                                  \
     do {                                                                                             \
-        if (slots == 2 && minb == 3) MSCAN(GG, 2, 3);                                                \
+        if (slots == 2 && minb == 4) MSCAN(GG, 2, 4);                                                \
+        else if (slots == 3 && minb == 4) MSCAN(GG, 3, 4);                                           \
+        else if (slots == 4 && minb == 4) MSCAN(GG, 4, 4);                                           \
         else if (slots == 3 && minb == 3) MSCAN(GG, 3, 3);                                           \
         else if (slots == 4 && minb == 3) MSCAN(GG, 4, 3);                                           \
-        else if (slots == 4 && minb == 2) MSCAN(GG, 4, 2);                                           \
+        else if (slots == 5 && minb == 3) MSCAN(GG, 5, 3);                                           \
+        else if (slots == 6 && minb == 3) MSCAN(GG, 6, 3);                                           \
         else if (slots == 6 && minb == 2) MSCAN(GG, 6, 2);                                           \
-        else if (slots == 2 && minb == 4) MSCAN(GG, 2, 4);                                           \
-        else if (slots == 3 && minb == 4) MSCAN(GG, 3, 4);                                           \
+        else if (slots == 8 && minb == 2) MSCAN(GG, 8, 2);                                           \
         else if (slots == 2 && minb == 5) MSCAN(GG, 2, 5);                                           \
-        else if (slots == 1 && minb == 5) MSCAN(GG, 1, 5);                                           \
-        else if (slots == 1 && minb == 6) MSCAN(GG, 1, 6);                                           \
-        else if (slots == 2 && minb == 6) MSCAN(GG, 2, 6);                                           \
         else { set_error("GWASDEV_MSCAN_CFG=%d,%d is not an instantiated configuration", slots, minb); return GWASDEV_EINVAL; } \
     } while (0)
+#else
+#define MSCAN_G(GG)                                                                                  \
+    do { if (mode == 2) MSCAN1(GG, 4, 3, 2); else if (mode == 1) MSCAN1(GG, 2, 4, 1); else MSCAN1(GG, 2, 4, 0); } while (0)
+#endif
     if (G == 8) MSCAN_G(8);
     else if (G == 16) MSCAN_G(16);
     else MSCAN_G(32);
 #undef MSCAN_G
 #undef MSCAN
 #undef MSCAN1
+    (void)slots; (void)minb;
     GW_LAUNCHED();
     return GWASDEV_OK;
 }
 
-// one scan of [b, e) with the kernel the store's state calls for; outputs indexed from out_base
-static int scan_dispatch(gwasdev_store *s, bool masked, uint64_t b, uint64_t e, uint32_t *d_counts, gwasdev_marginal_information *d_mi,
-                         gwasdev_snp_stats *d_stats, uint64_t out_base) {
-    if (masked)
-        return scan_masked(s, b, e, d_counts ? d_counts + 8 * (b - out_base) : nullptr, d_mi ? d_mi + (b - out_base) : nullptr,
-                           d_stats ? d_stats + (b - out_base) : nullptr, b);
-    return scan_compacted(s, b, e, d_counts ? d_counts + 8 * (b - out_base) : nullptr, d_mi ? d_mi + (b - out_base) : nullptr,
-                          d_stats ? d_stats + (b - out_base) : nullptr);
+// Which kernel a marginal scan runs: the compacted layout when it exists; otherwise through the masks on the raw rows
+// (no K0) -- always when the classes partition the cohort (with cached row totals that costs what the compacted scan
+// costs), else for the first scan after a selection only: the second builds the compacted layout, which every later
+// scan streams with half the popcount work per byte.
+static bool choose_masked(gwasdev_store *s) {
+    if (s->sel_built || s->opt[GWASDEV_OPT_MASKED_SCAN] != 0 || !masked_fits(s)) return false;
+    return partitioned(s) || s->scans_since_select == 0;
+}
+
+// Scan for the other translation units (margins of the pairwise screen, probes): any SNP range, device outputs, the
+// kernel the store's state calls for; timed for gwasdev_last_scan_ms.
+int gwasdev_internal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts,
+                          gwasdev_marginal_information *d_mi, gwasdev_snp_stats *d_stats) {
+    GW_REQUIRE(s->selected, "call gwasdev_select_case_control first");
+    const bool masked = choose_masked(s);
+    if (!masked) { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
+    ScanOut out = {};
+    out.counts = d_counts; out.mi = d_mi; out.stats = d_stats; out.out_base = snp_begin;
+    GW_CUDA(cudaEventRecord(s->ev0, s->stream));
+    const int rc = masked ? scan_masked(s, snp_begin, snp_end, out) : scan_compacted(s, snp_begin, snp_end, out);
+    if (rc != GWASDEV_OK) return rc;
+    if (masked && partitioned(s) && s->opt[GWASDEV_OPT_ROW_TOTALS] == 0 && snp_begin == 0 && snp_end == s->M) s->tot_valid = true;
+    GW_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return GWASDEV_OK;
+}
+
+// the compacted kernel on the compacted rows, whatever the store would choose (layout probe gwasdev_counts mode 2)
+static int scan_compacted_forced(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, uint32_t *d_counts) {
+    { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
+    ScanOut out = {};
+    out.counts = d_counts; out.out_base = snp_begin;
+    return scan_compacted(s, snp_begin, snp_end, out);
+}
+
+// Shared body of the two public scans: device outputs directly, host outputs through staging buffers in pieces whose
+// D2H copies overlap the next piece's scan.
+struct HostCopy { void *host; void *dev; size_t bytes_per_snp; };
+
+static int run_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, ScanOut out, int on_device, HostCopy *copies, int n_copies) {
+    const uint64_t n = snp_end - snp_begin;
+    const bool full = snp_begin == 0 && snp_end == s->M;
+    const bool masked = choose_masked(s);
+    ++s->scans_since_select;
+    if (!masked) { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
+    out.out_base = snp_begin;
+    GW_CUDA(cudaEventRecord(s->ev0, s->stream));   // ev0..ev1: the scan kernel(s) of this call (gwasdev_last_scan_ms)
+    int pieces = 1;
+    if (!on_device) {
+        if (!s->copy_stream) {
+            GW_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            for (cudaEvent_t &e : s->ev_piece) GW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        uint64_t out_bytes = 0;
+        for (int c = 0; c < n_copies; ++c) out_bytes += n * copies[c].bytes_per_snp;
+        pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(gwasdev_store::MAX_PIECES, out_bytes / (12ull << 20)));   // ~12 MB per piece (tools/sweep_pieces.py)
+        if (s->opt[GWASDEV_OPT_SCAN_PIECES]) pieces = (int)s->opt[GWASDEV_OPT_SCAN_PIECES];
+    }
+    cudaError_t e = cudaSuccess;
+    for (int p = 0; p < pieces && e == cudaSuccess; ++p) {
+        const uint64_t b = snp_begin + n * p / pieces, en = snp_begin + n * (p + 1) / pieces, o = b - snp_begin, k = en - b;
+        if (k == 0) continue;
+        const int rc = masked ? scan_masked(s, b, en, out) : scan_compacted(s, b, en, out);
+        if (rc != GWASDEV_OK) return rc;
+        if (on_device) continue;
+        e = cudaEventRecord(s->ev_piece[p], s->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s->copy_stream, s->ev_piece[p], 0);
+        for (int c = 0; c < n_copies && e == cudaSuccess; ++c)
+            e = cudaMemcpyAsync((char *)copies[c].host + o * copies[c].bytes_per_snp, (char *)copies[c].dev + o * copies[c].bytes_per_snp,
+                                k * copies[c].bytes_per_snp, cudaMemcpyDeviceToHost, s->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(s->ev1, s->stream);
+    if (!on_device) {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    }
+    if (e != cudaSuccess) { set_error("marginal scan: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    if (masked && full && partitioned(s) && s->opt[GWASDEV_OPT_ROW_TOTALS] == 0) s->tot_valid = true;   // every piece wrote its rows' totals
+    return GWASDEV_OK;
 }
 
 extern "C" {
@@ -492,56 +604,75 @@ int gwasdev_marginal_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     GW_CUDA(cudaSetDevice(s->device));
     const uint64_t n = snp_end - snp_begin;
     const bool full = snp_begin == 0 && snp_end == s->M;
-    // Which kernel: the compacted layout when it exists; otherwise the first scan after a selection counts through the
-    // masks on the raw rows (no K0), and a second scan builds the compacted layout, which every later scan streams
-    // with half the popcount work per byte.
-    const bool masked = !s->sel_built && s->scans_since_select == 0 && !getenv("GWASDEV_NO_MASKED_SCAN");
-    ++s->scans_since_select;
-    if (!masked) { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
-    GW_CUDA(cudaEventRecord(s->ev0, s->stream));   // ev0..ev1: the scan kernel(s) of this call (gwasdev_last_scan_ms)
+    ScanOut out = {};
     if (on_device) {
-        const int rc = scan_dispatch(s, masked, snp_begin, snp_end, counts, mi, stats, snp_begin);
-        if (rc != GWASDEV_OK) return rc;
-        GW_CUDA(cudaEventRecord(s->ev1, s->stream));
-        return GWASDEV_OK;
+        out.counts = counts; out.mi = mi; out.stats = stats;
+        return run_scan(s, snp_begin, snp_end, out, 1, nullptr, 0);
     }
-    uint32_t *d_counts = nullptr;
-    gwasdev_marginal_information *d_mi = nullptr;
-    gwasdev_snp_stats *d_stats = nullptr;
-    if (counts) { GW_CUDA(reserve(s->sc_out_counts, n * 8 * sizeof(uint32_t))); d_counts = (uint32_t *)s->sc_out_counts.p; }
-    if (stats) { GW_CUDA(reserve(s->sc_out_stats, n * sizeof(gwasdev_snp_stats))); d_stats = (gwasdev_snp_stats *)s->sc_out_stats.p; }
+    HostCopy copies[3];
+    int nc = 0;
+    if (counts) { GW_CUDA(reserve(s->sc_out_counts, n * 8 * sizeof(uint32_t))); out.counts = (uint32_t *)s->sc_out_counts.p; copies[nc++] = {counts, out.counts, 8 * sizeof(uint32_t)}; }
+    if (stats) { GW_CUDA(reserve(s->sc_out_stats, n * sizeof(gwasdev_snp_stats))); out.stats = (gwasdev_snp_stats *)s->sc_out_stats.p; copies[nc++] = {stats, out.stats, sizeof(gwasdev_snp_stats)}; }
     if (mi) {
         if (full) {   // keep the full-table margins resident for the pairwise screen
             GW_CUDA(reserve_raw(s->d_mi, s->cap_mi, s->M * sizeof(gwasdev_marginal_information)));
-            d_mi = s->d_mi;
-        } else { GW_CUDA(reserve(s->sc_out_mi, n * sizeof(gwasdev_marginal_information))); d_mi = (gwasdev_marginal_information *)s->sc_out_mi.p; }
+            out.mi = s->d_mi;
+        } else { GW_CUDA(reserve(s->sc_out_mi, n * sizeof(gwasdev_marginal_information))); out.mi = (gwasdev_marginal_information *)s->sc_out_mi.p; }
+        copies[nc++] = {mi, out.mi, sizeof(gwasdev_marginal_information)};
     }
-    // Host outputs: the SNP range is scanned in pieces and every piece's results leave on a second stream while the
-    // next piece is scanned, so the PCIe copy (96 to 288 bytes per SNP) overlaps the scan.
-    if (!s->copy_stream) {
-        GW_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-        for (cudaEvent_t &e : s->ev_piece) GW_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
-    const uint64_t out_bytes = n * ((counts ? 32 : 0) + (stats ? sizeof(gwasdev_snp_stats) : 0) + (mi ? sizeof(gwasdev_marginal_information) : 0));
-    int pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(gwasdev_store::MAX_PIECES, out_bytes / (12ull << 20)));   // ~12 MB per piece (tools/sweep_pieces.py)
-    if (const char *e = getenv("GWASDEV_SCAN_PIECES")) pieces = std::max(1, std::min((int)gwasdev_store::MAX_PIECES, atoi(e)));
-    cudaError_t e = cudaSuccess;
-    for (int p = 0; p < pieces && e == cudaSuccess; ++p) {
-        const uint64_t b = snp_begin + n * p / pieces, en = snp_begin + n * (p + 1) / pieces, o = b - snp_begin, k = en - b;
-        if (k == 0) continue;
-        int rc = scan_dispatch(s, masked, b, en, d_counts, d_mi, d_stats, snp_begin);
-        if (rc != GWASDEV_OK) return rc;
-        e = cudaEventRecord(s->ev_piece[p], s->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s->copy_stream, s->ev_piece[p], 0);
-        if (e == cudaSuccess && counts) e = cudaMemcpyAsync(counts + 8 * o, d_counts + 8 * o, k * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream);
-        if (e == cudaSuccess && stats) e = cudaMemcpyAsync(stats + o, d_stats + o, k * sizeof(gwasdev_snp_stats), cudaMemcpyDeviceToHost, s->copy_stream);
-        if (e == cudaSuccess && mi) e = cudaMemcpyAsync(mi + o, d_mi + o, k * sizeof(gwasdev_marginal_information), cudaMemcpyDeviceToHost, s->copy_stream);
-    }
-    if (e == cudaSuccess) e = cudaEventRecord(s->ev1, s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->copy_stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    if (e != cudaSuccess) { set_error("gwasdev_marginal_scan: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
+    const int rc = run_scan(s, snp_begin, snp_end, out, 0, copies, nc);
+    if (rc != GWASDEV_OK) return rc;
     if (mi && full) { s->mi_valid = true; s->side_valid = false; s->mma_side_valid = false; }
+    return GWASDEV_OK;
+}
+
+int gwasdev_marginal_scan_compact(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, gwasdev_snp_compact *out_rec,
+                                  double p_threshold, gwasdev_sig_snp *sig, uint64_t sig_capacity, uint64_t *n_sig, int on_device) {
+    GW_REQUIRE(s != nullptr, "gwasdev_marginal_scan_compact: NULL store");
+    GW_REQUIRE(s->selected, "gwasdev_marginal_scan_compact: call gwasdev_select_case_control first");
+    GW_REQUIRE(snp_begin <= snp_end && snp_end <= s->M, "gwasdev_marginal_scan_compact: bad SNP range [%llu, %llu)",
+               (unsigned long long)snp_begin, (unsigned long long)snp_end);
+    GW_REQUIRE(!out_rec || (s->n_case < 65536 && s->n_ctrl < 65536), "gwasdev_marginal_scan_compact: 16-bit counts need both classes below 65 536 samples");
+    const bool want_sig = p_threshold > 0.0;
+    GW_REQUIRE(!want_sig || (n_sig && (sig || sig_capacity == 0)), "gwasdev_marginal_scan_compact: a p-value threshold needs sig / n_sig");
+    GW_REQUIRE(out_rec || want_sig, "gwasdev_marginal_scan_compact: nothing to compute");
+    if (n_sig) *n_sig = 0;
+    if (snp_begin == snp_end) return GWASDEV_OK;
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint64_t n = snp_end - snp_begin;
+    ScanOut out = {};
+    HostCopy copies[1];
+    int nc = 0;
+    if (out_rec) {
+        if (on_device) out.compact = out_rec;
+        else { GW_CUDA(reserve(s->sc_out_stats, n * sizeof(gwasdev_snp_compact))); out.compact = (gwasdev_snp_compact *)s->sc_out_stats.p; copies[nc++] = {out_rec, out.compact, sizeof(gwasdev_snp_compact)}; }
+    }
+    unsigned long long *d_cnt = nullptr;
+    if (want_sig) {
+        GW_CUDA(reserve(s->sc_cnt, 2 * sizeof(unsigned long long)));
+        d_cnt = (unsigned long long *)s->sc_cnt.p;
+        GW_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), s->stream));
+        out.n_sig = d_cnt; out.sig_cap = sig_capacity; out.p_thr = p_threshold;
+        if (on_device) out.sig = sig;
+        else { GW_CUDA(reserve(s->sc_out_mi, std::max<uint64_t>(1, sig_capacity) * sizeof(gwasdev_sig_snp))); out.sig = (gwasdev_sig_snp *)s->sc_out_mi.p; }
+    }
+    const int rc = run_scan(s, snp_begin, snp_end, out, on_device, copies, nc);
+    if (rc != GWASDEV_OK) return rc;
+    if (want_sig) {
+        GW_CUDA(cudaMemcpyAsync(s->h_cnt, d_cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        GW_CUDA(cudaStreamSynchronize(s->stream));
+        const uint64_t found = s->h_cnt[0];
+        *n_sig = found;
+        if (found > sig_capacity) {
+            set_error("gwasdev_marginal_scan_compact: %llu significant SNPs exceed the caller's capacity of %llu", (unsigned long long)found, (unsigned long long)sig_capacity);
+            return GWASDEV_EOVERFLOW;
+        }
+        if (!on_device && found > 0) {
+            GW_CUDA(cudaMemcpyAsync(sig, out.sig, found * sizeof(gwasdev_sig_snp), cudaMemcpyDeviceToHost, s->stream));
+            GW_CUDA(cudaStreamSynchronize(s->stream));
+            std::sort(sig, sig + found, [](const gwasdev_sig_snp &a, const gwasdev_sig_snp &b) { return a.snp < b.snp; });   // appended in completion order
+        }
+    }
     return GWASDEV_OK;
 }
 
@@ -555,9 +686,8 @@ int gwasdev_marginal_accumulate(gwasdev_store *s, uint64_t snp_begin, uint64_t s
     const uint64_t n = snp_end - snp_begin;
     GW_CUDA(reserve(s->sc_out_counts, n * 8 * sizeof(uint32_t)));
     uint32_t *d_counts = (uint32_t *)s->sc_out_counts.p, *d_acc = acc;
-    // a block's rows are used once: count through the masks unless the compacted layout already exists
-    int rc = s->sel_built ? gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, nullptr, nullptr)
-                          : scan_masked(s, snp_begin, snp_end, d_counts, nullptr, nullptr, snp_begin);
+    // a block's rows are used once: counted through the masks unless the compacted layout already exists
+    int rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_counts, nullptr, nullptr);
     if (rc != GWASDEV_OK) return rc;
     if (!on_device) {
         GW_CUDA(reserve(s->sc_stage, n * 8 * sizeof(uint32_t)));
@@ -573,7 +703,6 @@ int gwasdev_marginal_accumulate(gwasdev_store *s, uint64_t snp_begin, uint64_t s
     }
     return GWASDEV_OK;
 }
-
 int gwasdev_marginal_finalize(int device, uint64_t n_snps, const uint32_t *counts, gwasdev_marginal_information *mi,
                               gwasdev_snp_stats *stats, int on_device) {
     GW_REQUIRE(counts && (mi || stats), "gwasdev_marginal_finalize: NULL argument");
@@ -620,7 +749,8 @@ int gwasdev_counts(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, int m
     GW_REQUIRE(s && out, "gwasdev_counts: NULL argument");
     GW_REQUIRE(mode >= 0 && mode <= 2, "gwasdev_counts: mode %d", mode);
     GW_REQUIRE(snp_begin <= snp_end && snp_end <= s->M, "gwasdev_counts: bad SNP range");
-    GW_REQUIRE(mode == 0 || s->selected, "gwasdev_counts: mode %d needs gwasdev_select_case_control", mode);
+    GW_REQUIRE(mode != 2 || s->selected, "gwasdev_counts: mode 2 needs gwasdev_select_case_control");
+    GW_REQUIRE(mode != 1 || s->fly_valid, "gwasdev_counts: mode 1 needs gwasdev_set_stream_masks or gwasdev_select_case_control");
     if (snp_begin == snp_end) return GWASDEV_OK;
     GW_CUDA(cudaSetDevice(s->device));
     const uint64_t n = snp_end - snp_begin;
@@ -629,12 +759,12 @@ int gwasdev_counts(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, int m
     uint32_t *d_out = (uint32_t *)s->sc_out_counts.p;
     int rc = GWASDEV_OK;
     cudaError_t e = cudaSuccess;
-    if (mode == 2) rc = gwasdev_internal_scan(s, snp_begin, snp_end, d_out, nullptr, nullptr);
+    if (mode == 2) rc = scan_compacted_forced(s, snp_begin, snp_end, d_out);
     else {
         const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
         raw_counts_kernel<<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, mode == 1 ? s->d_case_mask : nullptr,
                                                          mode == 1 ? s->d_ctrl_mask : nullptr,
-                                                         mode == 1 ? s->n_case : s->N, s->n_ctrl, snp_begin, snp_end, d_out, per);
+                                                         mode == 1 ? s->n_fly_case : s->N, s->n_fly_ctrl, snp_begin, snp_end, d_out, per);   // member counts as given (:649-653)
         ++g_launches;
         e = cudaGetLastError();
     }

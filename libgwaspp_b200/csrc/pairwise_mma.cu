@@ -98,11 +98,14 @@ struct MmaParams {
     uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only, rows of CTA `dump_rank`
     uint64_t dump_tile;
     uint32_t dump_rank;
-    unsigned long long *prof;   // GWASDEV_MMA_PROF: per CTA {mma busy, mma waiting for tempty, mma waiting for full, epilogue busy,
-                                // epilogue waiting for tfull, producer waiting for empty, tiles} in SM clocks (warp 0 / role threads)
-    uint32_t dbg;               // GWASDEV_MMA_DEBUG (timing diagnostics, results invalid): 1 epilogue only hand-shakes, 2 epilogue loads TMEM
-                                // but skips the math, 4 no MMAs issued, 16 no exact pass, 32 no TMA loads
+    unsigned long long *prof;   // role timers (builds with -DGWASDEV_SWEEP only, GWASDEV_MMA_PROF): per CTA {mma busy, mma waiting for tempty,
+                                // mma waiting for full, epilogue busy, epilogue waiting for tfull, producer waiting for empty, tiles} in SM clocks
 };
+#ifdef GWASDEV_SWEEP
+#define GW_PROF(x) x
+#else
+#define GW_PROF(x)
+#endif
 
 // ---- PTX: tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -395,7 +398,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         // ===== TMA producer (both CTAs: own 128 A rows, own half of the 256 B rows) =====
         if (lane == 0) {
             uint64_t it = 0;
-            long long prof_pw = 0;
+            GW_PROF(long long prof_pw = 0;)
             TileCursor cur; cur.locate(first, p.TB, p.n_bands);
             for (uint64_t t = first, u = u_first; t < last;) {
                 uint32_t I2, J;
@@ -405,11 +408,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
                     const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
-                    const long long w0 = clock64();
+                    GW_PROF(const long long w0 = clock64();)
                     mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
-                    prof_pw += clock64() - w0;
+                    GW_PROF(prof_pw += clock64() - w0;)
                     unsigned char *dst = sm + st * STAGE_BYTES_MMA;
-                    if (p.dbg & 32) { if (rank == 0) mbar_arrive(&full[st]); else mbar_arrive_remote(&full[st], 0); continue; }
                     if (rank == 0) mbar_expect_tx(&full[st], nk * 2 * KB_BYTES);
                     else mbar_arrive_remote(&full[st], 0);
                     for (uint32_t k2 = 0; k2 < nk; ++k2) {
@@ -418,30 +420,28 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     }
                 }
             }
-            if (p.prof) p.prof[blockIdx.x * 8 + 5] = (unsigned long long)prof_pw;
+            GW_PROF(if (p.prof) p.prof[blockIdx.x * 8 + 5] = (unsigned long long)prof_pw;)
         }
     } else if (warp == MMA_WARP) {
         // ===== MMA issuer (leader CTA only) =====
         if (lane == 0 && rank == 0) {
             uint64_t it = 0, tile_it = 0;
-            long long prof_te = 0, prof_fu = 0;
-            const long long prof_t0 = clock64();
+            GW_PROF(long long prof_te = 0; long long prof_fu = 0; const long long prof_t0 = clock64();)
             for (uint64_t t = first, u = u_first; t < last; ++tile_it) {
                 { u += u_step; t = p.dump ? last : shard_tile(u, p.shard, p.n_shards); }
                 const uint32_t buf = (uint32_t)(tile_it & 1);
-                const long long w0 = clock64();
+                GW_PROF(const long long w0 = clock64();)
                 mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
-                prof_te += clock64() - w0;
+                GW_PROF(prof_te += clock64() - w0;)
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + buf * ACC_COLS;
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
                     const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
-                    const long long w1 = clock64();
+                    GW_PROF(const long long w1 = clock64();)
                     mbar_wait_wd(&full[st], (uint32_t)((it / MMA_STAGES) & 1));
-                    prof_fu += clock64() - w1;
+                    GW_PROF(prof_fu += clock64() - w1;)
                     tc_fence_after();
-                    if (!(p.dbg & 4))
                     for (uint32_t k2 = 0; k2 < nk; ++k2) {
                         const uint32_t a_addr = base + st * STAGE_BYTES_MMA + k2 * KB_BYTES, b_addr = a_addr + A_STAGE_BYTES;
                         const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
@@ -453,10 +453,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 }
                 tc_commit_mc(&tfull[buf], 3);         // accumulator complete in both CTAs
             }
-            if (p.prof) {
+            GW_PROF(if (p.prof) {
                 unsigned long long *o = p.prof + blockIdx.x * 8;
                 o[0] = (unsigned long long)(clock64() - prof_t0); o[1] = (unsigned long long)prof_te; o[2] = (unsigned long long)prof_fu; o[6] = tile_it;
-            }
+            })
         }
     } else {
         // ===== epilogue (both CTAs: own 64 A-SNPs x the tile's 128 B-SNPs) =====
@@ -466,8 +466,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         const int a_loc = 16 * q + (lane >> 1);       // A-SNP of this lane inside the CTA's 64
         const int pl = lane & 1;                      // plane held by this lane's TMEM row (0: aa, 1: bb)
         uint64_t tile_it = 0;
-        long long prof_tw = 0;
-        const long long prof_e0 = clock64();
+        GW_PROF(long long prof_tw = 0; const long long prof_e0 = clock64();)
         TileCursor cur; cur.locate(first, p.TB, p.n_bands);
         for (uint64_t t = first, u = u_first; t < last; ++tile_it) {
             uint32_t I2, J;
@@ -508,14 +507,13 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 for (int k = 0; k < 4; ++k) dst[32 * k + lane] = __ldg(src + 32 * k + lane);
                 __syncwarp();
             }
-            const long long w2 = clock64();
+            GW_PROF(const long long w2 = clock64();)
             if (lane == 0) mbar_wait_wd(&tfull[buf], (uint32_t)((tile_it >> 1) & 1));
             __syncwarp();
-            prof_tw += clock64() - w2;
+            GW_PROF(prof_tw += clock64() - w2;)
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                if (p.dbg & 1) break;
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 64 * g + 32 * h, v);
                 tc_wait_ld();
@@ -537,7 +535,6 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     }
                     continue;
                 }
-                if (p.dbg & 2) { if (v[0] + v[13] + v[31] == 0x7fffffffu) p.cand[0].pad = 1; continue; }
                 // pass 1, branch-free so that the eight pairs interleave: upper bound of the statistic
                 const uint64_t gj0 = (uint64_t)J * MMA_B_SNPS + 32 * g + 16 * h + pl;
                 uint32_t hot = 0;
@@ -562,7 +559,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     hot |= (valid & (ub > thrA + Ccol)) ? (1u << s) : 0u;
                 }
                 // pass 2, rare: exact fp32 formula for the pairs whose bound passed
-                if (!(p.dbg & 16) && __any_sync(0xffffffffu, hot != 0)) {
+                if (__any_sync(0xffffffffu, hot != 0)) {
 #pragma unroll 1
                     for (int s = 0; s < 8; ++s) {
                         if (!((hot >> s) & 1u)) continue;
@@ -597,10 +594,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tempty[buf], 0);
         }
-        if (p.prof && lane == 0 && (warp == 0 || warp == 15)) {
+        GW_PROF(if (p.prof && lane == 0 && (warp == 0 || warp == 15)) {
             unsigned long long *o = p.prof + blockIdx.x * 8;
             o[warp == 0 ? 3 : 7] = (unsigned long long)(clock64() - prof_e0); if (warp == 0) o[4] = (unsigned long long)prof_tw;
-        }
+        })
     }
 
     tc_fence_before();
@@ -1202,7 +1199,11 @@ static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
     const size_t smem = mma_smem_bytes();
     GW_CUDA(cudaFuncSetAttribute(pair_screen_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));   // one CTA pair per TPC
+#ifdef GWASDEV_SWEEP
     const bool prof = getenv("GWASDEV_MMA_PROF") != nullptr && !p.dump;
+#else
+    const bool prof = false;
+#endif
     unsigned long long *d_prof = nullptr;
     if (prof) {
         GW_CUDA(cudaMalloc(&d_prof, (size_t)2 * pairs * 8 * sizeof(unsigned long long)));
@@ -1236,7 +1237,6 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
     p.N = (float)(s->n_case + s->n_ctrl);
     p.qc = s->mma_qc; p.q0 = s->mma_q0; p.thr2 = 0.f;
     p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0; p.prof = nullptr;
-    p.dbg = getenv("GWASDEV_MMA_DEBUG") ? (uint32_t)atoi(getenv("GWASDEV_MMA_DEBUG")) : 0u;
 }
 
 // ---- four-plane engine: host side ---------------------------------------------------------------------
@@ -1337,7 +1337,7 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, ui
 // Launches the tensor-core screen for this shard's clean tiles. thr already carries the fp32 margin.
 int gwasdev_internal_screen_mma(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, void *cand,
                                 unsigned long long *n_cand, uint64_t cap) {
-    const bool trace = getenv("GWASDEV_TRACE") != nullptr;
+    const bool trace = s->opt[GWASDEV_OPT_TRACE] != 0;
     if (trace) cudaEventRecord(s->ev2, s->stream);
     int rc = ensure_mma_inputs(s);
     if (rc != GWASDEV_OK) return rc;

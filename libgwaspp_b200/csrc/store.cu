@@ -14,7 +14,7 @@
 namespace gwasdev {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -26,7 +26,9 @@ void set_error(const char *fmt, ...) {
 // ---- kernels -------------------------------------------------------------------------------------
 
 // reference row [hdr][plane1: P][plane2: P] (16-bit blocks, odd stride) -> hdr[], raw[M][2][Wr] words
-__global__ void unpack_rows_kernel(const uint16_t *__restrict__ rows, uint32_t P, uint32_t Wr,
+// Bits at or beyond sample N (the reference's row padding) are cleared: every kernel may then take "bit set" as "sample
+// has the genotype" without a valid-sample mask.
+__global__ void unpack_rows_kernel(const uint16_t *__restrict__ rows, uint32_t P, uint32_t Wr, uint32_t N,
                                    uint16_t *__restrict__ hdr, uint32_t *__restrict__ raw,
                                    uint64_t first_row) {
     const uint64_t r = blockIdx.x;
@@ -38,6 +40,7 @@ __global__ void unpack_rows_kernel(const uint16_t *__restrict__ rows, uint32_t P
         uint32_t v = 0;
         if (2 * k < P) v = src[1 + plane * P + 2 * k];
         if (2 * k + 1 < P) v |= (uint32_t)src[1 + plane * P + 2 * k + 1] << 16;
+        if (32 * k + 32 > N) v &= 32 * k >= N ? 0u : (0xffffffffu >> (32 * k + 32 - N));
         dst[w] = v;
     }
 }
@@ -133,16 +136,17 @@ select_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, SelectTables ca, Se
 // the output row) is loaded once into registers and the per-row work is two loads, four bit-compresses and the ORs into
 // the shared-memory row buffer. The table-driven kernel above spends ~260 instructions per source word on table reads,
 // index arithmetic and divisions (ncu r1m); this one ~100.
-struct ColumnTables { uint32_t m, mv[5], sh, down, lo, hi; };   // down = 32 - members; lo / hi: word offsets (plane 1) of the piece's two output words
+struct ColumnTables { uint32_t m, mv[5], mul, down, lo, hi; };   // mul = 2^(landing bit); down = 32 - members; lo / hi: word offsets (plane 1) of the piece's two output words
 
-// compress towards the MOST significant end: the moves are left shifts by constants, which ptxas issues as IMAD.SHL on the
-// FMA pipe, leaving two LOP3 per stage on the ALU pipe that bounds this kernel (ncu r1o: ALU 68 % busy, everything else idle)
+// compress towards the MOST significant end. A stage moves the bits t = x & mv left by k = 2^i: x' = (x ^ t) | (t << k). The
+// moved bits land on positions that are empty in x ^ t (a compress never collides) and t is a subset of x, so OR and XOR are
+// plain add and subtract: x' = x - t + (t << k) = x + t * (2^k - 1) -- ONE multiply-add on the FMA pipe after ONE LOP3 on the
+// ALU pipe, instead of two LOP3 plus a shift (the ALU pipe bounded the r1 form of this kernel: ncu r1q, ALU 68 % busy with
+// 44 of its 58 instructions per source word in these stages).
 __device__ __forceinline__ uint32_t compress_bits_left(uint32_t x, const uint32_t *mvl) {
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        const uint32_t t = x & mvl[i];
-        x = (x ^ t) | (t << (1 << i));
-    }
+#define GW_STAGE(I, MUL) { const uint32_t t = x & mvl[I]; asm("mad.lo.u32 %0, %1, " #MUL ", %0;" : "+r"(x) : "r"(t)); }
+    GW_STAGE(0, 1) GW_STAGE(1, 3) GW_STAGE(2, 15) GW_STAGE(3, 255) GW_STAGE(4, 65535)
+#undef GW_STAGE
     return x;
 }
 
@@ -152,21 +156,22 @@ __device__ __forceinline__ ColumnTables load_column(const SelectTables &t, uint3
 #pragma unroll
     for (int i = 0; i < 5; ++i) c.mv[i] = t.mvl[5 * sw + i];
     const uint32_t pos = t.rank[sw], o = pos >> 5;
-    c.sh = pos & 31;
-    c.down = 32 - __popc(c.m);
+    c.mul = 1u << (pos & 31);
+    c.down = min(32u - (uint32_t)__popc(c.m), 31u);      // an empty column compresses to 0 whatever the shift
     c.lo = sel_word(class_off, 0, min(o, W - 1));
     c.hi = sel_word(class_off, 0, min(o + 1, W - 1));
     return c;
 }
 
+// The compressed piece sits in the top bits; one shift brings it down and one 32 x 32 -> 64 bit multiply by 2^(landing bit)
+// (IMAD.WIDE, FMA pipe) yields both output words at once.
 __device__ __forceinline__ void place_piece(uint32_t *row, const ColumnTables &c, uint32_t w1, uint32_t w2) {
-    if (c.m == 0) return;   // (whole column outside the class; never true for a lane of a mixed cohort)
     const uint32_t x = compress_bits_left(w1 & c.m, c.mv) >> c.down, y = compress_bits_left(w2 & c.m, c.mv) >> c.down;
-    const uint32_t xh = __funnelshift_l(x, 0u, c.sh), yh = __funnelshift_l(y, 0u, c.sh);   // x >> (32 - sh), 0 when sh == 0
-    atomicOr(&row[c.lo], x << c.sh);       // unconditional: a test per OR costs more issue slots than the zero ORs
-    atomicOr(&row[c.lo + 4], y << c.sh);
-    atomicOr(&row[c.hi], xh);
-    atomicOr(&row[c.hi + 4], yh);
+    const unsigned long long px = (unsigned long long)x * c.mul, py = (unsigned long long)y * c.mul;
+    atomicOr(&row[c.lo], (uint32_t)px);       // unconditional: a test per OR costs more issue slots than the zero ORs
+    atomicOr(&row[c.lo + 4], (uint32_t)py);
+    atomicOr(&row[c.hi], (uint32_t)(px >> 32));
+    atomicOr(&row[c.hi + 4], (uint32_t)(py >> 32));
 }
 
 template <int SNPS>
@@ -178,7 +183,7 @@ select_columns_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, SelectTable
     const bool live = sw < Wr;
     ColumnTables ta, to;
     if (live) { ta = load_column(ca, Wr, sw, 0, Wc); to = load_column(co, Wr, sw, 2 * Wc, Wt); }
-    else { ta.m = 0; to.m = 0; }
+    else { ta = {}; to = {}; }     // a dead lane loads zeros, compresses them to zero and ORs zero into word 0
     for (uint32_t q = threadIdx.x; q < SNPS * sel_stride; q += blockDim.x) rows[q] = 0;
     __syncthreads();
     for (uint64_t snp0 = (uint64_t)blockIdx.x * SNPS; snp0 < M; snp0 += (uint64_t)gridDim.x * SNPS) {
@@ -333,6 +338,10 @@ int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_stor
     s->Mpad = (n_snps + TILE - 1) / TILE * TILE;
     cudaError_t e = cudaMalloc(&s->d_hdr, n_snps * sizeof(uint16_t));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_raw, n_snps * 2ull * s->Wr * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_masks, 4ull * s->Wr * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_masks, 0, 4ull * s->Wr * sizeof(uint32_t));
+    s->d_case_mask = s->d_masks; s->d_ctrl_mask = s->d_masks + s->Wr;
+    s->d_case_sel_mask = s->d_masks + 2ull * s->Wr; s->d_ctrl_sel_mask = s->d_masks + 3ull * s->Wr;
     if (e == cudaSuccess) e = cudaMemset(s->d_hdr, 0, n_snps * sizeof(uint16_t));
     if (e == cudaSuccess) e = cudaMemset(s->d_raw, 0, n_snps * 2ull * s->Wr * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -355,11 +364,20 @@ static void invalidate_selection(gwasdev_store *s) {
     s->selected = s->sel_built = s->pw_built = s->mi_valid = s->side_valid = s->mm_built = s->mm4_built = s->mma_side_valid = s->pc_valid = false;
 }
 
+}  // extern "C"
+
+void gwasdev_internal_rows_changed(gwasdev_store *s) {
+    invalidate_selection(s);
+    s->tot_valid = false;
+}
+
+extern "C" {
+
 void gwasdev_destroy(gwasdev_store *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     gwasdev_internal_free_ingest(s);
-    cudaFree(s->d_case_mask); cudaFree(s->d_ctrl_mask); cudaFree(s->d_ctrl_sel_mask); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
+    cudaFree(s->d_masks); cudaFree(s->d_row_tot); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
     cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
     free(s->tmap); free(s->tmap_mm); free(s->tmap_mm4);
     cudaFree(s->d_mm); cudaFree(s->d_mm4); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col);
@@ -381,6 +399,18 @@ void gwasdev_destroy(gwasdev_store *s) {
 int gwasdev_set_stream(gwasdev_store *s, void *cuda_stream) {
     GW_REQUIRE(s != nullptr, "gwasdev_set_stream: NULL store");
     s->stream = (cudaStream_t)cuda_stream;
+    return GWASDEV_OK;
+}
+
+int gwasdev_set_option(gwasdev_store *s, int option, long long value) {
+    GW_REQUIRE(s != nullptr, "gwasdev_set_option: NULL store");
+    GW_REQUIRE(option >= 0 && option < GWASDEV_OPT_COUNT, "gwasdev_set_option: unknown option %d", option);
+    if (option == GWASDEV_OPT_LANES_PER_ROW)
+        GW_REQUIRE(value == 0 || value == 8 || value == 16 || value == 32, "gwasdev_set_option: lanes per row must be 0, 8, 16 or 32");
+    if (option == GWASDEV_OPT_SCAN_PIECES) GW_REQUIRE(value >= 0 && value <= gwasdev_store::MAX_PIECES, "gwasdev_set_option: 0..%d pieces", gwasdev_store::MAX_PIECES);
+    if (option == GWASDEV_OPT_INGEST_CHUNK) GW_REQUIRE(value == 0 || value >= 64, "gwasdev_set_option: ingest chunks of at least 64 bytes");
+    GW_REQUIRE(value >= 0, "gwasdev_set_option: negative value");
+    s->opt[option] = value;
     return GWASDEV_OK;
 }
 
@@ -457,14 +487,14 @@ int gwasdev_put_rows(gwasdev_store *s, uint64_t first_row, uint64_t n_rows, cons
         cudaError_t e = cudaMemcpyAsync(d_stage, (const char *)rows + r * row_bytes, n * row_bytes,
                                         cudaMemcpyHostToDevice, s->stream);
         if (e == cudaSuccess) {
-            unpack_rows_kernel<<<(unsigned)n, 128, 0, s->stream>>>(d_stage, s->P, s->Wr, s->d_hdr, s->d_raw, first_row + r);
+            unpack_rows_kernel<<<(unsigned)n, 128, 0, s->stream>>>(d_stage, s->P, s->Wr, s->N, s->d_hdr, s->d_raw, first_row + r);
             ++g_launches;
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e != cudaSuccess) { set_error("gwasdev_put_rows: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
     }
-    invalidate_selection(s);
+    gwasdev_internal_rows_changed(s);
     return GWASDEV_OK;
 }
 
@@ -530,7 +560,7 @@ int gwasdev_simulate_block(gwasdev_store *s, uint64_t seed, const uint32_t bin_c
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     cudaFree(d_cum);
     if (e != cudaSuccess) { set_error("gwasdev_simulate: %s", cudaGetErrorString(e)); return GWASDEV_ENODEVICE; }
-    invalidate_selection(s);
+    gwasdev_internal_rows_changed(s);
     return GWASDEV_OK;
 }
 
@@ -585,50 +615,72 @@ static void build_select_tables(const std::vector<uint32_t> &mask, uint32_t n_cl
     }
 }
 
+// 16-bit stream-mask blocks -> 32-bit words over the raw sample positions, bits at or beyond sample N dropped
+static void mask_words(const uint16_t *blocks, uint32_t P, uint32_t N, uint32_t Wr, uint32_t *out) {
+    for (uint32_t w = 0; w < Wr; ++w) {
+        uint32_t v = 0;
+        if (2 * w < P) v = blocks[2 * w];
+        if (2 * w + 1 < P) v |= (uint32_t)blocks[2 * w + 1] << 16;
+        if (32 * w + 32 > N) v &= 32 * w >= N ? 0u : (0xffffffffu >> (32 * w + 32 - N));
+        out[w] = v;
+    }
+}
+static uint32_t count_bits(const uint32_t *m, uint32_t n) { uint32_t c = 0; for (uint32_t w = 0; w < n; ++w) c += (uint32_t)__builtin_popcount(m[w]); return c; }
+
 int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask) {
     GW_REQUIRE(s && case_mask && ctrl_mask, "gwasdev_select_case_control: NULL argument");
     GW_CUDA(cudaSetDevice(s->device));
     // member masks as 32-bit words; a sample flagged in both masks is a case for the compaction
     // (compressed_genotype_table5.cpp:541-561) but stays in both masks for the mask-on-the-fly overloads
-    std::vector<uint32_t> mca(s->Wr, 0), mco(s->Wr, 0), mco_sel(s->Wr, 0);
-    uint32_t nca = 0, nco = 0;
-    for (uint32_t c = 0; c < s->N; ++c) {
-        const bool is_ca = (case_mask[c >> 4] >> (c & 15)) & 1, is_co = (ctrl_mask[c >> 4] >> (c & 15)) & 1;
-        if (is_ca) { mca[c >> 5] |= 1u << (c & 31); ++nca; }
-        else if (is_co) { mco_sel[c >> 5] |= 1u << (c & 31); ++nco; }
-        if (is_co) mco[c >> 5] |= 1u << (c & 31);
-    }
+    const uint32_t Wr = s->Wr;
+    std::vector<uint32_t> m(4ull * Wr);
+    uint32_t *mca = m.data(), *mco = mca + Wr, *mca_sel = mco + Wr, *mco_sel = mca_sel + Wr;
+    mask_words(case_mask, s->P, s->N, Wr, mca);
+    mask_words(ctrl_mask, s->P, s->N, Wr, mco);
+    for (uint32_t w = 0; w < Wr; ++w) { mca_sel[w] = mca[w]; mco_sel[w] = mco[w] & ~mca[w]; }
+    const uint32_t nca = count_bits(mca_sel, Wr), nco = count_bits(mco_sel, Wr);
     GW_REQUIRE(nca + nco > 0, "gwasdev_select_case_control: both masks are empty");
     invalidate_selection(s);
     s->n_case = nca;
     s->n_ctrl = nco;
+    s->n_fly_case = nca;
+    s->n_fly_ctrl = count_bits(mco, Wr);
     s->Pca = plane_blocks(nca);
     s->Pco = plane_blocks(nco);
     s->Kc = (nca + 31) / 32;
     s->Kt = (nco + 31) / 32;
     s->Wc = round_up(std::max(s->Kc, 1u), 4);
     s->Wt = round_up(std::max(s->Kt, 1u), 4);
-    std::vector<uint32_t> bca, bco;
-    build_select_tables(mca, nca, s->Kc, bca);
-    build_select_tables(mco_sel, nco, s->Kt, bco);
-    GW_CUDA(reserve_raw(s->d_case_mask, s->cap_mask, s->Wr * 4ull));
-    { size_t cap2 = s->d_ctrl_mask ? s->cap_mask : 0; GW_CUDA(reserve_raw(s->d_ctrl_mask, cap2, s->Wr * 4ull)); }
-    GW_CUDA(reserve_raw(s->d_case_idx, s->cap_case_idx, bca.size() * 4));
-    GW_CUDA(reserve_raw(s->d_ctrl_idx, s->cap_ctrl_idx, bco.size() * 4));
-    { size_t cap3 = s->d_ctrl_sel_mask ? s->cap_mask : 0; GW_CUDA(reserve_raw(s->d_ctrl_sel_mask, cap3, s->Wr * 4ull)); }
-    GW_CUDA(cudaMemcpyAsync(s->d_case_mask, mca.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
-    GW_CUDA(cudaMemcpyAsync(s->d_ctrl_mask, mco.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
-    GW_CUDA(cudaMemcpyAsync(s->d_case_idx, bca.data(), bca.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    GW_CUDA(cudaMemcpyAsync(s->d_ctrl_idx, bco.data(), bco.size() * 4, cudaMemcpyHostToDevice, s->stream));
-    GW_CUDA(cudaMemcpyAsync(s->d_ctrl_sel_mask, mco_sel.data(), s->Wr * 4ull, cudaMemcpyHostToDevice, s->stream));
-    GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
+    // the four masks in one copy; K0's compress tables are built (host) and uploaded only if K0 ever runs
+    GW_CUDA(cudaMemcpyAsync(s->d_masks, m.data(), 4ull * Wr * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    GW_CUDA(cudaStreamSynchronize(s->stream));   // m goes out of scope
+    s->h_sel_masks.assign(mca_sel, mca_sel + 2ull * Wr);
     s->selected = true;
+    s->fly_valid = true;
     s->sel_built = false;
     s->scans_since_select = 0;
-    // Compaction (K0) is deferred until something needs the compacted layout (pairwise screen, layout probes, a
-    // second marginal scan): the first marginal scan after a selection counts through the masks on the raw rows,
-    // the reference's own mask-on-the-fly overload (compressed_genotype_table5.cpp:609-657), and needs no K0.
+    // Compaction (K0) is deferred until something needs the compacted layout (layout probes, the AND+POPC engine, a
+    // second marginal scan of a cohort with samples outside both classes): scans after a selection count through the
+    // masks on the raw rows, the reference's own mask-on-the-fly overload (compressed_genotype_table5.cpp:609-657).
     if (s->eager_select) return gwasdev_internal_ensure_compacted(s);
+    return GWASDEV_OK;
+}
+
+// Masks of the mask-on-the-fly overloads only (getCaseControlGenotypeDistribution(r, ccs, ..) :609-657,
+// getCaseControlContingencyTable(i, j, ccs, ..) :806-895): in the reference these never touch the pre-selected
+// m_cases_controls, so the selection, the compacted rows, the margins and the pairwise layouts all stay valid.
+int gwasdev_set_stream_masks(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask) {
+    GW_REQUIRE(s && case_mask && ctrl_mask, "gwasdev_set_stream_masks: NULL argument");
+    GW_CUDA(cudaSetDevice(s->device));
+    const uint32_t Wr = s->Wr;
+    std::vector<uint32_t> m(2ull * Wr);
+    mask_words(case_mask, s->P, s->N, Wr, m.data());
+    mask_words(ctrl_mask, s->P, s->N, Wr, m.data() + Wr);
+    s->n_fly_case = count_bits(m.data(), Wr);
+    s->n_fly_ctrl = count_bits(m.data() + Wr, Wr);
+    GW_CUDA(cudaMemcpyAsync(s->d_masks, m.data(), 2ull * Wr * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    GW_CUDA(cudaStreamSynchronize(s->stream));
+    s->fly_valid = true;
     return GWASDEV_OK;
 }
 
@@ -673,17 +725,28 @@ int gwasdev_internal_ensure_compacted(gwasdev_store *s) {
     GW_CUDA(cudaSetDevice(s->device));
     const uint32_t stride = 2 * (s->Wc + s->Wt);
     GW_CUDA(reserve_raw(s->d_sel, s->cap_sel, s->M * (uint64_t)stride * 4));
+    {   // compress tables of this selection (host arithmetic over the two masks, 0.05 ms at 10 000 samples)
+        std::vector<uint32_t> mca(s->h_sel_masks.begin(), s->h_sel_masks.begin() + s->Wr), mco(s->h_sel_masks.begin() + s->Wr, s->h_sel_masks.end());
+        std::vector<uint32_t> bca, bco;
+        build_select_tables(mca, s->n_case, s->Kc, bca);
+        build_select_tables(mco, s->n_ctrl, s->Kt, bco);
+        GW_CUDA(reserve_raw(s->d_case_idx, s->cap_case_idx, bca.size() * 4));
+        GW_CUDA(reserve_raw(s->d_ctrl_idx, s->cap_ctrl_idx, bco.size() * 4));
+        GW_CUDA(cudaMemcpyAsync(s->d_case_idx, bca.data(), bca.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        GW_CUDA(cudaMemcpyAsync(s->d_ctrl_idx, bco.data(), bco.size() * 4, cudaMemcpyHostToDevice, s->stream));
+        GW_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
+    }
     SelectTables ta, to;
     ta.m = s->d_case_idx; ta.mv = ta.m + s->Wr; ta.rank = ta.m + 6ull * s->Wr; ta.first = ta.rank + s->Wr + 1; ta.mvl = ta.first + std::max(s->Kc, 1u); ta.n_class = s->n_case; ta.Kout = s->Kc;
     to.m = s->d_ctrl_idx; to.mv = to.m + s->Wr; to.rank = to.m + 6ull * s->Wr; to.first = to.rank + s->Wr + 1; to.mvl = to.first + std::max(s->Kt, 1u); to.n_class = s->n_ctrl; to.Kout = s->Kt;
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    const bool trace = getenv("GWASDEV_TRACE") != nullptr;
+    const bool trace = s->opt[GWASDEV_OPT_TRACE] != 0;
     if (trace) cudaEventRecord(s->ev2, s->stream);
     constexpr int SNPS = 4;                                     // rows assembled per block iteration
     const size_t smem_rows = (size_t)SNPS * stride * sizeof(uint32_t);
     const size_t smem_tab = 2 * (7ull * s->Wr + 1) * sizeof(uint32_t);
-    if (s->Wr <= 1024 && !getenv("GWASDEV_SELECT_TABLE_KERNEL")) {   // register form: one thread per source column
+    if (s->Wr <= 1024 && s->opt[GWASDEV_OPT_SELECT_KERNEL] == 0) {   // register form: one thread per source column
         constexpr int CS = 8;
         const unsigned threads = round_up(s->Wr, 32);
         const size_t smem = (size_t)CS * stride * sizeof(uint32_t);

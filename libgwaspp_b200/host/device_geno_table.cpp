@@ -58,7 +58,7 @@ void CaseControlSet::setAllAsControls() {
 // ---- DeviceGenoTable -----------------------------------------------------------------------------
 DeviceGenoTable::DeviceGenoTable(int n_markers, int n_individuals, int device)
     : max_row(n_markers), max_column(n_individuals), store(nullptr), pending_first(0), pending_count(0),
-      selected_rev(0), selected_set(nullptr) {
+      selected_rev(0), selected_set(nullptr), fly_rev(0), fly_set(nullptr) {
     GW_MUST(gwasdev_create((uint64_t)n_markers, (uint32_t)n_individuals, device, &store));
     plane_blocks = gwasdev_plane_blocks((uint32_t)n_individuals);
     cell_row.resize(2 * plane_blocks + 1);
@@ -67,7 +67,8 @@ DeviceGenoTable::DeviceGenoTable(int n_markers, int n_individuals, int device)
 
 // table sized from and loaded with a transposed-PLINK genotype file in one pass (plain) or two (.gz), parsed on the device
 DeviceGenoTable::DeviceGenoTable(const std::string &tped_path, int device)
-    : max_row(0), max_column(0), store(nullptr), pending_first(0), pending_count(0), selected_rev(0), selected_set(nullptr) {
+    : max_row(0), max_column(0), store(nullptr), pending_first(0), pending_count(0), selected_rev(0), selected_set(nullptr),
+      fly_rev(0), fly_set(nullptr) {
     uint64_t rows = 0;
     uint32_t cols = 0;
     GW_MUST(gwasdev_create_from_tped(tped_path.c_str(), device, &store, &rows, &cols));
@@ -161,13 +162,19 @@ DataBlock DeviceGenoTable::operator()(int r, int c) {
 void DeviceGenoTable::selectCaseControl(CaseControlSet &ccs) {
     flush();
     GW_MUST(gwasdev_select_case_control(store, ccs.stream_case_begin(), ccs.stream_control_begin()));
-    selected_rev = ccs.revision();
-    selected_set = &ccs;
+    selected_rev = fly_rev = ccs.revision();      // a selection also sets the on-the-fly masks (to its own)
+    selected_set = fly_set = &ccs;
 }
 
+// Masks of the mask-on-the-fly overloads. As in the reference (compressed_genotype_table5.cpp:609-657, :806-895) these never
+// touch the pre-selected store: a caller may select with one set, probe on the fly with another and go on using the
+// pre-selected overloads.
 void DeviceGenoTable::ensureMasks(CaseControlSet &ccs) {
     flush();
-    if (selected_set != &ccs || selected_rev != ccs.revision()) selectCaseControl(ccs);
+    if (fly_set == &ccs && fly_rev == ccs.revision()) return;
+    GW_MUST(gwasdev_set_stream_masks(store, ccs.stream_case_begin(), ccs.stream_control_begin()));
+    fly_set = &ccs;
+    fly_rev = ccs.revision();
 }
 
 void DeviceGenoTable::selectMarker(uint) { assert(false); }            // as in the reference's bit-plane tables

@@ -84,6 +84,8 @@ private:
     std::vector<ushort> cell_row;         // scratch row for addGenotype
     uint64_t selected_rev;                // CaseControlSet revision currently compacted on the device
     const CaseControlSet *selected_set;
+    uint64_t fly_rev;                     // CaseControlSet whose masks the mask-on-the-fly overloads currently use
+    const CaseControlSet *fly_set;
     char call_buf[3];
 };
 

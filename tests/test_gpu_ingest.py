@@ -103,15 +103,14 @@ def test_messy_text_and_chunk_boundaries(orc, tmp_path, monkeypatch):
     assert gw.tped_dims(str(p)) == (M, N)
     for chunk in (None, 9000, 4097 * 3, 1000):                          # lines straddle chunks, newline blocks, both; 1000: shorter
                                                                         # than a line, the loader has to grow its buffers
-        if chunk:
-            monkeypatch.setenv("GWASDEV_INGEST_CHUNK", str(chunk))
         with gw.GenoStore(M, N) as st:
+            if chunk:
+                st.set_option(gw.OPT_INGEST_CHUNK, chunk)
             assert st.load_tped(str(p)) == M
             assert np.array_equal(st.get_rows(), want)
-        with gw.GenoStore.from_tped(str(p)) as st:                      # table sized by the loader itself, one pass
-            assert (st.n_snps, st.n_samples) == (M, N)
-            assert np.array_equal(st.get_rows(), want)
-    monkeypatch.delenv("GWASDEV_INGEST_CHUNK")
+    with gw.GenoStore.from_tped(str(p)) as st:                          # table sized by the loader itself, one pass
+        assert (st.n_snps, st.n_samples) == (M, N)
+        assert np.array_equal(st.get_rows(), want)
     # the same through the in-memory entry point, in three calls; an unterminated tail is left to the caller
     with gw.GenoStore(M, N) as st:
         row, pos = 0, 0

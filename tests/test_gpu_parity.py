@@ -28,12 +28,12 @@ def make_store(orc, codes, pheno=None):
 
 @pytest.mark.parametrize("k0", ["columns", "tables"])
 @pytest.mark.parametrize("name", COHORTS)
-def test_store_layout_roundtrip(orc, monkeypatch, name, k0):
-    if k0 == "tables":          # the table-driven compaction kernel (cohorts beyond 32 768 samples) on the same fixtures
-        monkeypatch.setenv("GWASDEV_SELECT_TABLE_KERNEL", "1")
+def test_store_layout_roundtrip(orc, name, k0):
     g = load_golden(name)
     codes, pheno = g["codes"], g["pheno"]
     with make_store(orc, codes) as st:
+        if k0 == "tables":      # the table-driven compaction kernel (cohorts beyond 32 768 samples) on the same fixtures
+            st.set_option(gw.OPT_SELECT_KERNEL, 1)
         assert np.array_equal(st.get_rows(), g["raw_rows"])                    # a5 layout incl. headers
         assert np.array_equal(st.get_rows(7, 5), g["raw_rows"][7:12])
         txt = {0: "AA", 1: "AC", 2: "CC", 3: "00"}
@@ -82,14 +82,12 @@ def test_marginal_scan_matches_reference_golden(orc, name):
         assert np.array_equal(whole[:, 3], codes.shape[1] - g["whole"][:, :3].sum(1))   # what inline_maf_print prints
 
 
-@pytest.mark.parametrize("N,cfg", [(677, None), (2000, "3,3,16"), (3900, "2,3,32"), (130, "4,2,8"), (1111, "6,2,16")])
-def test_fused_select_scan_equals_compacted_scan(orc, monkeypatch, N, cfg):
+@pytest.mark.parametrize("N,lanes", [(677, 0), (2000, 16), (3900, 32), (130, 8), (1111, 16)])
+def test_fused_select_scan_equals_compacted_scan(orc, N, lanes):
     """The first scan after a selection counts through the masks on the raw rows (no compaction, the reference's
     mask-on-the-fly overload compressed_genotype_table5.cpp:609-657); later scans stream the compacted rows (:703-747).
     Both must give the oracle's counts and bit-identical statistics -- also when samples belong to neither class or are
     flagged in both masks (a case for the compaction, :541-561), and for every lane-group width of the kernels."""
-    if cfg:
-        monkeypatch.setenv("GWASDEV_MSCAN_CFG", cfg)             # loads in flight, CTAs per SM, lanes per row
     M = 301
     codes, _ = orc.simulate(77 + N, M, N, N // 2, missing_rate=0.03)
     rng = np.random.default_rng(N)
@@ -108,6 +106,7 @@ def test_fused_select_scan_equals_compacted_scan(orc, monkeypatch, N, cfg):
         eager.set_select_mode(True)
         outs = []
         for st in (lazy, eager):
+            st.set_option(gw.OPT_LANES_PER_ROW, lanes)            # lanes cooperating on one row (0: chosen from the row length)
             st.put_rows(rows)
             st.select_case_control(case_mask=ca, ctrl_mask=co)
             assert (st.n_case, st.n_ctrl) == (nca, nco)
