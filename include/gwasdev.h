@@ -258,6 +258,27 @@ GWASDEV_API int gwasdev_pair_tables(gwasdev_store *s, uint64_t n, const uint32_t
 GWASDEV_API int gwasdev_pairwise_scan(gwasdev_store *s, double threshold, uint32_t shard, uint32_t n_shards,
                           gwasdev_hit *hits, uint64_t capacity, uint64_t *n_hits,
                           gwasdev_pair_stats *stats, int on_device);
+/* The same screen with a bounded result: the top_k pairs with the largest statistic above the threshold (ties at the k-th
+ * place go to the smaller (i, j)), sorted by (i, j); hits holds top_k records. computeBoost keeps every pair above its
+ * threshold in an unbounded vector (epistasis_func.cpp:388, :482-484); with a low threshold or real data that list has
+ * no useful bound, this one does: the kernels raise a device-wide threshold as soon as k better pairs have been seen, so
+ * the candidate buffer needs room for a few times k whatever the threshold. Sharded runs return each shard's top_k; the
+ * top_k of their union is the global answer (gwasdev_pairwise_scan_multi does that). */
+GWASDEV_API int gwasdev_pairwise_topk(gwasdev_store *s, double threshold, uint64_t top_k, uint32_t shard, uint32_t n_shards,
+                          gwasdev_hit *hits, uint64_t *n_hits, gwasdev_pair_stats *stats, int on_device);
+/* ---- several devices, one host process (the multi-GPU driver a C++ caller reaches) -------------------------------------
+ * Copy of a store on another device: headers and raw rows travel device to device (NVLink when peer access is available),
+ * options, engine choice and the current selection are re-applied. What a caller does after loading the genotype file once. */
+GWASDEV_API int gwasdev_replicate(gwasdev_store *src, int device, gwasdev_store **out);
+/* computeBoost's pre-screen (algorithms/epistasis_func.cpp:397-486) over n_stores stores that hold the same table and
+ * selection on n_stores different devices: store d runs shard d of n_stores of the tile-pair schedule on its own host thread
+ * (as gwasdev_pairwise_scan / gwasdev_pairwise_topk would), the fixed-size hit records are combined with one ncclAllGather
+ * (gather = 0; NCCL is loaded at run time, communicators are created once per device list) or with peer copies to
+ * stores[0]'s device (gather = 1), and that device merges them: hits[0..*n_hits) in host memory, sorted by (i, j) -- the
+ * top_k largest statistics when top_k != 0, every pair above the threshold otherwise (capacity as for gwasdev_pairwise_scan).
+ * stats (may be NULL) receives n_stores records, one per shard. Identical to the single-device result. */
+GWASDEV_API int gwasdev_pairwise_scan_multi(gwasdev_store *const *stores, uint32_t n_stores, double threshold, uint64_t top_k,
+                                gwasdev_hit *hits, uint64_t capacity, uint64_t *n_hits, gwasdev_pair_stats *stats, int gather);
 /* Engine for the tile pairs without missing calls. 0 (default): tensor cores (tcgen05 kind::i8 GEMM over signed
  * one-hot bytes, pairwise_mma.cu) when n_case < 16384 and n_ctrl < 131072, else AND+POPC tiles; 1: AND+POPC
  * tiles; 2: tensor cores or GWASDEV_EINVAL. Tile pairs with missing calls (the reference's other branch,

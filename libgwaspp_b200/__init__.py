@@ -62,7 +62,8 @@ ABI_SYMBOLS = [
     "gwasdev_ksa_screen_mma_f32", "gwasdev_pack_row_text_block", "gwasdev_simulate_block", "gwasdev_marginal_accumulate",
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
     "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs", "gwasdev_create_from_tped",
-    "gwasdev_set_option", "gwasdev_set_stream_masks", "gwasdev_marginal_scan_compact",
+    "gwasdev_set_option", "gwasdev_set_stream_masks", "gwasdev_marginal_scan_compact", "gwasdev_pairwise_topk",
+    "gwasdev_replicate", "gwasdev_pairwise_scan_multi",
 ]
 
 
@@ -103,6 +104,9 @@ def load_library():
     L.gwasdev_counts.argtypes = [vp, u64, u64, i32, vp]
     L.gwasdev_pair_tables.argtypes = [vp, u64, vp, vp, i32, vp]
     L.gwasdev_pairwise_scan.argtypes = [vp, C.c_double, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(PairStats), i32]
+    L.gwasdev_pairwise_topk.argtypes = [vp, C.c_double, u64, u32, u32, vp, C.POINTER(u64), C.POINTER(PairStats), i32]
+    L.gwasdev_replicate.argtypes = [vp, i32, C.POINTER(vp)]
+    L.gwasdev_pairwise_scan_multi.argtypes = [C.POINTER(vp), u32, C.c_double, u64, vp, u64, C.POINTER(u64), C.POINTER(PairStats), i32]
     L.gwasdev_ksa.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_ksa_screen_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_gtest.argtypes = [vp, u64, vp, vp, vp, vp]
@@ -231,6 +235,24 @@ def bed_dims(path: str, n_samples: int) -> int:
 
 def launch_count() -> int:
     return int(load_library().gwasdev_launch_count())
+
+
+def pairwise_scan_multi(stores, threshold: float = 30.0, top_k: int = 0, capacity: int = 1 << 20, gather: str = "nccl"):
+    """One process, len(stores) devices: every store runs its shard of the tile-pair schedule on its own host thread
+    inside the library and the hit records are combined over NVLink (NCCL all-gather, or peer copies with gather="peer").
+    Returns (hits[HIT_DTYPE] sorted by (i, j), [PairStats per shard])."""
+    L = load_library()
+    n = len(stores)
+    arr = (C.c_void_p * n)(*[st.h for st in stores])
+    stats = (PairStats * n)()
+    cap = top_k if top_k else capacity
+    hits = np.zeros(cap, HIT_DTYPE)
+    got = C.c_uint64()
+    rc = L.gwasdev_pairwise_scan_multi(arr, n, threshold, top_k, _ptr(hits), cap, C.byref(got), stats, {"nccl": 0, "peer": 1}[gather])
+    if rc == 4 and not top_k:   # GWASDEV_EOVERFLOW: grow and retry once
+        return pairwise_scan_multi(stores, threshold, top_k, int(got.value), gather)
+    _check(rc, "gwasdev_pairwise_scan_multi")
+    return hits[: got.value].copy(), list(stats)
 
 
 class GenoStore:
@@ -487,6 +509,28 @@ class GenoStore:
         ll, p = np.zeros(len(pi)), np.zeros(len(pi))
         _check(self.L.gwasdev_epi_pairs(self.h, len(pi), _ptr(pi), _ptr(pj), mode, _ptr(ll), _ptr(p)), "gwasdev_epi_pairs")
         return ll, p
+
+    def pairwise_topk(self, top_k: int, threshold: float = 30.0, shard: int = 0, n_shards: int = 1, hits=None, on_device: bool = False):
+        """The top_k pairs with the largest statistic above `threshold`, sorted by (i, j): (hits, PairStats)."""
+        st = PairStats()
+        n = C.c_uint64()
+        own = hits is None
+        if own:
+            assert not on_device
+            hits = np.zeros(top_k, HIT_DTYPE)
+        _check(self.L.gwasdev_pairwise_topk(self.h, threshold, top_k, shard, n_shards, _ptr(hits), C.byref(n), C.byref(st),
+                                            1 if on_device else 0), "gwasdev_pairwise_topk")
+        return (hits[: n.value].copy() if own else int(n.value)), st
+
+    def replicate(self, device: int) -> "GenoStore":
+        """Copy of this store (table, options, selection) on another device of the same process."""
+        other = GenoStore.__new__(GenoStore)
+        other.L = self.L
+        other.h = C.c_void_p()
+        _check(self.L.gwasdev_replicate(self.h, device, C.byref(other.h)), "gwasdev_replicate")
+        other.n_snps, other.n_samples, other.device, other.P = self.n_snps, self.n_samples, device, self.P
+        other.n_case, other.n_ctrl = self.n_case, self.n_ctrl
+        return other
 
     def pairwise_scan(self, threshold: float = 30.0, shard: int = 0, n_shards: int = 1, capacity: int = 1 << 20,
                       hits=None, on_device: bool = False):

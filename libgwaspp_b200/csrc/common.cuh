@@ -144,6 +144,7 @@ struct gwasdev_store {
     bool fly_valid = false;                                            // on-the-fly masks uploaded (by a selection or gwasdev_set_stream_masks)
     uint32_t n_fly_case = 0, n_fly_ctrl = 0;                           // members of the on-the-fly masks as given (reference: ccs.getCaseCount() / getControlCount())
     std::vector<uint32_t> h_sel_masks;                                 // host copy of the selection masks [2][Wr]: K0's tables are built from it on demand
+    std::vector<uint16_t> h_given_masks;                               // the selection's stream masks as given [2][P] (gwasdev_replicate re-applies them)
     // per-SNP totals over ALL samples (|p1|, |p2|, |p1 & p2|, 0), independent of the phenotype: when the classes partition the
     // cohort the control counts are totals - case counts, so a re-selection's scan needs three masked popcount streams only
     uint4 *d_row_tot = nullptr;
@@ -201,12 +202,14 @@ struct gwasdev_store {
     Scratch sc_cnt, sc_cand, sc_keys, sc_keys2, sc_vals, sc_vals2, sc_sort, sc_hits;   // pairwise scan
     Scratch sc_pi, sc_pj, sc_a, sc_b;                        // pair probes
     Scratch sc_stage;                                        // row upload / download staging
+    Scratch sc_gather;                                       // multi-device driver: the shards' hit records after the gather
     unsigned long long *h_cnt = nullptr;                     // pinned host counters
     void *ingest = nullptr;                                  // file / text ingestion state (ingest.cu)
 
     long long opt[GWASDEV_OPT_COUNT] = {};                   // gwasdev_set_option (explicit knobs; the library reads no environment variables)
 
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;   // ev0..ev1: last marginal scan; ev2..ev3: last pair screen
+    cudaEvent_t ev_pw = nullptr;                                               // end of the last pairwise scan (its total_ms)
     static constexpr int MAX_PIECES = 8;                     // host-output scans: pieces whose copies overlap the next piece's scan
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_piece[MAX_PIECES] = {};

@@ -8,6 +8,56 @@ namespace gwasdev {
 
 struct Candidate { uint32_t i, j; float stat; uint32_t pad; };
 
+// Where the screen kernels put the pairs that pass their fp32 test. Threshold mode (hist == nullptr): every pair above
+// `thr` (= threshold - margin) is appended; the host re-runs with a larger buffer if it overflowed. Top-k mode: the
+// kernels also keep a histogram of the appended statistics, and whenever the buffer passes a fill mark one thread
+// raises a device-wide threshold to the lower edge of the bin above which k candidates have already been seen (minus
+// `slack`, twice the fp32 error budget: the final choice is made on the fp64 re-scores) -- a pair below it can no
+// longer be among the k best, so the buffer stops growing however low the caller's threshold is.
+constexpr int CAND_HIST_BINS = 2048;
+struct CandSink {
+    Candidate *cand;
+    unsigned long long *n_cand;       // pairs appended so far (may exceed cap)
+    unsigned long long cap;
+    float thr;                        // static floor
+    uint32_t *hist;                   // [CAND_HIST_BINS] of width hist_w from thr up, last bin open-ended; nullptr: threshold mode
+    float *thr_dyn;                   // current device-wide threshold
+    int *lost_max;                    // largest statistic (float bits, >= 0) among the pairs that found the buffer full
+    float hist_w, slack;
+    unsigned long long k_keep;
+    unsigned long long raise_from, raise_mask;   // raise when slot + 1 >= raise_from and ((slot + 1) & raise_mask) == 0
+};
+
+// threshold the pairs of the next tile are tested against
+__device__ __forceinline__ float sink_threshold(const CandSink &s) {
+    if (!s.hist) return s.thr;
+    float t;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(t) : "l"(s.thr_dyn) : "memory");
+    return fmaxf(t, s.thr);
+}
+static __device__ __noinline__ void sink_raise(const uint32_t *hist, float *thr_dyn, float thr, float hist_w, float slack, unsigned long long k_keep) {
+    unsigned long long acc = 0;
+    for (int b = CAND_HIST_BINS - 1; b >= 0; --b) {
+        acc += *reinterpret_cast<const volatile uint32_t *>(hist + b);
+        if (acc >= k_keep) {
+            const float t = thr + (float)b * hist_w - slack;
+            if (t > thr && t > 0.f) atomicMax(reinterpret_cast<int *>(thr_dyn), __float_as_int(t));   // positive floats order like ints
+            return;
+        }
+    }
+}
+// append pair (i, j); the caller has checked stat > sink_threshold
+__device__ __forceinline__ void sink_push(const CandSink &s, uint32_t i, uint32_t j, float stat) {
+    if (s.hist) {
+        const int b = min(max((int)((stat - s.thr) / s.hist_w), 0), CAND_HIST_BINS - 1);
+        atomicAdd(s.hist + b, 1u);
+    }
+    const unsigned long long slot = atomicAdd(s.n_cand, 1ull);
+    if (slot < s.cap) { Candidate cd; cd.i = i; cd.j = j; cd.stat = stat; cd.pad = 0; s.cand[slot] = cd; }
+    else if (s.hist) atomicMax(s.lost_max, __float_as_int(fmaxf(stat, 0.f)));
+    if (s.hist && slot + 1 >= s.raise_from && ((slot + 1) & s.raise_mask) == 0) sink_raise(s.hist, s.thr_dyn, s.thr, s.hist_w, s.slack, s.k_keep);
+}
+
 // ---- PTX helpers (mbarrier + TMA) ----------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {

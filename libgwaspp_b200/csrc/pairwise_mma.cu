@@ -89,12 +89,9 @@ struct MmaParams {
     const MmaRowF *rowf;
     const MmaColF *colf;
     const uint8_t *tile_missing;   // per 64-SNP block
-    float thr, N;
+    float N;
     float qc, q0;               // upper-bound pre-filter: S <= qc * sum_ab c0^2/cab - q0 (see ksa_upper_bound)
-    float thr2;                 // thr / (2 ln 2): the bound pass compares in log2 units
-    Candidate *cand;
-    unsigned long long *n_cand;
-    uint64_t cap;
+    CandSink sink;
     uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only, rows of CTA `dump_rank`
     uint64_t dump_tile;
     uint32_t dump_rank;
@@ -488,7 +485,8 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                 A.C = __uint_as_float(r3.x);
                 if (pl) { float2 x = A.dA0; A.dA0 = A.dA2; A.dA2 = x; x = A.cm0; A.cm0 = A.cm2; A.cm2 = x; }
             }
-            const float thrA = p.thr2 + p.q0 + A.C;         // bound pass: N log2 tau + qc Q > thr2 + q0 + C_row + C_col
+            const float thr_now = sink_threshold(p.sink);
+            const float thrA = thr_now / 1.3862943611f + p.q0 + A.C;   // bound pass, log2 units: N log2 tau + qc Q > thr / (2 ln 2) + q0 + C_row + C_col
             // interior tile: every pair is i < j inside the table and no block has missing calls
             const bool interior = (uint64_t)(I + 1) * MMA_A_SNPS <= (uint64_t)J * MMA_B_SNPS && (uint64_t)(J + 1) * MMA_B_SNPS <= p.M &&
                                   !p.tile_missing[I] && !p.tile_missing[2 * J] && !p.tile_missing[2 * J + 1];
@@ -583,10 +581,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                         float tau;
                         (void)ksa_upper_bound(t, pca, w, Crow + Ccol, p.N, p.qc, p.q0, tau);
                         const float stat = ksa_screen_cells(t, tau, Crow + Ccol, p.N);
-                        if (stat > p.thr) {
-                            const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
-                            if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
-                        }
+                        if (stat > thr_now) sink_push(p.sink, (uint32_t)gi, (uint32_t)gj, stat);
                     }
                 }
             }
@@ -666,10 +661,8 @@ struct Mma4Params {
     uint32_t shard, n_shards;
     const PairSide *side;
     const uint8_t *tile_missing;   // per 64-SNP block
-    float thr, N, lnN;
-    Candidate *cand;
-    unsigned long long *n_cand;
-    uint64_t cap;
+    float N, lnN;
+    CandSink sink;
 };
 
 __device__ __forceinline__ uint32_t sel4(uint32_t k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -811,6 +804,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                 __syncwarp();
             }
             const PairSide &A = p.side[gi < p.M ? gi : 0];   // read through L1: 8 records per warp, reused for 16 B-SNPs
+            const float thr_now = sink_threshold(p.sink);
             if (lane == 0) mbar_wait_wd(&tfull[buf], TWOACC ? (uint32_t)(tile_it & 1) : (uint32_t)((tile_it >> 1) & 1));
             __syncwarp();
             tc_fence_after();
@@ -900,10 +894,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                         }
                     }
                     const float stat = ksa_screen_f32(n, A, B, p.N, p.lnN);
-                    if (stat > p.thr) {
-                        const unsigned long long slot = atomicAdd(p.n_cand, 1ull);
-                        if (slot < p.cap) { Candidate cd; cd.i = (uint32_t)gi; cd.j = (uint32_t)gj; cd.stat = stat; cd.pad = 0; p.cand[slot] = cd; }
-                    }
+                    if (stat > thr_now) sink_push(p.sink, (uint32_t)gi, (uint32_t)gj, stat);
                 }
             }
             tc_fence_before();
@@ -1235,7 +1226,8 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
     p.row = (const MmaRow *)s->d_mma_row; p.col = (const MmaCol *)s->d_mma_col; p.tile_missing = s->d_tile_missing;
     p.rowf = (const MmaRowF *)(p.row + Msnp); p.colf = (const MmaColF *)(p.col + Msnp);
     p.N = (float)(s->n_case + s->n_ctrl);
-    p.qc = s->mma_qc; p.q0 = s->mma_q0; p.thr2 = 0.f;
+    p.qc = s->mma_qc; p.q0 = s->mma_q0;
+    p.sink = CandSink{};
     p.dump = nullptr; p.dump_tile = 0; p.dump_rank = 0; p.prof = nullptr;
 }
 
@@ -1306,8 +1298,7 @@ uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uin
 }
 
 // Launches the four-plane tensor-core screen over this shard's tiles with missing calls. thr carries the fp32 margin.
-int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, int mode, void *cand,
-                                 unsigned long long *n_cand, uint64_t cap) {
+int gwasdev_internal_screen_mma4(gwasdev_store *s, const CandSink &sink, uint32_t shard, uint32_t n_shards, int mode) {
     int rc = ensure_mma4_inputs(s, mode);
     if (rc != GWASDEV_OK) return rc;
     Mma4Params p;
@@ -1315,8 +1306,8 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, ui
     p.case_kb = round_up(s->n_case, MMA_KB) / MMA_KB;
     p.shard = shard; p.n_shards = n_shards; p.side = s->d_side; p.tile_missing = s->d_tile_missing;
     const uint32_t n_ind = s->n_case + s->n_ctrl;
-    p.thr = thr; p.N = (float)n_ind; p.lnN = (float)std::log((double)n_ind);
-    p.cand = (Candidate *)cand; p.n_cand = n_cand; p.cap = cap;
+    p.N = (float)n_ind; p.lnN = (float)std::log((double)n_ind);
+    p.sink = sink;
     const uint64_t my_tiles = shard_tiles_before(p.n_tiles, shard, n_shards);
     if (my_tiles == 0) return GWASDEV_OK;
     int sms = 0;
@@ -1335,8 +1326,7 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, float thr, uint32_t shard, ui
 }
 
 // Launches the tensor-core screen for this shard's clean tiles. thr already carries the fp32 margin.
-int gwasdev_internal_screen_mma(gwasdev_store *s, float thr, uint32_t shard, uint32_t n_shards, void *cand,
-                                unsigned long long *n_cand, uint64_t cap) {
+int gwasdev_internal_screen_mma(gwasdev_store *s, const CandSink &sink, uint32_t shard, uint32_t n_shards) {
     const bool trace = s->opt[GWASDEV_OPT_TRACE] != 0;
     if (trace) cudaEventRecord(s->ev2, s->stream);
     int rc = ensure_mma_inputs(s);
@@ -1351,7 +1341,7 @@ int gwasdev_internal_screen_mma(gwasdev_store *s, float thr, uint32_t shard, uin
     fill_params(s, p, shard, n_shards);
     const uint64_t n_tiles = s->mm_tiles;
     p.n_tiles = n_tiles;
-    p.thr = thr; p.thr2 = thr / 1.3862943611f; p.cand = (Candidate *)cand; p.n_cand = n_cand; p.cap = cap;
+    p.sink = sink;
     const uint64_t my_tiles = shard_tiles_before(n_tiles, shard, n_shards);
     if (my_tiles == 0) return GWASDEV_OK;
     return launch_mma(s, p, my_tiles);
@@ -1390,7 +1380,6 @@ int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *
     GW_CUDA(reserve(s->sc_a, bytes));
     GW_CUDA(cudaMemsetAsync(s->sc_a.p, 0xff, bytes, s->stream));
     p.dump = (uint32_t *)s->sc_a.p; p.dump_tile = t; p.dump_rank = I & 1;
-    p.thr = 0.f; p.cand = nullptr; p.n_cand = nullptr; p.cap = 0;
     if ((rc = launch_mma(s, p, 1)) != GWASDEV_OK) return rc;
     GW_CUDA(cudaMemcpyAsync(out, s->sc_a.p, bytes, cudaMemcpyDeviceToHost, s->stream));
     GW_CUDA(cudaStreamSynchronize(s->stream));

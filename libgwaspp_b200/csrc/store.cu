@@ -348,6 +348,7 @@ int gwasdev_create(uint64_t n_snps, uint32_t n_samples, int device, gwasdev_stor
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev2);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev3);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_pw);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&s->h_cnt, 4 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         set_error("gwasdev_create: %s", cudaGetErrorString(e));
@@ -383,7 +384,7 @@ void gwasdev_destroy(gwasdev_store *s) {
     cudaFree(s->d_mm); cudaFree(s->d_mm4); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col);
     for (gwasdev_store::Scratch *sc : {&s->sc_out_counts, &s->sc_out_stats, &s->sc_out_mi, &s->sc_cnt, &s->sc_cand, &s->sc_keys,
                                       &s->sc_keys2, &s->sc_vals, &s->sc_vals2, &s->sc_sort, &s->sc_hits, &s->sc_pi, &s->sc_pj,
-                                      &s->sc_a, &s->sc_b, &s->sc_stage})
+                                      &s->sc_a, &s->sc_b, &s->sc_stage, &s->sc_gather})
         free_scratch(*sc);
     if (s->h_cnt) cudaFreeHost(s->h_cnt);
     cudaFree(s->d_hdr); cudaFree(s->d_raw);
@@ -391,6 +392,7 @@ void gwasdev_destroy(gwasdev_store *s) {
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
     if (s->ev3) cudaEventDestroy(s->ev3);
+    if (s->ev_pw) cudaEventDestroy(s->ev_pw);
     for (cudaEvent_t e : s->ev_piece) if (e) cudaEventDestroy(e);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
@@ -655,6 +657,8 @@ int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, con
     GW_CUDA(cudaMemcpyAsync(s->d_masks, m.data(), 4ull * Wr * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaStreamSynchronize(s->stream));   // m goes out of scope
     s->h_sel_masks.assign(mca_sel, mca_sel + 2ull * Wr);
+    s->h_given_masks.assign(case_mask, case_mask + s->P);
+    s->h_given_masks.insert(s->h_given_masks.end(), ctrl_mask, ctrl_mask + s->P);
     s->selected = true;
     s->fly_valid = true;
     s->sel_built = false;

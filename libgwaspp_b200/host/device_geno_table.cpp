@@ -3,7 +3,9 @@
 
 #include <cassert>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace libgwaspp {
 namespace genetics {
@@ -58,7 +60,7 @@ void CaseControlSet::setAllAsControls() {
 // ---- DeviceGenoTable -----------------------------------------------------------------------------
 DeviceGenoTable::DeviceGenoTable(int n_markers, int n_individuals, int device)
     : max_row(n_markers), max_column(n_individuals), store(nullptr), pending_first(0), pending_count(0),
-      selected_rev(0), selected_set(nullptr), fly_rev(0), fly_set(nullptr) {
+      selected_rev(0), selected_set(nullptr), fly_rev(0), fly_set(nullptr), device0(device), n_devices(1), replica_rev(0) {
     GW_MUST(gwasdev_create((uint64_t)n_markers, (uint32_t)n_individuals, device, &store));
     plane_blocks = gwasdev_plane_blocks((uint32_t)n_individuals);
     cell_row.resize(2 * plane_blocks + 1);
@@ -68,7 +70,7 @@ DeviceGenoTable::DeviceGenoTable(int n_markers, int n_individuals, int device)
 // table sized from and loaded with a transposed-PLINK genotype file in one pass (plain) or two (.gz), parsed on the device
 DeviceGenoTable::DeviceGenoTable(const std::string &tped_path, int device)
     : max_row(0), max_column(0), store(nullptr), pending_first(0), pending_count(0), selected_rev(0), selected_set(nullptr),
-      fly_rev(0), fly_set(nullptr) {
+      fly_rev(0), fly_set(nullptr), device0(device), n_devices(1), replica_rev(0) {
     uint64_t rows = 0;
     uint32_t cols = 0;
     GW_MUST(gwasdev_create_from_tped(tped_path.c_str(), device, &store, &rows, &cols));
@@ -79,13 +81,43 @@ DeviceGenoTable::DeviceGenoTable(const std::string &tped_path, int device)
     call_buf[0] = call_buf[1] = call_buf[2] = 0;
 }
 
-DeviceGenoTable::~DeviceGenoTable() { gwasdev_destroy(store); }
+DeviceGenoTable::~DeviceGenoTable() { dropReplicas(); gwasdev_destroy(store); }
+
+void DeviceGenoTable::dropReplicas() {
+    for (gwasdev_store *r : replicas) gwasdev_destroy(r);
+    replicas.clear();
+    replica_rev = 0;
+}
+
+void DeviceGenoTable::useDevices(int n) {
+    assert(n >= 1 && device0 + n <= gwasdev_device_count());
+    if (n != n_devices) dropReplicas();
+    n_devices = n;
+}
+
+// replicas of the table on devices device0 + 1 .. device0 + n_devices - 1, carrying the current selection
+void DeviceGenoTable::syncReplicas() {
+    if (n_devices <= 1) return;
+    assert(selected_set != nullptr && selected_rev != 0);
+    if (replicas.empty()) {
+        for (int d = 1; d < n_devices; ++d) {
+            gwasdev_store *r = nullptr;
+            GW_MUST(gwasdev_replicate(store, device0 + d, &r));      // table + selection, device to device
+            replicas.push_back(r);
+        }
+    } else if (replica_rev != selected_rev) {
+        CaseControlSet &ccs = *const_cast<CaseControlSet *>(selected_set);
+        for (gwasdev_store *r : replicas) GW_MUST(gwasdev_select_case_control(r, ccs.stream_case_begin(), ccs.stream_control_begin()));
+    }
+    replica_rev = selected_rev;
+}
 
 void DeviceGenoTable::flush() {
     if (pending_count == 0) return;
     GW_MUST(gwasdev_put_rows(store, (uint64_t)pending_first, (uint64_t)pending_count, pending.data()));
     pending_count = 0;
     selected_rev = 0;
+    dropReplicas();
 }
 
 int DeviceGenoTable::loadTransposedPlink(const std::string &tped_path, int first_row) {
@@ -93,6 +125,7 @@ int DeviceGenoTable::loadTransposedPlink(const std::string &tped_path, int first
     uint64_t rows = 0;
     GW_MUST(gwasdev_load_tped(store, tped_path.c_str(), (uint64_t)first_row, &rows));
     selected_rev = 0;
+    dropReplicas();
     return (int)rows;
 }
 
@@ -101,6 +134,7 @@ int DeviceGenoTable::loadBed(const std::string &bed_path, const std::vector<unsi
     uint64_t rows = 0;
     GW_MUST(gwasdev_load_bed(store, bed_path.c_str(), alleles.empty() ? nullptr : alleles.data(), (uint64_t)first_row, &rows));
     selected_rev = 0;
+    dropReplicas();
     return (int)rows;
 }
 
@@ -135,6 +169,7 @@ void DeviceGenoTable::addGenotype(int rIdx, int cIdx, const std::string &gt) {
     GW_MUST(gwasdev_pack_row_text(line.data(), line.size() - 1, (uint32_t)max_column, cell_row.data()));
     GW_MUST(gwasdev_put_rows(store, (uint64_t)rIdx, 1, cell_row.data()));
     selected_rev = 0;
+    dropReplicas();
 }
 
 static int allele_index(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; }
@@ -279,6 +314,31 @@ void DeviceGenoTable::scanCaseControl(std::vector<frequency_table> &cases, std::
 void DeviceGenoTable::screenPairs(double threshold, std::vector<gwasdev_hit> &hits, gwasdev_pair_stats *stats, uint shard, uint n_shards) {
     flush();
     uint64_t n = 0;
+    if (n_devices > 1) {     // all shards at once, one per device, inside the library
+        assert(shard == 0 && n_shards == 1);
+        syncReplicas();
+        std::vector<gwasdev_store *> all(1, store);
+        all.insert(all.end(), replicas.begin(), replicas.end());
+        std::vector<gwasdev_pair_stats> st(all.size());
+        if (hits.size() < (1u << 22)) hits.resize(1u << 22);
+        int rc = gwasdev_pairwise_scan_multi(all.data(), (uint32_t)all.size(), threshold, 0, hits.data(), hits.size(), &n, st.data(), 0);
+        if (rc == GWASDEV_EOVERFLOW) {
+            hits.resize((size_t)n);
+            rc = gwasdev_pairwise_scan_multi(all.data(), (uint32_t)all.size(), threshold, 0, hits.data(), hits.size(), &n, st.data(), 0);
+        }
+        GW_MUST(rc);
+        hits.resize((size_t)n);
+        if (stats) {         // totals over the shards; times are the slowest shard's
+            *stats = st[0];
+            for (size_t d = 1; d < st.size(); ++d) {
+                stats->pairs_tested += st[d].pairs_tested; stats->candidates += st[d].candidates; stats->word_cells += st[d].word_cells;
+                stats->tiles += st[d].tiles; stats->tiles_nine_cell += st[d].tiles_nine_cell;
+                stats->screen_ms = std::max(stats->screen_ms, st[d].screen_ms); stats->total_ms = std::max(stats->total_ms, st[d].total_ms);
+            }
+            stats->hits = n;
+        }
+        return;
+    }
     if (hits.size() < 1024) hits.resize(1024);
     int rc = gwasdev_pairwise_scan(store, threshold, shard, n_shards, hits.data(), hits.size(), &n, stats, 0);
     if (rc == GWASDEV_EOVERFLOW) {

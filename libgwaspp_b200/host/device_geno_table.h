@@ -69,6 +69,10 @@ public:
     void computeMargins(std::vector<marginal_information> &out);        // == algorithms::computeMargins over all rows
     void scanCaseControl(std::vector<frequency_table> &cases, std::vector<frequency_table> &controls,
                          std::vector<gwasdev_snp_stats> *stats = nullptr);
+    // n > 1: screenPairs runs on n devices of this process (this table's own and n - 1 replicas made over NVLink on first
+    // use), sharded by tile pairs inside the library, hits combined with an NCCL all-gather (gwasdev_pairwise_scan_multi)
+    void useDevices(int n);
+    int deviceCount() const { return n_devices; }
     void screenPairs(double threshold, std::vector<gwasdev_hit> &hits, gwasdev_pair_stats *stats = nullptr,
                      uint shard = 0, uint n_shards = 1);
     void gtestPairs(const std::vector<gwasdev_hit> &hits, std::vector<double> &stat, std::vector<double> &z);
@@ -87,6 +91,11 @@ private:
     uint64_t fly_rev;                     // CaseControlSet whose masks the mask-on-the-fly overloads currently use
     const CaseControlSet *fly_set;
     char call_buf[3];
+    int device0, n_devices;
+    std::vector<gwasdev_store *> replicas;   // the same table on the other devices (multi-device screen)
+    uint64_t replica_rev;                  // selection revision the replicas carry (0: stale, rebuild)
+    void dropReplicas();
+    void syncReplicas();
 };
 
 }  // namespace genetics

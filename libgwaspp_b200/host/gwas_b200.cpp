@@ -17,7 +17,7 @@ using namespace libgwaspp::genetics;
 using namespace libgwaspp::algorithms;
 
 static void usage() {
-    std::cerr << "usage: gwas_b200 -g X.tped -p X.tfam [-o out] [--device N] "
+    std::cerr << "usage: gwas_b200 -g X.tped -p X.tfam [-o out] [--device N] [--devices N] [--comp-level 5] "
                  "(--test-inline-maf | --select-cc-maf | --inline-cc-maf | --dist-perform | --test-boost-epi | "
                  "--contin-debug | --contin-perform | --contin-cc-perform | --epi-debug | --epi-perform)\n";
 }
@@ -78,7 +78,7 @@ static int run_test(GeneticData &gd, const std::set<int> &cases, const std::set<
 
 int main(int argc, char **argv) {
     std::string geno, pheno, outfile, test;
-    int device = 0;
+    int device = 0, devices = 1, comp_level = 5;
     bool host_parse = false;
     for (int a = 1; a < argc; ++a) {
         std::string s = argv[a];
@@ -86,12 +86,29 @@ int main(int argc, char **argv) {
         else if ((s == "-p" || s == "--pheno") && a + 1 < argc) pheno = argv[++a];
         else if ((s == "-o" || s == "--output") && a + 1 < argc) outfile = argv[++a];
         else if (s == "--device" && a + 1 < argc) device = atoi(argv[++a]);
-        else if (s == "--comp-level" && a + 1 < argc) ++a;          // accepted for command-line compatibility
+        else if (s == "--devices" && a + 1 < argc) devices = atoi(argv[++a]);
+        else if (s == "--comp-level" && a + 1 < argc) comp_level = atoi(argv[++a]);
         else if (s == "--tplink") {}
         else if (s == "--host-parse") host_parse = true;
         else if (s.rfind("--", 0) == 0) test = s.substr(2);
     }
     if (geno.empty() || pheno.empty() || test.empty()) { usage(); return 1; }
+    // --comp-level picks the reference's HOST layout (src/test/gwas_basic.cpp:265; genetics/genetic_data.cpp:60-79). The
+    // device table replaces the bit-plane layouts 3 (2-bit blocks), 4 (three one-hot streams) and 5 (two streams), which
+    // give identical counts; the byte-per-genotype tables 0-2 are not on this path.
+    if (comp_level < 3 || comp_level > 5) {
+        std::cerr << "--comp-level " << comp_level << ": only the bit-plane levels 3, 4 and 5 are replaced by the device table" << std::endl;
+        return 1;
+    }
+    if (comp_level == 3 && (test == "test-boost-epi" || test == "contin-cc-perform")) {
+        // the reference's level-3 table has no margins overloads: compressed_genotype_table3.h:250, .cpp:850-856 assert(false)
+        std::cerr << "--comp-level 3 cannot run --" << test << ": the reference's 2-bit block table aborts in its margins overloads; use --comp-level 4 or 5" << std::endl;
+        return 1;
+    }
+    if (devices < 1 || device + devices > gwasdev_device_count()) {
+        std::cerr << "--devices " << devices << " from device " << device << ": " << gwasdev_device_count() << " CUDA devices visible" << std::endl;
+        return 1;
+    }
 
     std::set<int> cases, controls;
     int n_individs = 0;
@@ -122,6 +139,7 @@ int main(int argc, char **argv) {
             return 1;
         }
         std::cout << "Found " << gd_file.getGenotypedMarkersCount() << " markers" << std::endl;
+        gd_file.getGenotypeTable()->useDevices(devices);
         return run_test(gd_file, cases, controls, test, outfile);
     }
     uint64_t n_rows64 = 0;
@@ -171,5 +189,6 @@ int main(int argc, char **argv) {
             gd.addGenotypeRow(row++, buf.data(), buf.data() + buf.size(), '\t');
         }
     }
+    gd.getGenotypeTable()->useDevices(devices);
     return run_test(gd, cases, controls, test, outfile);
 }
