@@ -279,6 +279,9 @@ GWASDEV_API int gwasdev_replicate(gwasdev_store *src, int device, gwasdev_store 
  * stats (may be NULL) receives n_stores records, one per shard. Identical to the single-device result. */
 GWASDEV_API int gwasdev_pairwise_scan_multi(gwasdev_store *const *stores, uint32_t n_stores, double threshold, uint64_t top_k,
                                 gwasdev_hit *hits, uint64_t capacity, uint64_t *n_hits, gwasdev_pair_stats *stats, int gather);
+/* computeGTest (as gwasdev_gtest) on n given pairs, the list cut into one contiguous piece per store / device. */
+GWASDEV_API int gwasdev_gtest_multi(gwasdev_store *const *stores, uint32_t n_stores, uint64_t n, const uint32_t *pi, const uint32_t *pj,
+                        double *stat, double *z);
 /* Engine for the tile pairs without missing calls. 0 (default): tensor cores (tcgen05 kind::i8 GEMM over signed
  * one-hot bytes, pairwise_mma.cu) when n_case < 16384 and n_ctrl < 131072, else AND+POPC tiles; 1: AND+POPC
  * tiles; 2: tensor cores or GWASDEV_EINVAL. Tile pairs with missing calls (the reference's other branch,
@@ -287,6 +290,13 @@ GWASDEV_API int gwasdev_pairwise_scan_multi(gwasdev_store *const *stores, uint32
  * with one pair of planes per class (no missing calls) or one accumulator per class (missing calls). Results are
  * identical. */
 GWASDEV_API int gwasdev_set_pair_engine(gwasdev_store *s, int engine);
+/* Host arithmetic only (works without a device): the tile pairs (I <= J, as SNP-block indices) of the screen's schedule that
+ * `shard` of `n_shards` owns, in schedule order, and the pairs i < j < n_snps they cover. engine 2: the tensor-core
+ * schedule (128-SNP blocks, bands of 8 A-blocks, shards own alternating runs of 64 consecutive tiles); engine 1: the
+ * AND+POPC schedule (64-SNP blocks, row-major upper triangle, single tiles round-robin). tiles (may be NULL) receives
+ * min(*n_tiles, capacity) (I, J) pairs. */
+GWASDEV_API int gwasdev_shard_schedule(uint64_t n_snps, int engine, uint32_t shard, uint32_t n_shards, uint32_t *tiles, uint64_t capacity,
+                           uint64_t *n_tiles, uint64_t *n_pairs);
 /* Parity probe of the tensor-core engine: raw corner counts of one tile pair of its schedule (A-block I of 64
  * SNPs, B-block J of 128 SNPs, I/2 <= J): out[(a*128 + b)*8 + {0,1,2,3}] = cases AA_BB, AA_bb, aa_BB, aa_bb
  * (compressed_genotype_table5.cpp:1069-1083), +4: controls (:1118-1132). out holds 64*128*8 values. */
@@ -321,6 +331,11 @@ GWASDEV_API int gwasdev_epi_pairs(gwasdev_store *s, uint64_t n, const uint32_t *
 /* Register-only __popc throughput in 32-bit word-cells (AND+POPC) per second on `device`; the
  * integer-pipe roofline denominator of the pairwise screen. */
 GWASDEV_API int gwasdev_popc_peak(int device, double *word_cells_per_s, double *sm_clock_mhz);
+/* int8 tensor-core throughput of `device` with the screen kernel's own instruction (tcgen05.mma.cta_group::2.kind::i8,
+ * M = 256, N = 256, K = 32, operands resident in shared memory, accumulators in TMEM, no TMA traffic, no epilogue), in
+ * 1e12 operations per second at 2 operations per multiply-accumulate: the best launch (burst) and the mean over ~50 ms of
+ * back-to-back launches (sustained; may be NULL). The tensor-core roofline denominator of the pairwise screen. */
+GWASDEV_API int gwasdev_i8_peak(int device, double *tops_burst, double *tops_sustained);
 /* Read-only streaming bandwidth (GB/s) of a plain 128-bit-load kernel over `bytes` of HBM on `device`:
  * context for the marginal scan's roofline next to the driver-measured copy bandwidth. */
 GWASDEV_API int gwasdev_hbm_read_peak(int device, uint64_t bytes, double *gb_per_s);

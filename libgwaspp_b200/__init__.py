@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
     "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs", "gwasdev_create_from_tped",
     "gwasdev_set_option", "gwasdev_set_stream_masks", "gwasdev_marginal_scan_compact", "gwasdev_pairwise_topk",
-    "gwasdev_replicate", "gwasdev_pairwise_scan_multi",
+    "gwasdev_replicate", "gwasdev_pairwise_scan_multi", "gwasdev_shard_schedule", "gwasdev_i8_peak", "gwasdev_gtest_multi",
 ]
 
 
@@ -107,6 +107,7 @@ def load_library():
     L.gwasdev_pairwise_topk.argtypes = [vp, C.c_double, u64, u32, u32, vp, C.POINTER(u64), C.POINTER(PairStats), i32]
     L.gwasdev_replicate.argtypes = [vp, i32, C.POINTER(vp)]
     L.gwasdev_pairwise_scan_multi.argtypes = [C.POINTER(vp), u32, C.c_double, u64, vp, u64, C.POINTER(u64), C.POINTER(PairStats), i32]
+    L.gwasdev_shard_schedule.argtypes = [u64, i32, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.gwasdev_ksa.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_ksa_screen_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_gtest.argtypes = [vp, u64, vp, vp, vp, vp]
@@ -128,6 +129,8 @@ def load_library():
     L.gwasdev_ksa_screen_mma_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_pairwise_epi_test.argtypes = [i32, u64, vp, vp, vp, vp]
     L.gwasdev_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.gwasdev_i8_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.gwasdev_gtest_multi.argtypes = [C.POINTER(vp), u32, u64, vp, vp, vp, vp]
     L.gwasdev_hbm_read_peak.argtypes = [i32, u64, C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -204,6 +207,13 @@ def popc_peak(device: int = 0) -> tuple[float, float]:
     return r.value, mhz.value
 
 
+def i8_peak(device: int = 0) -> tuple[float, float]:
+    """(burst, sustained) int8 tensor-core TOP/s of the screen kernel's own MMA instruction on resident operands."""
+    a, b = C.c_double(), C.c_double()
+    _check(load_library().gwasdev_i8_peak(device, C.byref(a), C.byref(b)), "gwasdev_i8_peak")
+    return a.value, b.value
+
+
 def hbm_read_peak(device: int = 0, nbytes: int = 1 << 31) -> float:
     r = C.c_double()
     _check(load_library().gwasdev_hbm_read_peak(device, nbytes, C.byref(r)), "gwasdev_hbm_read_peak")
@@ -235,6 +245,28 @@ def bed_dims(path: str, n_samples: int) -> int:
 
 def launch_count() -> int:
     return int(load_library().gwasdev_launch_count())
+
+
+def gtest_multi(stores, pi, pj):
+    """computeGTest on the given pairs, split over the stores' devices (one host thread each inside the library)."""
+    L = load_library()
+    pi = np.ascontiguousarray(pi, np.uint32).ravel()
+    pj = np.ascontiguousarray(pj, np.uint32).ravel()
+    s, z = np.zeros(len(pi)), np.zeros(len(pi))
+    arr = (C.c_void_p * len(stores))(*[st.h for st in stores])
+    _check(L.gwasdev_gtest_multi(arr, len(stores), len(pi), _ptr(pi), _ptr(pj), _ptr(s), _ptr(z)), "gwasdev_gtest_multi")
+    return s, z
+
+
+def shard_schedule(n_snps: int, shard: int, n_shards: int, engine: int = 2):
+    """Tile pairs ((I, J) SNP-block indices, [n, 2]) the shard owns in the screen's schedule, and the pairs they cover: the
+    library's own enumeration (host arithmetic, no device needed). engine 2: tensor cores (128-SNP blocks), 1: AND+POPC (64)."""
+    L = load_library()
+    nt, npairs = C.c_uint64(), C.c_uint64()
+    _check(L.gwasdev_shard_schedule(n_snps, engine, shard, n_shards, None, 0, C.byref(nt), C.byref(npairs)), "gwasdev_shard_schedule")
+    tiles = np.zeros((nt.value, 2), np.uint32)
+    _check(L.gwasdev_shard_schedule(n_snps, engine, shard, n_shards, _ptr(tiles), nt.value, C.byref(nt), C.byref(npairs)), "gwasdev_shard_schedule")
+    return tiles, int(npairs.value)
 
 
 def pairwise_scan_multi(stores, threshold: float = 30.0, top_k: int = 0, capacity: int = 1 << 20, gather: str = "nccl"):

@@ -186,4 +186,27 @@ int gwasdev_pairwise_scan_multi(gwasdev_store *const *stores, uint32_t n_stores,
     return gwasdev_internal_merge_hits(s0, (const gwasdev_hit *)s0->sc_gather.p, n_stores, mx, found.data(), top_k, hits, capacity, n_hits);
 }
 
+// computeGTest (algorithms/epistasis_func.cpp:508-704) on n given pairs, the list cut into one contiguous piece per device.
+int gwasdev_gtest_multi(gwasdev_store *const *stores, uint32_t n_stores, uint64_t n, const uint32_t *pi, const uint32_t *pj, double *stat, double *z) {
+    GW_REQUIRE(stores && n_stores >= 1 && pi && pj && stat && z, "gwasdev_gtest_multi: NULL argument");
+    if (n == 0) return GWASDEV_OK;
+    std::vector<int> rcs(n_stores, GWASDEV_OK);
+    std::vector<std::string> errs(n_stores);
+    auto work = [&](uint32_t d) {
+        const uint64_t b = n * d / n_stores, e = n * (d + 1) / n_stores;
+        if (e == b) return;
+        rcs[d] = gwasdev_gtest(stores[d], e - b, pi + b, pj + b, stat + b, z + b);
+        if (rcs[d] != GWASDEV_OK) errs[d] = gwasdev_last_error();
+    };
+    if (n_stores == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t d = 0; d < n_stores; ++d) th.emplace_back(work, d);
+        for (auto &t : th) t.join();
+    }
+    for (uint32_t d = 0; d < n_stores; ++d)
+        if (rcs[d] != GWASDEV_OK) { set_error("device %d: %s", stores[d]->device, errs[d].c_str()); return rcs[d]; }
+    return GWASDEV_OK;
+}
+
 }  // extern "C"

@@ -603,6 +603,59 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
     }
 }
 
+// ---- tensor-core roofline probe ---------------------------------------------------------------------
+// The screen kernel's own instruction -- tcgen05.mma.cta_group::2.kind::i8, M = 256, N = 256, K = 32, operands in the
+// SWIZZLE_128B K-major layout, accumulators alternating between the two halves of TMEM -- issued back to back on
+// operands that stay resident in shared memory: no TMA traffic, no epilogue. What the pair of SMs can do when nothing
+// but the MMA pipe and its shared-memory operand reads is in the way; the denominator of roofline.tensor.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+i8_peak_kernel(uint32_t kblocks, uint32_t seed) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t *done = reinterpret_cast<uint64_t *>(sm + KB_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    // operands: signed one-hot-like bytes (0, +1, -128) as in the real matrix; the values do not matter for the rate
+    for (uint32_t q = tid; q < KB_BYTES / 4; q += blockDim.x) {
+        uint32_t h = (q + 1u) * 2654435761u ^ seed ^ (rank * 0x9E3779B9u);
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        uint32_t w = 0;
+        for (int b = 0; b < 4; ++b) { const uint32_t r = (h >> (8 * b)) & 7u; w |= (r == 0 ? 0x01u : (r == 1 ? 0x80u : 0u)) << (8 * b); }
+        reinterpret_cast<uint32_t *>(sm)[q] = w;
+    }
+    if (tid == 0) { mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores above -> async-proxy reads of the MMAs
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1 && lane == 0 && rank == 0) {
+        const uint64_t ad = umma_desc(base), bd = umma_desc(base + A_STAGE_BYTES);
+        for (uint32_t kb = 0; kb < kblocks; ++kb) {
+            const uint32_t d_addr = tmem_base + ((kb >> 4) & 1u) * ACC_COLS;      // 16 sample blocks per accumulator, then the other one
+#pragma unroll
+            for (int k = 0; k < MMA_KB / UMMA_K; ++k)
+                tc_mma_i8(d_addr, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (kb & 15u) != 0 || k != 0);
+        }
+        tc_commit_mc(done, 1);            // arrives on the leader's barrier once every MMA above has completed
+        mbar_wait_wd(done, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---- operand matrix: scan layout -> signed one-hot bytes ---------------------------------------------
 // One thread per (SNP, 32-sample word): 32 bytes of plane aa and 32 bytes of plane bb.
 __device__ __forceinline__ uint32_t spread4(uint32_t nibble) { return (nibble * 0x00204081u) & 0x01010101u; }   // bit i -> byte i
@@ -1137,6 +1190,8 @@ static int ensure_mma_inputs(gwasdev_store *s) {
 
 static uint64_t rect_pairs(uint64_t M, uint64_t i0, uint64_t i1, uint64_t j0, uint64_t j1) {   // pairs i<j, i in [i0,i1), j in [j0,j1), < M
     i1 = std::min(i1, M); j1 = std::min(j1, M);
+    if (i1 <= i0 || j1 <= j0) return 0;
+    if (i1 <= j0) return (i1 - i0) * (j1 - j0);     // rectangle entirely above the diagonal
     uint64_t n = 0;
     for (uint64_t i = i0; i < i1; ++i) { const uint64_t lo = std::max(j0, i + 1); if (j1 > lo) n += j1 - lo; }
     return n;
@@ -1349,10 +1404,84 @@ int gwasdev_internal_screen_mma(gwasdev_store *s, const CandSink &sink, uint32_t
 
 extern "C" {
 
+// Host arithmetic only (no device): the tile pairs of the screen's schedule that `shard` of `n_shards` owns, in schedule
+// order, and the pairs i < j < n_snps they cover. engine 2: tensor-core schedule (128-SNP blocks, bands of 8 A-blocks,
+// column-major inside a band, shards own alternating runs of 64 consecutive tiles); engine 1: AND+POPC schedule (64-SNP
+// blocks, row-major upper triangle, single tiles dealt round-robin).
+int gwasdev_shard_schedule(uint64_t n_snps, int engine, uint32_t shard, uint32_t n_shards, uint32_t *tiles, uint64_t capacity,
+                           uint64_t *n_tiles, uint64_t *n_pairs) {
+    GW_REQUIRE(n_snps >= 1 && n_shards >= 1 && shard < n_shards && (engine == 1 || engine == 2), "gwasdev_shard_schedule: bad argument");
+    uint64_t cnt = 0, pairs = 0;
+    auto take = [&](uint32_t I, uint32_t J, uint32_t blk) {
+        if (tiles && cnt < capacity) { tiles[2 * cnt] = I; tiles[2 * cnt + 1] = J; }
+        ++cnt;
+        pairs += rect_pairs(n_snps, (uint64_t)I * blk, (uint64_t)(I + 1) * blk, (uint64_t)J * blk, (uint64_t)(J + 1) * blk);
+    };
+    if (engine == 2) {
+        const uint32_t TB = (uint32_t)((n_snps + MMA_BLK - 1) / MMA_BLK), n_bands = (TB + BAND - 1) / BAND;
+        uint64_t t = 0;
+        for (uint32_t b = 0; b < n_bands; ++b) {
+            const uint32_t na = band_height(TB, b);
+            for (uint32_t J = BAND * b; J < TB; ++J)
+                for (uint32_t ii = 0; ii < column_height(na, J - BAND * b); ++ii, ++t)
+                    if (tile_in_shard(t, shard, n_shards)) take(BAND * b + ii, J, MMA_BLK);
+        }
+    } else {
+        const uint32_t T = (uint32_t)((n_snps + TILE - 1) / TILE);
+        uint64_t t = 0;
+        for (uint32_t I = 0; I < T; ++I)
+            for (uint32_t J = I; J < T; ++J, ++t)
+                if (t % n_shards == shard) take(I, J, TILE);
+    }
+    if (n_tiles) *n_tiles = cnt;
+    if (n_pairs) *n_pairs = pairs;
+    return GWASDEV_OK;
+}
+
 int gwasdev_set_pair_engine(gwasdev_store *s, int engine) {
     GW_REQUIRE(s != nullptr, "gwasdev_set_pair_engine: NULL store");
     GW_REQUIRE(engine >= 0 && engine <= 2, "gwasdev_set_pair_engine: engine %d (0 auto, 1 popcount, 2 tensor core)", engine);
     s->pair_engine = engine;
+    return GWASDEV_OK;
+}
+
+// int8 tensor-core throughput of this device with the screen kernel's instruction shape (i8_peak_kernel above):
+// *tops_burst = best launch, *tops_sustained = mean over ~50 ms of back-to-back launches (the SM clock drops under the
+// tensor cores' power draw), in 1e12 int8 operations per second (2 per multiply-accumulate, as vendors quote it).
+int gwasdev_i8_peak(int device, double *tops_burst, double *tops_sustained) {
+    GW_REQUIRE(tops_burst != nullptr, "gwasdev_i8_peak: NULL argument");
+    if (gwasdev_device_count() <= device || device < 0) { set_error("gwasdev_i8_peak: no CUDA device %d", device); return GWASDEV_ENODEVICE; }
+    GW_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const size_t smem = 1024 + KB_BYTES + 64;
+    GW_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned pairs = (unsigned)std::max(1, sms / 2);
+    const uint32_t kblocks = 16384;                                   // 65 536 MMAs per CTA pair: ~5 ms per launch
+    const double ops = 2.0 * (double)MMA_M * MMA_N * MMA_KB * (double)kblocks * pairs;
+    cudaEvent_t a, b;
+    GW_CUDA(cudaEventCreate(&a)); GW_CUDA(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {                               // warm-up + burst
+        GW_CUDA(cudaEventRecord(a));
+        i8_peak_kernel<<<2 * pairs, 128, smem>>>(kblocks, 12345u + rep);
+        GW_LAUNCHED();
+        GW_CUDA(cudaEventRecord(b));
+        GW_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        GW_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+    }
+    const int reps = 10;
+    GW_CUDA(cudaEventRecord(a));
+    for (int rep = 0; rep < reps; ++rep) { i8_peak_kernel<<<2 * pairs, 128, smem>>>(kblocks, 777u + rep); GW_LAUNCHED(); }
+    GW_CUDA(cudaEventRecord(b));
+    GW_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    GW_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tops_burst = best;
+    if (tops_sustained) *tops_sustained = ops * reps / (ms * 1e-3) / 1e12;
     return GWASDEV_OK;
 }
 

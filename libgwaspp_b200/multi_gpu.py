@@ -1,7 +1,11 @@
-"""Multi-GPU driver for the pairwise screen: one process per GPU (torch.distributed), the store replicated,
-64x64 SNP tile pairs dealt round-robin over the ranks (no data-path collective), hit lists combined with
-one all_gather at the end -- NCCL over NVLink on GPUs, gloo on CPU for the host-logic tests.
+"""One-process-per-GPU driver for the pairwise screen (torch.distributed): the store replicated on every rank, the
+tile-pair schedule of the screen cut into one shard per rank inside the library (gwasdev_pairwise_scan's shard
+arguments: the tensor-core engine deals runs of 64 consecutive 128x128-SNP tiles of its banded schedule, the AND+POPC
+engine single 64x64 tiles round-robin; `shard_tiles` asks the library for either), no data-path collective, hit lists
+combined with one all_gather at the end -- NCCL over NVLink on GPUs, gloo on CPU for the host-logic tests.
 
+The same split inside ONE process (a host thread per device, ncclAllGather of the hit records) is
+gwasdev_pairwise_scan_multi, which the C++ mirror and `gwas_b200 --devices N` use; this module is the torchrun form.
 The reference has no counterpart (single process, single thread); the work split follows SURVEY.md 8(e).
 """
 from __future__ import annotations
@@ -112,20 +116,13 @@ def marginal_scan_distributed(store, group=None, gather: bool = False, **kw):
     return (0, store.n_snps), {k: np.concatenate([p[k] for p in parts]) for k in out}
 
 
-def shard_tiles(n_snps: int, shard: int, n_shards: int, tile: int = 64):
-    """Tile pairs (I <= J) handled by `shard`: linear upper-triangular index t with t % n_shards == shard --
-    the same enumeration the screen kernel uses. Returns (list of (I, J), pairs covered)."""
-    T = (n_snps + tile - 1) // tile
-    out, pairs, t = [], 0, 0
-    for I in range(T):
-        mi = min(tile, n_snps - I * tile)
-        for J in range(I, T):
-            if t % n_shards == shard:
-                mj = min(tile, n_snps - J * tile)
-                out.append((I, J))
-                pairs += mi * (mi - 1) // 2 if I == J else mi * mj
-            t += 1
-    return out, pairs
+def shard_tiles(n_snps: int, shard: int, n_shards: int, engine: int = 2):
+    """Tile pairs (I <= J, SNP-block indices) `shard` handles and the pairs they cover, from the library's own schedule
+    (gwasdev_shard_schedule; host arithmetic, no GPU needed). engine 2 (default, tensor cores): blocks of 128 SNPs;
+    engine 1 (AND+POPC): blocks of 64. Returns (list of (I, J), pairs covered, SNPs per block)."""
+    import libgwaspp_b200 as gw
+    tiles, pairs = gw.shard_schedule(n_snps, shard, n_shards, engine)
+    return [(int(I), int(J)) for I, J in tiles], pairs, 128 if engine == 2 else 64
 
 
 def pairwise_scan_distributed(store, threshold: float = 30.0, group=None):

@@ -23,12 +23,12 @@ def _free_port():
 
 def _fake_hits(rank, world, n_snps=900):
     """Deterministic pseudo-hits living in this rank's tile shard."""
-    tiles, _ = mg.shard_tiles(n_snps, rank, world)
+    tiles, _, blk = mg.shard_tiles(n_snps, rank, world)          # the default (tensor-core) engine's schedule, from the library
     rng = np.random.default_rng(100 + rank)
     out = []
     for I, J in tiles[:: max(1, len(tiles) // 7)]:
-        i = I * 64 + int(rng.integers(0, 32))
-        j = J * 64 + 32 + int(rng.integers(0, 32))
+        i = I * blk + int(rng.integers(0, blk // 2))
+        j = J * blk + blk // 2 + int(rng.integers(0, blk // 2))
         if i < j < n_snps:
             out.append((i, j, 30.0 + float(rng.random()) * 10))
     return np.array(out, mg.HIT_DTYPE)
@@ -65,17 +65,23 @@ def test_gloo_gather_of_hits(world):
     assert np.all(np.diff(key) > 0)                                          # the reference's (i, j) emission order
 
 
-@pytest.mark.parametrize("n_snps,world", [(130, 2), (1000, 3), (64, 4), (50_000, 8), (4097, 5)])
-def test_shards_partition_the_pair_space(n_snps, world):
-    seen, total = set(), 0
+@pytest.mark.parametrize("n_snps,world,engine", [(130, 2, 1), (130, 2, 2), (1000, 3, 1), (1000, 3, 2), (64, 4, 2), (50_000, 8, 1), (50_000, 8, 2),
+                                                 (4097, 5, 1), (4097, 5, 2), (150_000, 8, 2), (20_000, 7, 2)])
+def test_shards_partition_the_pair_space(n_snps, world, engine):
+    """The library's own shard enumeration (both engines' schedules): disjoint, complete, every pair counted once,
+    and -- tensor-core engine -- balanced to one run of 64 tiles."""
+    seen, total, sizes = set(), 0, []
     for r in range(world):
-        tiles, pairs = mg.shard_tiles(n_snps, r, world)
+        tiles, pairs, blk = mg.shard_tiles(n_snps, r, world, engine)
+        assert all(I <= J for I, J in tiles)
         assert not (seen & set(tiles))
         seen |= set(tiles)
         total += pairs
-    T = (n_snps + 63) // 64
+        sizes.append(len(tiles))
+    T = (n_snps + blk - 1) // blk
     assert len(seen) == T * (T + 1) // 2
     assert total == n_snps * (n_snps - 1) // 2
+    assert max(sizes) - min(sizes) <= (64 if engine == 2 else 1)
 
 
 def test_merge_rejects_duplicates_and_orders_top_k():
