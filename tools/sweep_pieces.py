@@ -7,7 +7,7 @@ st = gw.GenoStore(M, N); st.simulate(20121127)
 pheno = gw.simulate_phenotype(20121127, N, NCASE); ca, co = gw.stream_masks(pheno)
 hc = torch.empty((M, 8), dtype=torch.int32, pin_memory=True); hs = torch.empty((M, 8), dtype=torch.float64, pin_memory=True)
 for pieces in (1, 2, 3, 4, 6, 8):
-    os.environ["GWASDEV_SCAN_PIECES"] = str(pieces)
+    st.set_option(gw.OPT_SCAN_PIECES, pieces)
     ts = []
     for it in range(12):
         torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -1,5 +1,5 @@
 """Times the pair screen alone on configs[2] (or --snps/--samples): prints the screen kernel's CUDA-event time.
-GWASDEV_MMA_DEBUG / GWASDEV_PAIR_ENGINE select kernel variants (diagnostics only; results are not checked here)."""
+--engine 1 times the AND+POPC engine, --lib another build of the library (A/B)."""
 import argparse
 import os
 import sys
@@ -16,6 +16,7 @@ ap.add_argument("--cases", type=int, default=0)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--shards", type=int, default=1)
 ap.add_argument("--missing", type=float, default=0.0, help="per-genotype missing rate of the synthetic cohort")
+ap.add_argument("--engine", type=int, default=0)
 ap.add_argument("--lib", default="", help="alternative libgwasdev.so (A/B timing of kernel variants)")
 a = ap.parse_args()
 if a.lib:
@@ -24,6 +25,7 @@ ncase = a.cases or a.samples // 2
 with gw.GenoStore(a.snps, a.samples) as st:
     st.simulate(20121127, missing_rate=a.missing)
     st.select_case_control(gw.simulate_phenotype(20121127, a.samples, ncase))
+    st.set_pair_engine(a.engine)
     for r in range(a.reps):
         hits, s = st.pairwise_scan(30.0, shard=0, n_shards=a.shards)
         print(f"rep {r}: engine {s.engine} tiles {s.tiles} (9-cell {s.tiles_nine_cell}) screen {s.screen_ms:.3f} ms total {s.total_ms:.3f} ms pairs {s.pairs_tested} "

@@ -1,4 +1,4 @@
-"""Phase trace of the pairwise e2e step of bench.py (select -> pairwise_scan -> gtest) at configs[2]; run with GWASDEV_TRACE=1."""
+"""Phase trace of the pairwise e2e step of bench.py (select -> pairwise_scan -> gtest) at configs[2] (or --cfg3: configs[3]); the library prints its phase times (GWASDEV_OPT_TRACE)."""
 import os
 import sys
 import time
@@ -6,8 +6,9 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import libgwaspp_b200 as gw  # noqa: E402
 
-M, N, NC = 50000, 4000, 2000
+M, N, NC = (500000, 10000, 5000) if "--cfg3" in sys.argv else (50000, 4000, 2000)
 st = gw.GenoStore(M, N)
+st.set_option(gw.OPT_TRACE, 1)
 st.simulate(20121127)
 ph = gw.simulate_phenotype(20121127, N, NC)
 cm, km = gw.stream_masks(ph)
