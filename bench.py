@@ -192,6 +192,9 @@ class Ctx:
         self.sampler = ClockSampler(self.local, uuid)
         if self.rank == 0:
             self.sampler.start()
+        # roofline denominators measured once, on the idle device, before any section has warmed it up
+        self.i8_burst, self.i8_sustained = gw.i8_peak(self.local)
+        self.popc_peak, self.popc_clk = gw.popc_peak(self.local)
 
     def barrier(self):
         if self.world > 1:
@@ -260,10 +263,10 @@ def pairwise_section(cx: Ctx, shape, K, W, label, headline):
     # star's popcount view (4 AND+POPC word-cells per 32 samples per pair)
     macs = float(pairs) * 4.0 * N
     tops = 2.0 * macs / (k_ms * 1e-3) / 1e12
-    burst, sustained = gw.i8_peak(local)
+    burst, sustained = cx.i8_burst, cx.i8_sustained
     # a kernel timed inside a long step is held against the sustained figure, a short launch timed alone against the burst
     peak = sustained if k_ms > 50.0 else burst
-    peak_cells, clk = gw.popc_peak(local)
+    peak_cells, clk = cx.popc_peak, cx.popc_clk
     traffic, traffic_src = ncu_traffic("pair_screen_mma_kernel", M, N) if (engine == 2 and world == 1) else (None, None)
     kernel = {2: "pair_screen_mma_kernel (tcgen05.mma cta_group::2 kind::i8)", 1: "pair_screen_kernel<false> (AND+POPC)"}.get(engine, "?")
     roofline = {
@@ -418,7 +421,7 @@ def pairwise_missing_gpu(cx: Ctx):
             res[name] = {"value": round(s.pairs_tested / (k_ms * 1e-3), 1), "unit": "pairs/s", "kernel_ms": round(k_ms, 3),
                          "tiles_with_missing_calls": int(s.tiles_nine_cell), "candidates": int(s.candidates), "hits": int(len(hits))}
         cells = 9 * ((NCASE + 31) // 32 + (N - NCASE + 31) // 32)
-        peak, _ = gw.popc_peak(local)
+        peak = cx.popc_peak
         res["and_popc_nine_cells"]["frac_of_popc_roofline"] = round(res["and_popc_nine_cells"]["value"] * cells / peak, 4)
         res["tensor_cores_four_planes"]["x_popc_roofline"] = round(res["tensor_cores_four_planes"]["value"] * cells / peak, 4)
         res["same_hits"] = res["and_popc_nine_cells"]["hits"] == res["tensor_cores_four_planes"]["hits"]

@@ -231,7 +231,7 @@ __device__ __forceinline__ void for_each_batch(uint64_t snp_begin, uint64_t snp_
 template <int G, int SLOTS, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 marginal_scan_kernel(const uint4 *__restrict__ sel, uint32_t stride4, uint32_t Qc, uint32_t Qt,
-                     uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end, const ScanOut out) {
+                     uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin, uint64_t snp_end, const __grid_constant__ ScanOut out) {
     const uint32_t lane = threadIdx.x & 31, g = lane / G, l = lane % G;
     const uint32_t group_mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
     // One batch: up to 32 consecutive rows; in pass `it` the 32/G lane groups work on rows it*(32/G) .. +32/G-1 (so a short
@@ -284,7 +284,7 @@ template <int G, int SLOTS, int MINB, int MODE>
 __global__ void __launch_bounds__(256, MINB)
 marginal_scan_masked_kernel(const uint4 *__restrict__ raw, uint32_t Q, const uint4 *__restrict__ mask_case,
                             const uint4 *__restrict__ mask_ctrl, uint32_t n_case, uint32_t n_ctrl, uint64_t snp_begin,
-                            uint64_t snp_end, const ScanOut out) {
+                            uint64_t snp_end, const __grid_constant__ ScanOut out) {
     extern __shared__ uint4 sm_mask[];   // [Q] case, then (MODE 0) [Q] control
     for (uint32_t q = threadIdx.x; q < (MODE == 0 ? 2 * Q : Q); q += blockDim.x) sm_mask[q] = q < Q ? mask_case[q] : mask_ctrl[q - Q];
     __syncthreads();
@@ -393,16 +393,20 @@ __global__ void raw_counts_kernel(const uint32_t *__restrict__ raw, uint32_t Wr,
 
 using namespace gwasdev;
 
-static int lanes_per_row(const gwasdev_store *s, std::initializer_list<uint32_t> class_chunks) {
+static int lanes_per_row(const gwasdev_store *s, std::initializer_list<uint32_t> class_chunks, int slots) {
     if (s->opt[GWASDEV_OPT_LANES_PER_ROW]) return (int)s->opt[GWASDEV_OPT_LANES_PER_ROW];
-    // the width that wastes the fewest lane slots for this cohort, narrower on ties
+    // the width that wastes the fewest lane slots for this cohort; on ties the one whose lanes run whole rounds of `slots`
+    // chunk pairs (configs[1] on the raw rows: 80 chunk pairs = 16 lanes x 5, one round, measured 0.240 ms against 0.251 ms
+    // for 8 lanes x 10), else the narrower
     int G = 8;
     double best = 1e30;
+    bool best_whole = false;
     for (int cand : {8, 16, 32}) {
         double used = 0, have = 0;
-        for (uint32_t Q : class_chunks) { used += (double)((Q + cand - 1) / cand) * cand; have += Q; }
+        bool whole = true;
+        for (uint32_t Q : class_chunks) { const uint32_t per = (Q + cand - 1) / cand; used += (double)per * cand; have += Q; whole = whole && per % slots == 0; }
         const double waste = used / have;
-        if (waste < best - 1e-9) { best = waste; G = cand; }
+        if (waste < best - 1e-9 || (waste < best + 1e-9 && whole && !best_whole)) { best = waste; G = cand; best_whole = whole; }
     }
     return G;
 }
@@ -412,11 +416,11 @@ static int scan_compacted(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const uint32_t Qc = s->Wc / 4, Qt = s->Wt / 4, stride4 = 2 * (Qc + Qt);
-    int G = lanes_per_row(s, {Qc, Qt});
-    const uint64_t n = snp_end - snp_begin;
-    const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
     // loads in flight per lane and resident CTAs per SM: 5 chunk pairs, 3 CTAs (B200 sweep)
     int slots = 5, minb = 3;
+    int G = lanes_per_row(s, {Qc, Qt}, slots);
+    const uint64_t n = snp_end - snp_begin;
+    const uint4 *sel = reinterpret_cast<const uint4 *>(s->d_sel);
 #ifdef GWASDEV_SWEEP
     if (const char *cfg = getenv("GWASDEV_SCAN_CFG")) sscanf(cfg, "%d,%d,%d", &slots, &minb, &G);
 #endif
@@ -456,7 +460,6 @@ static int scan_masked(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, S
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const uint32_t Q = s->Wr / 4;
-    int G = lanes_per_row(s, {Q});
     const bool use_tot = partitioned(s) && s->opt[GWASDEV_OPT_ROW_TOTALS] == 0;
     const int mode = !partitioned(s) ? 0 : (use_tot && s->tot_valid ? 2 : 1);
     if (mode == 1 && use_tot) {
@@ -465,7 +468,8 @@ static int scan_masked(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, S
     } else out.row_tot = mode == 2 ? s->d_row_tot : nullptr;
     // loads in flight per lane, resident CTAs per SM (B200 sweeps, tools/sweep_mscan.py): modes 0 and 1 are bound by the
     // ALU pipe (occupancy pays more than loads in flight); mode 2 has the compacted scan's instruction mix
-    int slots = mode == 2 ? 4 : 2, minb = mode == 2 ? 3 : 4;
+    int slots = mode == 2 ? 5 : 2, minb = mode == 2 ? 3 : 4;
+    int G = lanes_per_row(s, {Q}, slots);
 #ifdef GWASDEV_SWEEP
     if (const char *cfg = getenv("GWASDEV_MSCAN_CFG")) sscanf(cfg, "%d,%d,%d", &slots, &minb, &G);
 #endif
@@ -499,7 +503,7 @@ static int scan_masked(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, S
     } while (0)
 #else
 #define MSCAN_G(GG)                                                                                  \
-    do { if (mode == 2) MSCAN1(GG, 4, 3, 2); else if (mode == 1) MSCAN1(GG, 2, 4, 1); else MSCAN1(GG, 2, 4, 0); } while (0)
+    do { if (mode == 2) MSCAN1(GG, 5, 3, 2); else if (mode == 1) MSCAN1(GG, 2, 4, 1); else MSCAN1(GG, 2, 4, 0); } while (0)
 #endif
     if (G == 8) MSCAN_G(8);
     else if (G == 16) MSCAN_G(16);
@@ -566,7 +570,8 @@ static int run_scan(gwasdev_store *s, uint64_t snp_begin, uint64_t snp_end, Scan
         }
         uint64_t out_bytes = 0;
         for (int c = 0; c < n_copies; ++c) out_bytes += n * copies[c].bytes_per_snp;
-        pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(gwasdev_store::MAX_PIECES, out_bytes / (12ull << 20)));   // ~12 MB per piece (tools/sweep_pieces.py)
+        pieces = (int)std::max<uint64_t>(1, std::min<uint64_t>(gwasdev_store::MAX_PIECES, out_bytes / (4ull << 20)));   // ~4 MB per piece and at most 8 (tools/r2_kernels.py: 16 MB of
+                                                                                                                         // compact records in 4 pieces 0.41 ms against 0.57 ms in one; 48 MB in 8)
         if (s->opt[GWASDEV_OPT_SCAN_PIECES]) pieces = (int)s->opt[GWASDEV_OPT_SCAN_PIECES];
     }
     cudaError_t e = cudaSuccess;

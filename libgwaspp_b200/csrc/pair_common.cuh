@@ -1,6 +1,7 @@
 // Pieces shared by the two pair-screen engines (pairwise.cu: AND+POPC tiles; pairwise_mma.cu: tcgen05 tiles).
 #pragma once
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -10,20 +11,37 @@ struct Candidate { uint32_t i, j; float stat; uint32_t pad; };
 
 // Where the screen kernels put the pairs that pass their fp32 test. Threshold mode (hist == nullptr): every pair above
 // `thr` (= threshold - margin) is appended; the host re-runs with a larger buffer if it overflowed. Top-k mode: the
-// kernels also keep a histogram of the appended statistics, and whenever the buffer passes a fill mark one thread
-// raises a device-wide threshold to the lower edge of the bin above which k candidates have already been seen (minus
-// `slack`, twice the fp32 error budget: the final choice is made on the fp64 re-scores) -- a pair below it can no
+// kernels also keep a two-level histogram of the appended statistics over the order-preserving integer image of fp32
+// (so it covers any threshold, however low, at under 1 % relative resolution), and whenever the buffer passes a fill mark
+// one thread raises a device-wide threshold to the lower edge of the bin above which k candidates have already been seen
+// (minus `slack`, twice the fp32 error budget: the final choice is made on the fp64 re-scores) -- a pair below it can no
 // longer be among the k best, so the buffer stops growing however low the caller's threshold is.
-constexpr int CAND_HIST_BINS = 2048;
+constexpr int CAND_HIST_COARSE = 256, CAND_HIST_FINE = 65536;     // bins: key >> 24, key >> 16
+__host__ __device__ inline uint32_t stat_key(float f) {           // fp32 -> uint32, monotone (total order of non-NaN floats)
+#ifdef __CUDA_ARCH__
+    const uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b; memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float key_stat(uint32_t k) {
+    const uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f; memcpy(&f, &b, 4); return f;
+#endif
+}
 struct CandSink {
     Candidate *cand;
     unsigned long long *n_cand;       // pairs appended so far (may exceed cap)
     unsigned long long cap;
     float thr;                        // static floor
-    uint32_t *hist;                   // [CAND_HIST_BINS] of width hist_w from thr up, last bin open-ended; nullptr: threshold mode
-    float *thr_dyn;                   // current device-wide threshold
-    int *lost_max;                    // largest statistic (float bits, >= 0) among the pairs that found the buffer full
-    float hist_w, slack;
+    uint32_t *hist;                   // [CAND_HIST_COARSE + CAND_HIST_FINE] counts per key bin; nullptr: threshold mode
+    uint32_t *thr_dyn_key;            // current device-wide threshold as a key (0: not raised yet)
+    uint32_t *lost_max_key;           // largest statistic (as a key) among the pairs that found the buffer full
+    float slack;
     unsigned long long k_keep;
     unsigned long long raise_from, raise_mask;   // raise when slot + 1 >= raise_from and ((slot + 1) & raise_mask) == 0
 };
@@ -31,31 +49,38 @@ struct CandSink {
 // threshold the pairs of the next tile are tested against
 __device__ __forceinline__ float sink_threshold(const CandSink &s) {
     if (!s.hist) return s.thr;
-    float t;
-    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(t) : "l"(s.thr_dyn) : "memory");
-    return fmaxf(t, s.thr);
+    uint32_t k;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(k) : "l"(s.thr_dyn_key) : "memory");
+    return k ? fmaxf(key_stat(k), s.thr) : s.thr;
 }
-static __device__ __noinline__ void sink_raise(const uint32_t *hist, float *thr_dyn, float thr, float hist_w, float slack, unsigned long long k_keep) {
+static __device__ __noinline__ void sink_raise(const uint32_t *hist, uint32_t *thr_dyn_key, float thr, float slack, unsigned long long k_keep) {
+    const volatile uint32_t *coarse = hist, *fine = hist + CAND_HIST_COARSE;
     unsigned long long acc = 0;
-    for (int b = CAND_HIST_BINS - 1; b >= 0; --b) {
-        acc += *reinterpret_cast<const volatile uint32_t *>(hist + b);
-        if (acc >= k_keep) {
-            const float t = thr + (float)b * hist_w - slack;
-            if (t > thr && t > 0.f) atomicMax(reinterpret_cast<int *>(thr_dyn), __float_as_int(t));   // positive floats order like ints
-            return;
+    for (int c = CAND_HIST_COARSE - 1; c >= 0; --c) {
+        const uint32_t n = coarse[c];
+        if (acc + n < k_keep) { acc += n; continue; }
+        for (int b = 256 * c + 255; b >= 256 * c; --b) {       // the fine bins of this coarse bin (counts may lag the coarse one by in-flight pushes)
+            acc += fine[b];
+            if (acc >= k_keep) {
+                const float t = key_stat((uint32_t)b << 16) - slack;      // lower edge of the bin
+                if (t > thr) atomicMax(thr_dyn_key, stat_key(t));
+                return;
+            }
         }
+        return;
     }
 }
 // append pair (i, j); the caller has checked stat > sink_threshold
 __device__ __forceinline__ void sink_push(const CandSink &s, uint32_t i, uint32_t j, float stat) {
     if (s.hist) {
-        const int b = min(max((int)((stat - s.thr) / s.hist_w), 0), CAND_HIST_BINS - 1);
-        atomicAdd(s.hist + b, 1u);
+        const uint32_t k = stat_key(stat);
+        atomicAdd(s.hist + CAND_HIST_COARSE + (k >> 16), 1u);     // fine first: a reader that sees the coarse count finds at least as much below it
+        atomicAdd(s.hist + (k >> 24), 1u);
     }
     const unsigned long long slot = atomicAdd(s.n_cand, 1ull);
     if (slot < s.cap) { Candidate cd; cd.i = i; cd.j = j; cd.stat = stat; cd.pad = 0; s.cand[slot] = cd; }
-    else if (s.hist) atomicMax(s.lost_max, __float_as_int(fmaxf(stat, 0.f)));
-    if (s.hist && slot + 1 >= s.raise_from && ((slot + 1) & s.raise_mask) == 0) sink_raise(s.hist, s.thr_dyn, s.thr, s.hist_w, s.slack, s.k_keep);
+    else if (s.hist) atomicMax(s.lost_max_key, stat_key(stat));
+    if (s.hist && slot + 1 >= s.raise_from && ((slot + 1) & s.raise_mask) == 0) sink_raise(s.hist, s.thr_dyn_key, s.thr, s.slack, s.k_keep);
 }
 
 // ---- PTX helpers (mbarrier + TMA) ----------------------------------------------------------------
