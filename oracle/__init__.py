@@ -21,6 +21,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libgwas_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libgwasref.so")
+# the same unmodified reference objects with the device table plugged into GeneticData's factory (level 6); see
+# oracle/ref_build/Makefile and libgwaspp_b200/binding/device_genotype_table.h
+REF_DEV_SO = os.path.join(HERE, "_ref", "libgwasref_dev.so")
 REFERENCE_ROOT = "/root/reference"
 
 # genetics/genotype/common_genotype.h:101-106 (192 bytes)
@@ -61,7 +64,9 @@ def build_ref(force: bool = False) -> str | None:
     (the GPU box): the prebuilt .so travels with the snapshot."""
     if not os.path.isdir(REFERENCE_ROOT):
         return REF_SO if os.path.exists(REF_SO) else None
-    if force or not os.path.exists(REF_SO):
+    gwasdev = os.path.join(os.path.dirname(HERE), "libgwaspp_b200", "libgwasdev.so")
+    stale = os.path.exists(gwasdev) and (not os.path.exists(REF_DEV_SO) or os.path.getmtime(REF_DEV_SO) < os.path.getmtime(gwasdev))
+    if force or not os.path.exists(REF_SO) or stale:
         subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "ref_build")],
                               stdout=subprocess.DEVNULL)
     return REF_SO
@@ -69,6 +74,10 @@ def build_ref(force: bool = False) -> str | None:
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_ref_dev() -> bool:
+    return os.path.exists(REF_DEV_SO)
 
 
 class Oracle:
@@ -267,13 +276,14 @@ class Ref:
     """The unmodified reference (T3/T4/T5 tables + its own test functions) behind a C-ABI harness."""
 
     _lib = None
+    SO = REF_SO
 
     @classmethod
     def lib(cls):
         if cls._lib is None:
-            if not os.path.exists(REF_SO):
-                raise FileNotFoundError(REF_SO)
-            L = C.CDLL(REF_SO)
+            if not os.path.exists(cls.SO):
+                raise FileNotFoundError(cls.SO)
+            L = C.CDLL(cls.SO)
             L.gwasref_create.restype = C.c_void_p
             L.gwasref_load_tplink.restype = C.c_void_p
             L.gwasref_load_tplink.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
@@ -383,6 +393,16 @@ class Ref:
 
     def time_phase(self, phase, reps=1):
         return float(self.L.gwasref_time_phase(self.h, phase, reps))
+
+
+class RefDev(Ref):
+    """The same harness over the reference build whose GeneticData factory knows the device table: level 6 =
+    libgwaspp_b200/binding/DeviceGenotypeTable (needs a GPU); levels 3-5 are the reference's own tables as in Ref."""
+    _lib = None
+    SO = REF_DEV_SO
+
+    def __init__(self, n_snps=None, n_samples=None, level=6, **kw):
+        super().__init__(n_snps, n_samples, level, **kw)
 
 
 def parse_boost_output(text: str):

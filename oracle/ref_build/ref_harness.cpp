@@ -306,12 +306,14 @@ double gwasref_pairwise_c(const int cs[9], const int ct[9], double *pval) {
 int gwasref_raw_row(void *h, int row, uint16_t *out, int cap) {
     Ref *r = (Ref *)h;
     int n = (int)r->gt->blocks_per_row;
+    if (r->gt->data == NULL) return 0;          // a table without host storage (the device table, level 6)
     if (out) memcpy(out, r->gt->data + (size_t)row * n, 2 * (size_t)(n < cap ? n : cap));
     return n;
 }
 // compacted row: nCaseControlBlockCount ushorts (T5: compressed_genotype_table5.cpp:443-575)
 int gwasref_selected_row(void *h, int row, uint16_t *out, int cap, int geom[4]) {
     Ref *r = (Ref *)h;
+    if (r->gt->m_cases_controls == NULL) return 0;
     int n = (int)r->gt->nCaseControlBlockCount;
     if (geom) {
         geom[0] = r->gt->nCaseBlockCount; geom[1] = r->gt->nControlBlockCount;
