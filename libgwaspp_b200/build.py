@@ -86,4 +86,9 @@ def build_host() -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, sweep="--sweep" in sys.argv))
+    if "--variant" in sys.argv:      # experiment build: libgwasdev_<name>.so with extra -D flags (tools/time_screen.py --lib ...)
+        name = sys.argv[sys.argv.index("--variant") + 1]
+        defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+        print(_build_lib(os.path.join(HERE, f"libgwasdev_{name}.so"), defs, f"build_{name}", "-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, sweep="--sweep" in sys.argv))

@@ -54,7 +54,10 @@ constexpr int MMA_THREADS = (2 + EPI_WARPS) * 32;
 // above the sixteen epilogue warps (which also makes warp % 4 the TMEM lane quadrant of epilogue warp `warp`).
 constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int COL_STAGE_BYTES = 32 * 64;                           // column-role records of one epilogue warp's 32 B-SNPs
-constexpr int BAND = 8;                                            // A-blocks per L2 band
+#ifndef GWASDEV_BAND
+#define GWASDEV_BAND 8
+#endif
+constexpr int BAND = GWASDEV_BAND;                                 // A-blocks per L2 band (experiment builds: build.py --variant NAME -DGWASDEV_BAND=n)
 constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
 constexpr uint32_t CTRL_SHIFT = 14;                                // (-128)^2 = 2^14
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                        // shared::cluster address of the pair's even CTA
