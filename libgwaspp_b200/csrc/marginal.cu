@@ -395,18 +395,18 @@ using namespace gwasdev;
 
 static int lanes_per_row(const gwasdev_store *s, std::initializer_list<uint32_t> class_chunks, int slots) {
     if (s->opt[GWASDEV_OPT_LANES_PER_ROW]) return (int)s->opt[GWASDEV_OPT_LANES_PER_ROW];
-    // the width that wastes the fewest lane slots for this cohort; on ties the one whose lanes run whole rounds of `slots`
-    // chunk pairs (configs[1] on the raw rows: 80 chunk pairs = 16 lanes x 5, one round, measured 0.240 ms against 0.251 ms
-    // for 8 lanes x 10), else the narrower
+    // the width that wastes the fewest lane slots for this cohort; on ties the one that needs the fewest rounds of `slots`
+    // chunk pairs per lane (configs[1] on the raw rows: 80 chunk pairs = 16 lanes x 5, one round, measured 0.240 ms against
+    // 0.251 ms for 8 lanes x 10, two rounds), then the narrower
     int G = 8;
     double best = 1e30;
-    bool best_whole = false;
+    uint32_t best_rounds = 0;
     for (int cand : {8, 16, 32}) {
         double used = 0, have = 0;
-        bool whole = true;
-        for (uint32_t Q : class_chunks) { const uint32_t per = (Q + cand - 1) / cand; used += (double)per * cand; have += Q; whole = whole && per % slots == 0; }
+        uint32_t rounds = 0;
+        for (uint32_t Q : class_chunks) { const uint32_t per = (Q + cand - 1) / cand; used += (double)per * cand; have += Q; rounds += (per + slots - 1) / slots; }
         const double waste = used / have;
-        if (waste < best - 1e-9 || (waste < best + 1e-9 && whole && !best_whole)) { best = waste; G = cand; best_whole = whole; }
+        if (waste < best - 1e-9 || (waste < best + 1e-9 && rounds < best_rounds)) { best = waste; G = cand; best_rounds = rounds; }
     }
     return G;
 }

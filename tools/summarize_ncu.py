@@ -67,7 +67,7 @@ def full(src, dst, cmd):
                     f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
             rd, wr = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]])
             ur, uw = units[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_write.sum"]]
-            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
             f.write(f"\nDRAM traffic per launch = {rd * scale[ur] + wr * scale[uw]:.4g} bytes\n\n")
 
 
