@@ -342,7 +342,8 @@ def pairwise_section(cx: Ctx, shape, K, W, label, headline):
             try:
                 e2e = single_process_e2e(cx, shape, e2e_steps, total_pairs, case_mask, ctrl_mask)
             except Exception as exc:                   # keep the line; say what happened
-                e2e = dict(res["e2e_torchrun"], error=f"single-process multi-device e2e failed: {exc!r}; value is the per-rank form")
+                e2e = dict(res["e2e_torchrun"], h2d_bytes_per_step=0, d2h_bytes_per_step=0,
+                           error=f"single-process multi-device e2e failed: {exc!r}; value is the per-rank form")
         cx.cpu_barrier()
         res["e2e"] = e2e
     return res

@@ -19,6 +19,9 @@
 
 namespace gwasdev {
 
+static_assert(sizeof(gwasdev_snp_compact) == 32 && sizeof(gwasdev_sig_snp) == 48 && sizeof(gwasdev_snp_stats) == 64 &&
+              sizeof(gwasdev_marginal_information) == 192, "C-ABI record sizes (include/gwasdev.h)");
+
 struct ChunkPair { uint4 x, y; };   // 4 words of plane 1, 4 words of plane 2 (same 128 samples)
 
 __device__ __forceinline__ ChunkPair ld_pair(const uint4 *p, bool pred) {   // read-once: keep out of L1
@@ -157,39 +160,58 @@ struct ScanOut {
     uint64_t out_base;
 };
 
-// One SNP's epilogue, kept out of line so that the streaming loop stays small in the instruction cache.
-__device__ __noinline__ void finish_snp(uint32_t m1c, uint32_t m2c, uint32_t mbc, uint32_t m1t, uint32_t m2t, uint32_t mbt,
-                                        uint32_t n_case, uint32_t n_ctrl, uint64_t snp, const ScanOut &out) {
-    const uint64_t o = snp - out.out_base;
-    uint32_t ca[4], co[4];
+// One SNP's epilogue, kept out of line so that the streaming loop stays small in the instruction cache. Two forms: the
+// plain one writes counts / marginal_information / statistics straight into the caller's arrays; the compact one (32-byte
+// records, significant-SNP list) needs the statistics in registers first and lives in its own function so that its local
+// record does not cost the plain scan a stack frame (0.2296 -> 0.2237 ms at configs[1] when the two were one function).
+__device__ __forceinline__ void snp_counts(uint32_t m1c, uint32_t m2c, uint32_t mbc, uint32_t m1t, uint32_t m2t, uint32_t mbt,
+                                           uint32_t n_case, uint32_t n_ctrl, uint32_t (&ca)[4], uint32_t (&co)[4]) {
     ca[0] = m1c - mbc; ca[1] = m2c - mbc; ca[2] = mbc; ca[3] = n_case - ca[0] - ca[1] - ca[2];
     co[0] = m1t - mbt; co[1] = m2t - mbt; co[2] = mbt; co[3] = n_ctrl - co[0] - co[1] - co[2];
-    if (out.counts) {
-        uint4 *dst = reinterpret_cast<uint4 *>(out.counts + 8 * o);
+}
+
+__device__ __noinline__ void finish_snp_plain(uint32_t m1c, uint32_t m2c, uint32_t mbc, uint32_t m1t, uint32_t m2t, uint32_t mbt,
+                                              uint32_t n_case, uint32_t n_ctrl, uint64_t o, uint32_t *__restrict__ counts,
+                                              gwasdev_marginal_information *__restrict__ mi, gwasdev_snp_stats *__restrict__ stats) {
+    uint32_t ca[4], co[4];
+    snp_counts(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, ca, co);
+    if (counts) {
+        uint4 *dst = reinterpret_cast<uint4 *>(counts + 8 * o);
         dst[0] = make_uint4(ca[0], ca[1], ca[2], ca[3]);
         dst[1] = make_uint4(co[0], co[1], co[2], co[3]);
     }
-    if (out.mi) fill_marginal_information(ca, co, n_case + n_ctrl, out.mi[o]);
-    if (out.stats || out.compact || out.sig) {
-        gwasdev_snp_stats st;
-        fill_stats(ca, co, st);
-        if (out.stats) out.stats[o] = st;
-        if (out.compact) {
-            uint4 *dst = reinterpret_cast<uint4 *>(out.compact + o);
-            dst[0] = make_uint4(ca[0] | (ca[1] << 16), ca[2] | (ca[3] << 16), co[0] | (co[1] << 16), co[2] | (co[3] << 16));
-            dst[1] = make_uint4(__float_as_uint((float)st.chi2_allelic), __float_as_uint((float)st.p_allelic),
-                                __float_as_uint((float)st.chi2_genotypic), __float_as_uint((float)st.p_genotypic));
-        }
-        if (out.sig && (st.p_allelic < out.p_thr || st.p_genotypic < out.p_thr)) {
-            const unsigned long long slot = atomicAdd(out.n_sig, 1ull);
-            if (slot < out.sig_cap) {
-                gwasdev_sig_snp g;
-                g.snp = (uint32_t)snp; g.df_genotypic = (uint32_t)st.df_genotypic; g.maf_pooled = st.maf_pooled;
-                g.chi2_allelic = st.chi2_allelic; g.p_allelic = st.p_allelic; g.chi2_genotypic = st.chi2_genotypic; g.p_genotypic = st.p_genotypic;
-                out.sig[slot] = g;
-            }
+    if (mi) fill_marginal_information(ca, co, n_case + n_ctrl, mi[o]);
+    if (stats) fill_stats(ca, co, stats[o]);
+}
+
+__device__ __noinline__ void finish_snp_compact(uint32_t m1c, uint32_t m2c, uint32_t mbc, uint32_t m1t, uint32_t m2t, uint32_t mbt,
+                                                uint32_t n_case, uint32_t n_ctrl, uint64_t snp, const ScanOut &out) {
+    const uint64_t o = snp - out.out_base;
+    uint32_t ca[4], co[4];
+    snp_counts(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, ca, co);
+    gwasdev_snp_stats st;
+    fill_stats(ca, co, st);
+    if (out.compact) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out.compact + o);
+        dst[0] = make_uint4(ca[0] | (ca[1] << 16), ca[2] | (ca[3] << 16), co[0] | (co[1] << 16), co[2] | (co[3] << 16));
+        dst[1] = make_uint4(__float_as_uint((float)st.chi2_allelic), __float_as_uint((float)st.p_allelic),
+                            __float_as_uint((float)st.chi2_genotypic), __float_as_uint((float)st.p_genotypic));
+    }
+    if (out.sig && (st.p_allelic < out.p_thr || st.p_genotypic < out.p_thr)) {
+        const unsigned long long slot = atomicAdd(out.n_sig, 1ull);
+        if (slot < out.sig_cap) {
+            gwasdev_sig_snp g;
+            g.snp = (uint32_t)snp; g.df_genotypic = (uint32_t)st.df_genotypic; g.maf_pooled = st.maf_pooled;
+            g.chi2_allelic = st.chi2_allelic; g.p_allelic = st.p_allelic; g.chi2_genotypic = st.chi2_genotypic; g.p_genotypic = st.p_genotypic;
+            out.sig[slot] = g;
         }
     }
+}
+
+__device__ __forceinline__ void finish_snp(uint32_t m1c, uint32_t m2c, uint32_t mbc, uint32_t m1t, uint32_t m2t, uint32_t mbt,
+                                           uint32_t n_case, uint32_t n_ctrl, uint64_t snp, const ScanOut &out) {
+    if (out.compact || out.sig) finish_snp_compact(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, snp, out);      // (the compact scan writes no plain outputs)
+    else finish_snp_plain(m1c, m2c, mbc, m1t, m2t, mbt, n_case, n_ctrl, snp - out.out_base, out.counts, out.mi, out.stats);
 }
 
 // SLOTS = chunk pairs a lane loads back to back (2*SLOTS 128-bit loads in flight per lane)

@@ -143,3 +143,31 @@ def test_file_dims_helpers_run_on_the_host(lib, golden_dir, tmp_path):
     bed.write_bytes(b"not a bed file")
     with pytest.raises(gw.GwasDevError, match="not a PLINK .bed"):
         gw.bed_dims(str(bed), 10)
+
+
+@pytest.mark.skipif(gw.load_library().gwasdev_device_count() > 0, reason="a GPU is present")
+def test_round2_entry_points_fail_loudly_without_a_device(lib):
+    with pytest.raises(gw.GwasDevError):
+        gw.i8_peak(0)
+    # host arithmetic keeps working without a device: the shard schedule of both engines
+    tiles, pairs = gw.shard_schedule(1000, 0, 1, engine=2)
+    assert len(tiles) == 8 * 9 // 2 and pairs == 1000 * 999 // 2
+    tiles, pairs = gw.shard_schedule(1000, 1, 3, engine=1)
+    assert all(I <= J for I, J in tiles) and len(tiles) == (16 * 17 // 2 + 1) // 3
+    assert gw.COMPACT_DTYPE.itemsize == 32 and gw.SIG_DTYPE.itemsize == 48
+
+
+def test_binding_library_carries_the_reference_subclass():
+    """oracle/_ref/libgwasref_dev.so (built where /root/reference exists, travels to the GPU box): the reference objects +
+    class DeviceGenotypeTable : public GenoTable + the patched factory, linked against libgwasdev.so."""
+    import subprocess
+    import oracle
+    if not oracle.have_ref_dev():
+        pytest.skip("reference build absent")
+    syms = subprocess.run(["nm", "-DC", oracle.REF_DEV_SO], capture_output=True, text=True).stdout
+    for name in ("DeviceGenotypeTable::selectCaseControl", "DeviceGenotypeTable::getCaseControlContingencyTable",
+                 "DeviceGenotypeTable::getCaseControlGenotypeDistribution", "DeviceGenotypeTable::addGenotypeRow",
+                 "vtable for libgwaspp::genetics::DeviceGenotypeTable"):
+        assert name in syms, name
+    needed = subprocess.run(["readelf", "-d", oracle.REF_DEV_SO], capture_output=True, text=True).stdout
+    assert "libgwasdev.so" in needed
