@@ -184,12 +184,15 @@ GWASDEV_API int gwasdev_simulate_phenotype(uint64_t seed, uint32_t n_samples, ui
  * SNP-tiled pairwise store) on the device; the raw store stays resident, so this can be called
  * again with other masks. */
 GWASDEV_API int gwasdev_select_case_control(gwasdev_store *s, const uint16_t *case_mask, const uint16_t *ctrl_mask);
-/* Compaction is lazy by default: the call above uploads the masks, and the compacted rows are built (kernel K0) when
- * something first needs them -- the layout probes, the AND+POPC engine, the per-pair probes, or the second marginal scan of a
- * cohort with samples outside both classes; marginal scans after a selection count through the masks on the raw rows
- * instead, which is the reference's mask-on-the-fly overload (:609-657) and gives identical counts. eager != 0 runs K0
- * inside gwasdev_select_case_control. */
+/* Compaction is lazy by default: the call above uploads the masks, and the compacted rows are built (kernel K0) only when
+ * something needs that LAYOUT -- the layout probes (gwasdev_get_selected_rows, gwasdev_counts mode 2, gwasdev_pair_tables
+ * mode 2), the AND+POPC engine, cohorts beyond the packed accumulator with missing calls, or the second marginal scan of a
+ * cohort with samples outside both classes. Marginal scans count through the masks on the raw rows (the reference's
+ * mask-on-the-fly overload, :609-657: identical counts), and the tensor-core screen, its fp64 re-score and the G-test read
+ * raw rows + masks as well. eager != 0 runs K0 inside gwasdev_select_case_control. */
 GWASDEV_API int gwasdev_set_select_mode(gwasdev_store *s, int eager);
+/* 1 when the compacted rows of the current selection exist on the device (K0 has run for it), 0 when not, -1 without a selection. */
+GWASDEV_API int gwasdev_is_compacted(const gwasdev_store *s);
 /* Stream masks for the mask-on-the-fly overloads only -- getCaseControlGenotypeDistribution(r, ccs, ccgd) (:609-657,
  * gwasdev_counts mode 1) and getCaseControlContingencyTable(i, j, ccs, ccct) (:806-895, gwasdev_pair_tables mode 1). As in
  * the reference, they do not touch the pre-selected store: selection, compacted rows, margins and pairwise layouts stay

@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
     "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs", "gwasdev_create_from_tped",
     "gwasdev_set_option", "gwasdev_set_stream_masks", "gwasdev_marginal_scan_compact", "gwasdev_pairwise_topk",
-    "gwasdev_replicate", "gwasdev_pairwise_scan_multi", "gwasdev_shard_schedule", "gwasdev_i8_peak", "gwasdev_gtest_multi",
+    "gwasdev_replicate", "gwasdev_pairwise_scan_multi", "gwasdev_shard_schedule", "gwasdev_i8_peak", "gwasdev_gtest_multi", "gwasdev_is_compacted",
 ]
 
 
@@ -90,6 +90,7 @@ def load_library():
     L.gwasdev_synchronize.argtypes = [vp]
     L.gwasdev_set_option.argtypes = [vp, i32, C.c_longlong]
     L.gwasdev_set_stream_masks.argtypes = [vp, vp, vp]
+    L.gwasdev_is_compacted.argtypes = [vp]
     L.gwasdev_marginal_scan_compact.argtypes = [vp, u64, u64, vp, C.c_double, vp, u64, C.POINTER(u64), i32]
     L.gwasdev_pack_row_text.argtypes = [C.c_char_p, C.c_size_t, u32, vp]
     L.gwasdev_put_rows.argtypes = [vp, u64, u64, vp]
@@ -412,6 +413,10 @@ class GenoStore:
         a, b = C.c_uint32(), C.c_uint32()
         _check(self.L.gwasdev_case_control_counts(self.h, C.byref(a), C.byref(b)), "gwasdev_case_control_counts")
         self.n_case, self.n_ctrl = a.value, b.value
+
+    def is_compacted(self) -> bool:
+        """True when kernel K0 has built the compacted rows of the current selection."""
+        return self.L.gwasdev_is_compacted(self.h) == 1
 
     def set_stream_masks(self, pheno=None, *, case_mask=None, ctrl_mask=None):
         """Masks of the mask-on-the-fly overloads only (counts mode 1, pair_tables mode 1); the selection stays as it is."""

@@ -172,7 +172,7 @@ struct gwasdev_store {
     int pair_engine = 0;          // 0 auto, 1 AND+POPC tiles, 2 tcgen05 tiles (gwasdev_set_pair_engine)
     bool mm_built = false;
     uint64_t mm_rows = 0;         // 2 rows (planes aa, bb) per SNP, SNP count rounded up to 128
-    uint32_t mm_kbytes = 0;       // bytes per row: cases padded to 128, then controls padded to 128
+    uint32_t mm_kbytes = 0;       // bytes per row of d_mm: 32 * Wr, one byte per sample position of the raw row
     int8_t *d_mm = nullptr;
     void *tmap_mm = nullptr;      // host copies of the two CUtensorMaps (A box, B box)
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
@@ -183,6 +183,7 @@ struct gwasdev_store {
     int8_t *d_mm4 = nullptr;
     size_t cap_mm4 = 0;
     uint64_t mm4_rows = 0, mm4_tiles = 0;
+    uint32_t mm4_kbytes = 0;      // bytes per row of d_mm4: 32 * Wr (raw sample order; modes 0, 1) or cases | controls padded to 128 each (mode 2)
     void *tmap_mm4 = nullptr;
     float mma_qc = 0.f, mma_q0 = 0.f;   // constants of the upper-bound pre-filter (pairwise_mma.cu)
     uint32_t mma_bound_ncase = 0xffffffffu, mma_bound_n = 0;   // class split they were computed for

@@ -110,6 +110,42 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
 }
 
 
+// Where a per-pair kernel (fp64 re-score, G-test, probes) reads the two SNPs' genotypes: the compacted rows when K0 has run
+// for this selection, else the raw rows through the selection's class masks (the operand bytes of the tensor-core screen
+// are built the same way, so the pair path never needs the compaction).
+struct PairSrc {
+    const uint32_t *sel; uint32_t stride, Wc, Wt;              // compacted rows (scan layout) when sel != nullptr ...
+    const uint32_t *raw; uint32_t Wr; const uint32_t *mca, *mco;   // ... or raw rows + class masks (cases; controls-and-not-cases)
+};
+inline PairSrc pair_src(const gwasdev_store *s) {
+    PairSrc p;
+    p.sel = s->sel_built ? s->d_sel : nullptr; p.stride = 2 * (s->Wc + s->Wt); p.Wc = s->Wc; p.Wt = s->Wt;
+    p.raw = s->d_raw; p.Wr = s->Wr; p.mca = s->d_case_sel_mask; p.mco = s->d_ctrl_sel_mask;
+    return p;
+}
+// 3x3 core cells (4x4 row-major, cells 0,1,2,4,5,6,8,9,10) of both classes for pair (i, j); words w = w0, w0 + step, ...
+// (one thread: w0 = 0, step = 1; a warp: w0 = lane, step = 32 followed by a warp reduction)
+__device__ __forceinline__ void core_counts_src(const PairSrc &p, uint64_t i, uint64_t j, uint32_t w0, uint32_t step, uint32_t ca[16], uint32_t co[16]) {
+    auto add9 = [](uint32_t a1, uint32_t a2, uint32_t b1, uint32_t b2, uint32_t m, uint32_t t[16]) {
+        const uint32_t abb = a1 & a2 & m, aaa = (a1 & m) ^ abb, aab = (a2 & m) ^ abb, bbb = b1 & b2, baa = b1 ^ bbb, bab = b2 ^ bbb;
+        t[0] += __popc(aaa & baa); t[1] += __popc(aaa & bab); t[2] += __popc(aaa & bbb);
+        t[4] += __popc(aab & baa); t[5] += __popc(aab & bab); t[6] += __popc(aab & bbb);
+        t[8] += __popc(abb & baa); t[9] += __popc(abb & bab); t[10] += __popc(abb & bbb);
+    };
+    if (p.sel) {
+        const uint32_t *ri = p.sel + i * (uint64_t)p.stride, *rj = p.sel + j * (uint64_t)p.stride;
+        for (uint32_t w = w0; w < p.Wc; w += step) { const uint32_t x = sel_word(0, 0, w), y = sel_word(0, 1, w); add9(ri[x], ri[y], rj[x], rj[y], 0xffffffffu, ca); }
+        for (uint32_t w = w0; w < p.Wt; w += step) { const uint32_t x = sel_word(2 * p.Wc, 0, w), y = sel_word(2 * p.Wc, 1, w); add9(ri[x], ri[y], rj[x], rj[y], 0xffffffffu, co); }
+    } else {
+        const uint32_t *a1 = p.raw + i * 2ull * p.Wr, *a2 = a1 + p.Wr, *b1 = p.raw + j * 2ull * p.Wr, *b2 = b1 + p.Wr;
+        for (uint32_t w = w0; w < p.Wr; w += step) {
+            const uint32_t x1 = a1[w], x2 = a2[w], y1 = b1[w], y2 = b2[w];
+            add9(x1, x2, y1, y2, p.mca[w], ca);
+            add9(x1, x2, y1, y2, p.mco[w], co);
+        }
+    }
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

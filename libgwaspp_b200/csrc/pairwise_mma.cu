@@ -659,32 +659,43 @@ i8_peak_kernel(uint32_t kblocks, uint32_t seed) {
     }
 }
 
-// ---- operand matrix: scan layout -> signed one-hot bytes ---------------------------------------------
-// One thread per (SNP, 32-sample word): 32 bytes of plane aa and 32 bytes of plane bb.
+// ---- operand matrix: raw rows + class masks -> signed one-hot bytes ------------------------------------
 __device__ __forceinline__ uint32_t spread4(uint32_t nibble) { return (nibble * 0x00204081u) & 0x01010101u; }   // bit i -> byte i
 
-__global__ void expand_mma_kernel(const uint32_t *__restrict__ sel, uint32_t sel_stride, uint32_t Wc, uint32_t Kc, uint32_t Kt,
-                                  uint32_t case_bytes, uint32_t kbytes, uint64_t M, int8_t *__restrict__ mm) {
-    const uint32_t K = Kc + Kt;
+// Operand rows straight from the RAW rows and the selection's class masks (no compaction): a sample's byte is +1
+// when it is a case with the genotype, -128 (or +1 in its own plane, LAYOUT 1) when it is a control with it, 0 otherwise --
+// wherever the sample sits in the row, because a sample is a case or a control for BOTH SNPs of a pair and the products are
+// summed over all samples. One thread per (SNP, 32-sample word of the raw row); a row is 32 * Wr bytes.
+//   LAYOUT -1: two planes per SNP (aa, bb), rows 2s + p                     (pair_screen_mma_kernel)
+//   LAYOUT  0: four rows per SNP (aa, bb, xx = class member without a call, zero padding), rows 4s + p   (mma4 MODE 0)
+//   LAYOUT  1: four rows per SNP (aa cases, bb cases, aa controls, bb controls), every byte +1          (mma4 MODE 1)
+__device__ __forceinline__ void store_class_bytes(int8_t *dst, uint32_t xc, uint32_t xt) {     // 32 bytes: +1 for bits of xc, -128 for bits of xt
+    uint4 lo, hi;
+    lo.x = spread4(xc & 15u) | (spread4(xt & 15u) << 7);                 lo.y = spread4((xc >> 4) & 15u) | (spread4((xt >> 4) & 15u) << 7);
+    lo.z = spread4((xc >> 8) & 15u) | (spread4((xt >> 8) & 15u) << 7);   lo.w = spread4((xc >> 12) & 15u) | (spread4((xt >> 12) & 15u) << 7);
+    hi.x = spread4((xc >> 16) & 15u) | (spread4((xt >> 16) & 15u) << 7); hi.y = spread4((xc >> 20) & 15u) | (spread4((xt >> 20) & 15u) << 7);
+    hi.z = spread4((xc >> 24) & 15u) | (spread4((xt >> 24) & 15u) << 7); hi.w = spread4((xc >> 28) & 15u) | (spread4((xt >> 28) & 15u) << 7);
+    reinterpret_cast<uint4 *>(dst)[0] = lo; reinterpret_cast<uint4 *>(dst)[1] = hi;
+}
+
+template <int LAYOUT>
+__global__ void expand_raw_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, const uint32_t *__restrict__ mca, const uint32_t *__restrict__ mco,
+                                  uint32_t kbytes, uint64_t M, int8_t *__restrict__ mm) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t snp = idx / K;
+    const uint64_t snp = idx / Wr;
     if (snp >= M) return;
-    const uint32_t k = (uint32_t)(idx - snp * K);
-    const uint32_t *row = sel + snp * (uint64_t)sel_stride;
-    uint32_t p1, p2, off, shift;
-    if (k < Kc) { p1 = row[sel_word(0, 0, k)]; p2 = row[sel_word(0, 1, k)]; off = 32 * k; shift = 0; }
-    else { p1 = row[sel_word(2 * Wc, 0, k - Kc)]; p2 = row[sel_word(2 * Wc, 1, k - Kc)]; off = case_bytes + 32 * (k - Kc); shift = 7; }
+    const uint32_t w = (uint32_t)(idx - snp * Wr);
+    const uint32_t p1 = raw[snp * 2ull * Wr + w], p2 = raw[snp * 2ull * Wr + Wr + w], ca = mca[w], co = mco[w];
     const uint32_t bb = p1 & p2, aa = p1 ^ bb;
-#pragma unroll
-    for (int pl = 0; pl < 2; ++pl) {
-        const uint32_t x = pl ? bb : aa;
-        uint4 *dst = reinterpret_cast<uint4 *>(mm + (2 * snp + pl) * (uint64_t)kbytes + off);
-        uint4 lo, hi;
-        lo.x = spread4(x & 15u) << shift;         lo.y = spread4((x >> 4) & 15u) << shift;
-        lo.z = spread4((x >> 8) & 15u) << shift;  lo.w = spread4((x >> 12) & 15u) << shift;
-        hi.x = spread4((x >> 16) & 15u) << shift; hi.y = spread4((x >> 20) & 15u) << shift;
-        hi.z = spread4((x >> 24) & 15u) << shift; hi.w = spread4((x >> 28) & 15u) << shift;
-        dst[0] = lo; dst[1] = hi;
+    constexpr int ROWS = LAYOUT < 0 ? 2 : 4;
+    int8_t *row = mm + (ROWS * snp) * (uint64_t)kbytes + 32ull * w;
+    if (LAYOUT == 1) {
+        store_class_bytes(row, aa & ca, 0u);                     store_class_bytes(row + kbytes, bb & ca, 0u);
+        store_class_bytes(row + 2ull * kbytes, aa & co, 0u);     store_class_bytes(row + 3ull * kbytes, bb & co, 0u);
+    } else {
+        store_class_bytes(row, aa & ca, aa & co);
+        store_class_bytes(row + kbytes, bb & ca, bb & co);
+        if (LAYOUT == 0) { const uint32_t xx = ~(p1 | p2); store_class_bytes(row + 2ull * kbytes, xx & ca, xx & co); }     // the padding row stays zero (memset)
     }
 }
 
@@ -1069,24 +1080,21 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
 }
 
 // fp32 value of the tensor-core engine's epilogue for given pairs (diagnostic twin of screen_probe_kernel)
-__global__ void screen_probe_mma_kernel(const uint32_t *__restrict__ sel, uint32_t stride, uint32_t Wc, uint32_t Wt,
-                                        const MmaRow *__restrict__ row, const MmaCol *__restrict__ col,
+__global__ void screen_probe_mma_kernel(const PairSrc src, const MmaRow *__restrict__ row, const MmaCol *__restrict__ col,
                                         const MmaRowF *__restrict__ rowf, const MmaColF *__restrict__ colf,
                                         const uint32_t *__restrict__ pi, const uint32_t *__restrict__ pj, uint64_t n, float N,
                                         float qc, float q0, float *__restrict__ out) {
     const uint64_t qi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= n) return;
     const uint32_t i = pi[qi], j = pj[qi];
-    const uint32_t *ri = sel + i * (uint64_t)stride, *rj = sel + j * (uint64_t)stride;
-    uint32_t c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    for (int k = 0; k < 2; ++k) {
-        const uint32_t W = k ? Wt : Wc, off = k ? 2 * Wc : 0;
-        for (uint32_t wq = 0; wq < W; ++wq) {
-            const uint32_t x = sel_word(off, 0, wq), y = sel_word(off, 1, wq);
-            const uint32_t a1 = ri[x], a2 = ri[y], b1 = rj[x], b2 = rj[y];
-            const uint32_t abb = a1 & a2, aaa = a1 ^ abb, bbb = b1 & b2, baa = b1 ^ bbb;
-            c[k][0] += __popc(aaa & baa); c[k][1] += __popc(aaa & bbb); c[k][2] += __popc(abb & baa); c[k][3] += __popc(abb & bbb);
-        }
+    uint32_t c[2][4];
+    {
+        uint32_t t0[16], t1[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { t0[q] = 0; t1[q] = 0; }
+        core_counts_src(src, i, j, 0, 1, t0, t1);
+        c[0][0] = t0[0]; c[0][1] = t0[2]; c[0][2] = t0[8]; c[0][3] = t0[10];      // AA_BB, AA_bb, aa_BB, aa_bb
+        c[1][0] = t1[0]; c[1][1] = t1[2]; c[1][2] = t1[8]; c[1][3] = t1[10];
     }
     float2 pca[3], ca[3], w[3], cb[3]; float Crow, Ccol;
     load_record(row + i, pca, ca, Crow);
@@ -1148,16 +1156,14 @@ static void bound_constants(uint32_t n_case, uint32_t n, float *qc_out, float *q
 static int ensure_mma_inputs(gwasdev_store *s) {
     const uint64_t Msnp = (s->M + MMA_B_SNPS - 1) / MMA_B_SNPS * MMA_B_SNPS;
     if (!s->mm_built) {
-        const uint32_t case_bytes = round_up(s->n_case, MMA_KB), ctrl_bytes = round_up(s->n_ctrl, MMA_KB);
-        s->mm_kbytes = case_bytes + ctrl_bytes;
+        s->mm_kbytes = 32 * s->Wr;                             // one byte per sample position of the raw row (Wr is a multiple of 4 words: 128-byte blocks)
         s->mm_rows = 2 * Msnp;
         const size_t bytes = (size_t)s->mm_rows * s->mm_kbytes;
         GW_CUDA(reserve_raw(s->d_mm, s->cap_mm, bytes));
-        GW_CUDA(cudaMemsetAsync(s->d_mm, 0, bytes, s->stream));
-        const uint32_t K = s->Kc + s->Kt;
-        const uint64_t work = s->M * K;
-        expand_mma_kernel<<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt,
-                                                                                 case_bytes, s->mm_kbytes, s->M, s->d_mm);
+        if (Msnp > s->M) GW_CUDA(cudaMemsetAsync(s->d_mm + 2 * s->M * (size_t)s->mm_kbytes, 0, (size_t)(2 * (Msnp - s->M)) * s->mm_kbytes, s->stream));   // rows of the SNPs beyond the table
+        const uint64_t work = s->M * s->Wr;
+        expand_raw_kernel<-1><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask,
+                                                                                   s->mm_kbytes, s->M, s->d_mm);
         GW_LAUNCHED();
         if (!s->tmap_mm && posix_memalign(&s->tmap_mm, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
         int rc;
@@ -1304,23 +1310,31 @@ static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
     if (s->mm4_built && s->mm4_mode == mode) return GWASDEV_OK;
     const uint32_t TB = m4_blocks(s);
     const uint32_t case_bytes = round_up(s->n_case, MMA_KB), ctrl_bytes = round_up(s->n_ctrl, MMA_KB);
-    s->mm_kbytes = case_bytes + ctrl_bytes;                 // the same row geometry as the two-plane matrix
+    // modes 0 and 1: bytes in raw sample order, straight from the raw rows and the class masks. Mode 2 sends the sample blocks of
+    // the case range of K to one accumulator and the control range to the other, so its rows are class-pure: from the compacted rows.
+    s->mm4_kbytes = mode == 2 ? case_bytes + ctrl_bytes : 32 * s->Wr;
     s->mm4_rows = (uint64_t)M4_PLANES * TB * M4_BLK;
-    const size_t bytes = (size_t)s->mm4_rows * s->mm_kbytes;
+    const size_t bytes = (size_t)s->mm4_rows * s->mm4_kbytes;
     GW_CUDA(reserve_raw(s->d_mm4, s->cap_mm4, bytes));
     GW_CUDA(cudaMemsetAsync(s->d_mm4, 0, bytes, s->stream));
-    const uint32_t K = s->Kc + s->Kt;
-    const uint64_t work = s->M * K;
-#define EXPAND4(MODE_) expand_mma4_kernel<MODE_><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, \
-                                                            s->n_case, s->n_ctrl, case_bytes, s->mm_kbytes, s->M, s->d_mm4)
-    if (mode == 1) EXPAND4(1); else if (mode == 2) EXPAND4(2); else EXPAND4(0);
-#undef EXPAND4
+    if (mode == 2) {
+        { const int rc = gwasdev_internal_ensure_compacted(s); if (rc != GWASDEV_OK) return rc; }
+        const uint32_t K = s->Kc + s->Kt;
+        const uint64_t work = s->M * K;
+        expand_mma4_kernel<2><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Kc, s->Kt, s->n_case, s->n_ctrl,
+                                                                                    case_bytes, s->mm4_kbytes, s->M, s->d_mm4);
+    } else {
+        const uint64_t work = s->M * s->Wr;
+        const unsigned blocks = (unsigned)((work + 255) / 256);
+        if (mode == 1) expand_raw_kernel<1><<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask, s->mm4_kbytes, s->M, s->d_mm4);
+        else expand_raw_kernel<0><<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask, s->mm4_kbytes, s->M, s->d_mm4);
+    }
     GW_LAUNCHED();
     if (!s->tmap_mm4 && posix_memalign(&s->tmap_mm4, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm4 = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
     encode_tiled_fn encode = nullptr;
     { int rc = get_encode_tiled(&encode); if (rc != GWASDEV_OK) return rc; }
-    cuuint64_t gdim[2] = {s->mm_kbytes, s->mm4_rows};
-    cuuint64_t gstride[1] = {s->mm_kbytes};
+    cuuint64_t gdim[2] = {s->mm4_kbytes, s->mm4_rows};
+    cuuint64_t gstride[1] = {s->mm4_kbytes};
     cuuint32_t box[2] = {(cuuint32_t)MMA_KB, (cuuint32_t)(2 * MMA_A_SNPS)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode((CUtensorMap *)s->tmap_mm4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s->d_mm4, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1360,7 +1374,7 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, const CandSink &sink, uint32_
     int rc = ensure_mma4_inputs(s, mode);
     if (rc != GWASDEV_OK) return rc;
     Mma4Params p;
-    p.TB = m4_blocks(s); p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M; p.n_tiles = s->mm4_tiles;
+    p.TB = m4_blocks(s); p.NKB = s->mm4_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M; p.n_tiles = s->mm4_tiles;
     p.case_kb = round_up(s->n_case, MMA_KB) / MMA_KB;
     p.shard = shard; p.n_shards = n_shards; p.side = s->d_side; p.tile_missing = s->d_tile_missing;
     const uint32_t n_ind = s->n_case + s->n_ctrl;
@@ -1533,7 +1547,7 @@ int gwasdev_ksa_screen_mma_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi,
     GW_CUDA(cudaMemcpyAsync(s->sc_pi.p, pi, n * 4, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->sc_pj.p, pj, n * 4, cudaMemcpyHostToDevice, s->stream));
     screen_probe_mma_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
-        s->d_sel, 2 * (s->Wc + s->Wt), s->Wc, s->Wt, (const MmaRow *)s->d_mma_row, (const MmaCol *)s->d_mma_col,
+        pair_src(s), (const MmaRow *)s->d_mma_row, (const MmaCol *)s->d_mma_col,
         (const MmaRowF *)((const MmaRow *)s->d_mma_row + Msnp), (const MmaColF *)((const MmaCol *)s->d_mma_col + Msnp),
         (const uint32_t *)s->sc_pi.p, (const uint32_t *)s->sc_pj.p, n, (float)(s->n_case + s->n_ctrl), s->mma_qc, s->mma_q0,
         (float *)s->sc_a.p);

@@ -694,6 +694,8 @@ int gwasdev_set_select_mode(gwasdev_store *s, int eager) {
     return GWASDEV_OK;
 }
 
+int gwasdev_is_compacted(const gwasdev_store *s) { return (!s || !s->selected) ? -1 : (s->sel_built ? 1 : 0); }
+
 int gwasdev_case_control_counts(gwasdev_store *s, uint32_t *n_case, uint32_t *n_ctrl) {
     GW_REQUIRE(s && s->selected, "gwasdev_case_control_counts: no case/control selection");
     if (n_case) *n_case = s->n_case;

@@ -310,6 +310,35 @@ def test_reselection_scans_use_cached_row_totals(orc):
         assert np.array_equal(st.marginal_scan(mi=False, stats=False)["counts"], orc.cc_counts_selected(sel, nca, nco))
 
 
+@pytest.mark.parametrize("miss", [0.0, 0.02])
+def test_hot_paths_never_compact(orc, miss):
+    """Marginal scans of a partitioned cohort, the tensor-core screen (operands, fp64 re-score) and the G-test read the raw rows
+    through the class masks: K0 runs only for the layout probes, and running it afterwards changes nothing."""
+    M, N, NCASE = 500, 1100, 520
+    codes, pheno = planted_cohort(orc, 313, M, N, NCASE, miss, 6)
+    with make_store(orc, codes, pheno) as st, make_store(orc, codes) as eager:
+        eager.set_select_mode(True)
+        eager.select_case_control(pheno)
+        assert eager.is_compacted() and not st.is_compacted()
+        a, b = st.marginal_scan(), eager.marginal_scan()
+        assert all(a[k].tobytes() == b[k].tobytes() for k in a)
+        st.marginal_scan()                                                  # a second and third scan: still through the masks
+        h, s = st.pairwise_scan(30.0)
+        he, _ = eager.pairwise_scan(30.0)
+        assert s.engine == 2 and len(h) >= 3 and np.array_equal(h, he)
+        g, ge = st.gtest(h["i"], h["j"]), eager.gtest(he["i"], he["j"])
+        assert np.array_equal(g[0], ge[0]) and np.array_equal(g[1], ge[1], equal_nan=True)
+        pi, pj = np.triu_indices(60, 1)
+        assert np.array_equal(st.ksa(pi, pj), eager.ksa(pi, pj), equal_nan=True)
+        assert np.array_equal(st.pair_tables(pi, pj, mode=3), eager.pair_tables(pi, pj, mode=3))
+        top, _ = st.pairwise_topk(3, 30.0)
+        assert not st.is_compacted()                                        # none of the above needed the compacted layout
+        sel = st.get_selected_rows()                                        # the layout probe does
+        assert st.is_compacted() and np.array_equal(sel, eager.get_selected_rows())
+        h2, _ = st.pairwise_scan(30.0)
+        assert np.array_equal(h2, h)
+
+
 def test_tensor_peak_probe_is_plausible():
     burst, sustained = gw.i8_peak(0)
     assert 500.0 < sustained <= burst * 1.02 and burst < 5000.0, (burst, sustained)   # nominal dense int8: 4 500 TOP/s
