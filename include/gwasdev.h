@@ -111,6 +111,8 @@ GWASDEV_API int gwasdev_synchronize(gwasdev_store *s);
 #define GWASDEV_OPT_FOUR_PLANE 6     /* 0 auto; 1: tiles with missing calls stay on the 9-cell AND+POPC kernel */
 #define GWASDEV_OPT_ROW_TOTALS 7     /* K1': 0 auto (row totals cached per table when the classes partition the cohort); 1 never */
 #define GWASDEV_OPT_CAND_CAPACITY 8  /* pairwise screen: candidate buffer entries (0 auto); small values exercise the overflow paths */
+#define GWASDEV_OPT_CLASSIC_PLANES 9 /* two-plane tensor-core screen: 0 auto (every SNP puts its two rarest genotype classes on the tensor cores);
+                                        1: always the two homozygote planes, as the reference's shortcut counts them */
 #define GWASDEV_OPT_COUNT 16
 GWASDEV_API int gwasdev_set_option(gwasdev_store *s, int option, long long value);
 

@@ -35,7 +35,7 @@ assert COMPACT_DTYPE.itemsize == 32 and SIG_DTYPE.itemsize == 48
 
 # gwasdev_set_option keys (include/gwasdev.h)
 OPT_SELECT_KERNEL, OPT_LANES_PER_ROW, OPT_INGEST_CHUNK, OPT_SCAN_PIECES, OPT_MASKED_SCAN, OPT_TRACE, OPT_FOUR_PLANE, \
-    OPT_ROW_TOTALS, OPT_CAND_CAPACITY = range(9)
+    OPT_ROW_TOTALS, OPT_CAND_CAPACITY, OPT_CLASSIC_PLANES = range(10)
 
 
 class PairStats(C.Structure):

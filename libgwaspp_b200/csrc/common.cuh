@@ -176,6 +176,8 @@ struct gwasdev_store {
     int8_t *d_mm = nullptr;
     void *tmap_mm = nullptr;      // host copies of the two CUtensorMaps (A box, B box)
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
+    uint8_t *d_plane_derived = nullptr;                // per SNP: the genotype class (0 aa, 1 ab, 2 bb) the two-plane operands leave out
+    size_t cap_plane = 0;
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
     // four-plane operands (aa, bb, xx, padding) for the tiles with missing calls (pair_screen_mma4_kernel)
     bool mm4_built = false;

@@ -659,6 +659,29 @@ i8_peak_kernel(uint32_t kblocks, uint32_t seed) {
     }
 }
 
+// ---- which two genotype classes a SNP puts on the tensor cores ----------------------------------------
+// Any two of a SNP's three genotype planes determine the pair tables once the per-SNP class counts are known (the
+// reference's own shortcut derives the heterozygote cells from the two homozygote planes, compressed_genotype_table5.cpp:
+// 1084-1092). The statistic does not care how a SNP's genotypes are labelled, so every SNP puts its two RAREST classes on
+// the tensor cores and derives the commonest one: the operand bytes of a SNP with a 10 % minor allele are then 19 %
+// non-zero instead of 82 %, which is what the multipliers and the operand buses toggle on. `derived` (0 aa, 1 ab, 2 bb; 1 =
+// the reference's choice) is per SNP; "role" 0 / 2 are the two planes in genotype order, role 1 the derived class, and all
+// per-SNP epilogue records are stored by role, so nothing downstream knows.
+__device__ __forceinline__ void plane_roles(uint32_t derived, int (&perm)[3]) {
+    perm[0] = derived == 0 ? 1 : 0; perm[1] = (int)derived; perm[2] = derived == 2 ? 1 : 2;
+}
+__global__ void plane_choice_kernel(const gwasdev_marginal_information *__restrict__ mi, uint64_t M, uint64_t Mrec, int classic,
+                                    uint8_t *__restrict__ derived) {
+    const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (snp >= Mrec) return;
+    uint32_t d = 1;
+    if (!classic && snp < M) {
+        const uint32_t a = mi[snp].margins[0], h = mi[snp].margins[1], b = mi[snp].margins[2];
+        if (a > h && a >= b) d = 0; else if (b > h && b > a) d = 2;      // ties keep the heterozygote derived
+    }
+    derived[snp] = (uint8_t)d;
+}
+
 // ---- operand matrix: raw rows + class masks -> signed one-hot bytes ------------------------------------
 __device__ __forceinline__ uint32_t spread4(uint32_t nibble) { return (nibble * 0x00204081u) & 0x01010101u; }   // bit i -> byte i
 
@@ -680,7 +703,7 @@ __device__ __forceinline__ void store_class_bytes(int8_t *dst, uint32_t xc, uint
 
 template <int LAYOUT>
 __global__ void expand_raw_kernel(const uint32_t *__restrict__ raw, uint32_t Wr, const uint32_t *__restrict__ mca, const uint32_t *__restrict__ mco,
-                                  uint32_t kbytes, uint64_t M, int8_t *__restrict__ mm) {
+                                  uint32_t kbytes, uint64_t M, const uint8_t *__restrict__ derived, int8_t *__restrict__ mm) {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t snp = idx / Wr;
     if (snp >= M) return;
@@ -692,10 +715,16 @@ __global__ void expand_raw_kernel(const uint32_t *__restrict__ raw, uint32_t Wr,
     if (LAYOUT == 1) {
         store_class_bytes(row, aa & ca, 0u);                     store_class_bytes(row + kbytes, bb & ca, 0u);
         store_class_bytes(row + 2ull * kbytes, aa & co, 0u);     store_class_bytes(row + 3ull * kbytes, bb & co, 0u);
-    } else {
+    } else if (LAYOUT == 0) {
         store_class_bytes(row, aa & ca, aa & co);
         store_class_bytes(row + kbytes, bb & ca, bb & co);
-        if (LAYOUT == 0) { const uint32_t xx = ~(p1 | p2); store_class_bytes(row + 2ull * kbytes, xx & ca, xx & co); }     // the padding row stays zero (memset)
+        const uint32_t xx = ~(p1 | p2);
+        store_class_bytes(row + 2ull * kbytes, xx & ca, xx & co);       // the padding row stays zero (memset)
+    } else {
+        const uint32_t d = derived[snp], ab = p2 ^ bb;
+        const uint32_t g0 = d == 0 ? ab : aa, g2 = d == 2 ? ab : bb;    // roles 0 and 2 (plane_roles)
+        store_class_bytes(row, g0 & ca, g0 & co);
+        store_class_bytes(row + kbytes, g2 & ca, g2 & co);
     }
 }
 
@@ -1013,13 +1042,15 @@ __global__ void expand_mma4_kernel(const uint32_t *__restrict__ sel, uint32_t se
 }
 
 __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__ mi, uint64_t M, uint64_t Mrec, uint32_t n_ind,
-                                MmaRow *__restrict__ row, MmaCol *__restrict__ col, MmaRowF *__restrict__ rowf, MmaColF *__restrict__ colf) {
+                                const uint8_t *__restrict__ derived, MmaRow *__restrict__ row, MmaCol *__restrict__ col, MmaRowF *__restrict__ rowf, MmaColF *__restrict__ colf) {
     const uint64_t snp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (snp >= Mrec) return;
     MmaRow r; MmaCol c;
     r.pad[0] = r.pad[1] = r.pad[2] = c.pad[0] = c.pad[1] = c.pad[2] = 0.f;
     const float qnan = __int_as_float(0x7fc00000);
     float rp[2][3], cw[2][3], cn[2][3];
+    int perm[3];
+    plane_roles(derived[snp], perm);
     if (snp < M) {
         const gwasdev_marginal_information m = mi[snp];
         double Cr = (double)n_ind * log2((double)n_ind), Cc = 0.0;
@@ -1027,11 +1058,12 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
         for (int k = 0; k < 2; ++k) {
             const uint32_t *cnt = k ? m.controls : m.cases;
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
+            for (int role = 0; role < 3; ++role) {         // records are stored by role: planes in genotype order at 0 and 2, the derived class at 1
+                const int g = perm[role];
                 const double pca = m.dPca[4 * k + g], pbc = m.dPbc[4 * k + g], mar = (double)m.margins[g];
-                rp[k][g] = (float)pca;
-                cw[k][g] = m.margins[g] > 0 ? (float)(pbc / mar) : qnan;
-                cn[k][g] = (float)cnt[g];
+                rp[k][role] = (float)pca;
+                cw[k][role] = m.margins[g] > 0 ? (float)(pbc / mar) : qnan;
+                cn[k][role] = (float)cnt[g];
                 if (cnt[g] > 0) { Cr += (double)cnt[g] * log2(pca); Cc += (double)cnt[g] * (log2(pbc) - log2(mar)); }
             }
         }
@@ -1080,7 +1112,7 @@ __global__ void mma_side_kernel(const gwasdev_marginal_information *__restrict__
 }
 
 // fp32 value of the tensor-core engine's epilogue for given pairs (diagnostic twin of screen_probe_kernel)
-__global__ void screen_probe_mma_kernel(const PairSrc src, const MmaRow *__restrict__ row, const MmaCol *__restrict__ col,
+__global__ void screen_probe_mma_kernel(const PairSrc src, const uint8_t *__restrict__ derived, const MmaRow *__restrict__ row, const MmaCol *__restrict__ col,
                                         const MmaRowF *__restrict__ rowf, const MmaColF *__restrict__ colf,
                                         const uint32_t *__restrict__ pi, const uint32_t *__restrict__ pj, uint64_t n, float N,
                                         float qc, float q0, float *__restrict__ out) {
@@ -1093,8 +1125,11 @@ __global__ void screen_probe_mma_kernel(const PairSrc src, const MmaRow *__restr
 #pragma unroll
         for (int q = 0; q < 16; ++q) { t0[q] = 0; t1[q] = 0; }
         core_counts_src(src, i, j, 0, 1, t0, t1);
-        c[0][0] = t0[0]; c[0][1] = t0[2]; c[0][2] = t0[8]; c[0][3] = t0[10];      // AA_BB, AA_bb, aa_BB, aa_bb
-        c[1][0] = t1[0]; c[1][1] = t1[2]; c[1][2] = t1[8]; c[1][3] = t1[10];
+        int pa[3], pb[3];
+        plane_roles(derived[i], pa); plane_roles(derived[j], pb);
+        // the four corners the kernel counts: (role 0 | 2 of A) x (role 0 | 2 of B); AA_BB, AA_bb, aa_BB, aa_bb with the reference's planes
+        c[0][0] = t0[4 * pa[0] + pb[0]]; c[0][1] = t0[4 * pa[0] + pb[2]]; c[0][2] = t0[4 * pa[2] + pb[0]]; c[0][3] = t0[4 * pa[2] + pb[2]];
+        c[1][0] = t1[4 * pa[0] + pb[0]]; c[1][1] = t1[4 * pa[0] + pb[2]]; c[1][2] = t1[4 * pa[2] + pb[0]]; c[1][3] = t1[4 * pa[2] + pb[2]];
     }
     float2 pca[3], ca[3], w[3], cb[3]; float Crow, Ccol;
     load_record(row + i, pca, ca, Crow);
@@ -1156,6 +1191,9 @@ static void bound_constants(uint32_t n_case, uint32_t n, float *qc_out, float *q
 static int ensure_mma_inputs(gwasdev_store *s) {
     const uint64_t Msnp = (s->M + MMA_B_SNPS - 1) / MMA_B_SNPS * MMA_B_SNPS;
     if (!s->mm_built) {
+        GW_CUDA(reserve_raw(s->d_plane_derived, s->cap_plane, Msnp));
+        plane_choice_kernel<<<(unsigned)((Msnp + 255) / 256), 256, 0, s->stream>>>(s->d_mi, s->M, Msnp, s->opt[GWASDEV_OPT_CLASSIC_PLANES] != 0, s->d_plane_derived);
+        GW_LAUNCHED();
         s->mm_kbytes = 32 * s->Wr;                             // one byte per sample position of the raw row (Wr is a multiple of 4 words: 128-byte blocks)
         s->mm_rows = 2 * Msnp;
         const size_t bytes = (size_t)s->mm_rows * s->mm_kbytes;
@@ -1163,7 +1201,7 @@ static int ensure_mma_inputs(gwasdev_store *s) {
         if (Msnp > s->M) GW_CUDA(cudaMemsetAsync(s->d_mm + 2 * s->M * (size_t)s->mm_kbytes, 0, (size_t)(2 * (Msnp - s->M)) * s->mm_kbytes, s->stream));   // rows of the SNPs beyond the table
         const uint64_t work = s->M * s->Wr;
         expand_raw_kernel<-1><<<(unsigned)((work + 255) / 256), 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask,
-                                                                                   s->mm_kbytes, s->M, s->d_mm);
+                                                                                   s->mm_kbytes, s->M, s->d_plane_derived, s->d_mm);
         GW_LAUNCHED();
         if (!s->tmap_mm && posix_memalign(&s->tmap_mm, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
         int rc;
@@ -1189,7 +1227,7 @@ static int ensure_mma_inputs(gwasdev_store *s) {
         GW_CUDA(reserve_raw(row, s->cap_mma_row, Msnp * (sizeof(MmaRow) + sizeof(MmaRowF))));
         GW_CUDA(reserve_raw(col, s->cap_mma_col, Msnp * (sizeof(MmaCol) + sizeof(MmaColF))));
         s->d_mma_row = row; s->d_mma_col = col;
-        mma_side_kernel<<<(unsigned)((Msnp + 127) / 128), 128, 0, s->stream>>>(s->d_mi, s->M, Msnp, s->n_case + s->n_ctrl, row, col,
+        mma_side_kernel<<<(unsigned)((Msnp + 127) / 128), 128, 0, s->stream>>>(s->d_mi, s->M, Msnp, s->n_case + s->n_ctrl, s->d_plane_derived, row, col,
                                                                              (MmaRowF *)(row + Msnp), (MmaColF *)(col + Msnp));
         GW_LAUNCHED();
         s->mma_side_valid = true;
@@ -1326,8 +1364,8 @@ static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
     } else {
         const uint64_t work = s->M * s->Wr;
         const unsigned blocks = (unsigned)((work + 255) / 256);
-        if (mode == 1) expand_raw_kernel<1><<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask, s->mm4_kbytes, s->M, s->d_mm4);
-        else expand_raw_kernel<0><<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask, s->mm4_kbytes, s->M, s->d_mm4);
+        if (mode == 1) expand_raw_kernel<1><<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask, s->mm4_kbytes, s->M, nullptr, s->d_mm4);
+        else expand_raw_kernel<0><<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask, s->mm4_kbytes, s->M, nullptr, s->d_mm4);
     }
     GW_LAUNCHED();
     if (!s->tmap_mm4 && posix_memalign(&s->tmap_mm4, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm4 = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
@@ -1512,6 +1550,10 @@ int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *
     GW_CUDA(cudaSetDevice(s->device));
     int rc = gwasdev_internal_ensure_side(s);
     if (rc != GWASDEV_OK) return rc;
+    // the probe reports the corners of the two homozygote planes: operands with the reference's planes for this call
+    const long long planes_opt = s->opt[GWASDEV_OPT_CLASSIC_PLANES];
+    struct Restore { gwasdev_store *s; long long v; ~Restore() { s->opt[GWASDEV_OPT_CLASSIC_PLANES] = v; if (!v) { s->mm_built = false; s->mma_side_valid = false; } } } restore{s, planes_opt};
+    if (!planes_opt) { s->opt[GWASDEV_OPT_CLASSIC_PLANES] = 1; s->mm_built = false; s->mma_side_valid = false; }
     if ((rc = ensure_mma_inputs(s)) != GWASDEV_OK) return rc;
     MmaParams p;
     fill_params(s, p, 0, 1);
@@ -1547,7 +1589,7 @@ int gwasdev_ksa_screen_mma_f32(gwasdev_store *s, uint64_t n, const uint32_t *pi,
     GW_CUDA(cudaMemcpyAsync(s->sc_pi.p, pi, n * 4, cudaMemcpyHostToDevice, s->stream));
     GW_CUDA(cudaMemcpyAsync(s->sc_pj.p, pj, n * 4, cudaMemcpyHostToDevice, s->stream));
     screen_probe_mma_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(
-        pair_src(s), (const MmaRow *)s->d_mma_row, (const MmaCol *)s->d_mma_col,
+        pair_src(s), s->d_plane_derived, (const MmaRow *)s->d_mma_row, (const MmaCol *)s->d_mma_col,
         (const MmaRowF *)((const MmaRow *)s->d_mma_row + Msnp), (const MmaColF *)((const MmaCol *)s->d_mma_col + Msnp),
         (const uint32_t *)s->sc_pi.p, (const uint32_t *)s->sc_pj.p, n, (float)(s->n_case + s->n_ctrl), s->mma_qc, s->mma_q0,
         (float *)s->sc_a.p);

@@ -17,6 +17,7 @@ ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--shards", type=int, default=1)
 ap.add_argument("--missing", type=float, default=0.0, help="per-genotype missing rate of the synthetic cohort")
 ap.add_argument("--engine", type=int, default=0)
+ap.add_argument("--classic-planes", action="store_true", help="two homozygote planes per SNP instead of the two rarest genotype classes")
 ap.add_argument("--lib", default="", help="alternative libgwasdev.so (A/B timing of kernel variants)")
 a = ap.parse_args()
 if a.lib:
@@ -26,6 +27,8 @@ with gw.GenoStore(a.snps, a.samples) as st:
     st.simulate(20121127, missing_rate=a.missing)
     st.select_case_control(gw.simulate_phenotype(20121127, a.samples, ncase))
     st.set_pair_engine(a.engine)
+    if a.classic_planes:
+        st.set_option(gw.OPT_CLASSIC_PLANES, 1)
     for r in range(a.reps):
         hits, s = st.pairwise_scan(30.0, shard=0, n_shards=a.shards)
         print(f"rep {r}: engine {s.engine} tiles {s.tiles} (9-cell {s.tiles_nine_cell}) screen {s.screen_ms:.3f} ms total {s.total_ms:.3f} ms pairs {s.pairs_tested} "
