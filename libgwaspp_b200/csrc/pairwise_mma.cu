@@ -141,6 +141,25 @@ __device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *m
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar) & PEER_MASK) : "memory");
 }
+// the same for a 3-D box (sample bytes, planes, SNPs)
+__device__ __forceinline__ void tma_load_3d_pair(void *dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+// 24 accumulator columns (eight B-SNPs of three planes) of this warp's 32 lanes
+__device__ __forceinline__ void tc_ld24(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23])
+        : "r"(taddr + 16u) : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -181,7 +200,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return d;
 }
 // instruction descriptor kind::i8: D s32, A and B signed 8-bit, both K-major, N >> 3, M >> 4
-constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MMA_N >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24);   // M = 256 over the CTA pair
+constexpr uint32_t idesc_i8(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(MMA_M >> 4) << 24); }   // M = 256 over the CTA pair
+constexpr uint32_t IDESC_I8 = idesc_i8(MMA_N);
 
 // ---- tile order -------------------------------------------------------------------------------------
 // Tiles are pairs of 128-SNP blocks (I2 <= J). Band b holds A-blocks [8b, 8b+8); inside a band tiles run
@@ -778,8 +798,13 @@ __device__ __forceinline__ uint32_t sel4(uint32_t k, uint32_t a, uint32_t b, uin
 //                epilogue of a tile no longer overlaps the MMAs of the next). All tiles of such a cohort take it.
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MMA_THREADS, 1)
-pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Params p) {
+pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid_constant__ CUtensorMap map_b3, const Mma4Params p) {
     constexpr bool SPLIT = MODE == 1, TWOACC = MODE == 2;
+    // B side: the padding plane never enters a pair's table, so the missing-call layouts send only three rows per B-SNP to the
+    // tensor cores (a 3-D TMA box over the same matrix: sample bytes x 3 of the 4 planes x 32 SNPs = 96 dense rows): N = 192.
+    constexpr int CPB = SPLIT ? 4 : 3;                            // accumulator columns per B-SNP
+    constexpr int B_BYTES = MMA_B_SNPS / 4 * CPB * MMA_KB;        // this CTA's half of B per sample block (32 SNPs)
+    constexpr uint32_t IDESC = idesc_i8(M4_BLK * CPB);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
@@ -828,11 +853,12 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                     const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
                     mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
                     unsigned char *dst = sm + st * STAGE_BYTES_MMA;
-                    if (rank == 0) mbar_expect_tx(&full[st], nk * 2 * KB_BYTES);
+                    if (rank == 0) mbar_expect_tx(&full[st], nk * 2 * (A_STAGE_BYTES + B_BYTES));
                     else mbar_arrive_remote(&full[st], 0);
                     for (uint32_t k2 = 0; k2 < nk; ++k2) {
                         tma_load_2d_pair(dst + k2 * KB_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), a_row, &full[st]);
-                        tma_load_2d_pair(dst + k2 * KB_BYTES + A_STAGE_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), b_row, &full[st]);
+                        if (SPLIT) tma_load_2d_pair(dst + k2 * KB_BYTES + A_STAGE_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), b_row, &full[st]);
+                        else tma_load_3d_pair(dst + k2 * KB_BYTES + A_STAGE_BYTES, &map_b3, (int)((kb + k2) * MMA_KB), 0, b_row / M4_PLANES, &full[st]);
                     }
                 }
             }
@@ -865,7 +891,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                         const uint32_t first_blk = ctrl ? p.case_kb : 0u;
 #pragma unroll
                         for (int k = 0; k < MMA_KB / UMMA_K; ++k)
-                            tc_mma_i8(d_blk, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC_I8, (blk != first_blk) || k != 0);
+                            tc_mma_i8(d_blk, ad + (uint64_t)(k * UMMA_K >> 4), bd + (uint64_t)(k * UMMA_K >> 4), IDESC, (blk != first_blk) || k != 0);
                     }
                     tc_commit_mc(&empty[st], 3);
                 }
@@ -877,7 +903,8 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
         // ===== epilogue (both CTAs: own 32 A-SNPs x the tile's 64 B-SNPs) =====
         const int ew = warp;
         const int q = warp & 3;                       // TMEM lane quadrant: rows 32q.. = A-SNPs 8q..8q+7 of this CTA
-        const int g = ew >> 2;                        // column group: 64 accumulator columns = 16 B-SNPs
+        const int g = ew >> 2;                        // column group: 16 B-SNPs = 16 * CPB accumulator columns
+        auto ld_half = [&](uint32_t taddr, uint32_t (&v)[32]) { if (SPLIT) tc_ld32(taddr, v); else tc_ld24(taddr, v); };
         const int a_loc = 8 * q + (lane >> 2);        // A-SNP of this lane inside the CTA's 32
         const uint32_t pl = (uint32_t)lane & 3u;      // plane held by this lane's TMEM row (0 aa, 1 bb, 2 xx, 3 padding)
         const unsigned qbase = (unsigned)lane & ~3u;
@@ -909,7 +936,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                 uint32_t v[32];
                 uint32_t Dctl[2][4][3];                  // TWOACC: the control accumulator's products, exchanged first
                 if (TWOACC) {
-                    tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + ACC_COLS + 64 * g + 32 * h, v);
+                    ld_half(tmem_base + ((uint32_t)(32 * q) << 16) + ACC_COLS + 8 * CPB * (2 * g + h), v);
                     tc_wait_ld();
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
@@ -919,14 +946,14 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                         for (int e = 0; e < 2; ++e)
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
-                                const uint32_t mine = sel4(d, v[16 * e + 0 + c], v[16 * e + 4 + c], v[16 * e + 8 + c], v[16 * e + 12 + c]);
+                                const uint32_t mine = sel4(d, v[4 * CPB * e + c], v[4 * CPB * e + CPB + c], v[4 * CPB * e + 2 * CPB + c], v[4 * CPB * e + 3 * CPB + c]);
                                 Dctl[e][r][c] = __shfl_sync(0xffffffffu, mine, src);
                             }
                     }
                 }
-                tc_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 64 * g + 32 * h, v);
+                ld_half(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 8 * CPB * (2 * g + h), v);
                 tc_wait_ld();
-                // columns 4s..4s+3 = planes (aa, bb, xx, pad) of B-SNP s of this load (s < 8). Lane o of the quad owns the
+                // columns CPB s .. CPB s + CPB - 1 = planes of B-SNP s of this load (s < 8). Lane o of the quad owns the
                 // pairs (a, s) for s = o and o + 4. In rotation r every lane reads from quad lane (o + r) & 3 the three
                 // products that lane holds for the reader's two pairs: D[e][r][c] = product (plane (o + r) & 3 of A,
                 // plane c of B-SNP o + 4e).
@@ -940,7 +967,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const Mma4Pa
                     for (int e = 0; e < 2; ++e)
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
-                            const uint32_t mine = sel4(d, v[16 * e + 0 + c], v[16 * e + 4 + c], v[16 * e + 8 + c], v[16 * e + 12 + c]);
+                            const uint32_t mine = sel4(d, v[4 * CPB * e + c], v[4 * CPB * e + CPB + c], v[4 * CPB * e + 2 * CPB + c], v[4 * CPB * e + 3 * CPB + c]);
                             D[e][r][c] = __shfl_sync(0xffffffffu, mine, src);
                         }
                 }
@@ -1368,7 +1395,7 @@ static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
         else expand_raw_kernel<0><<<blocks, 256, 0, s->stream>>>(s->d_raw, s->Wr, s->d_case_sel_mask, s->d_ctrl_sel_mask, s->mm4_kbytes, s->M, nullptr, s->d_mm4);
     }
     GW_LAUNCHED();
-    if (!s->tmap_mm4 && posix_memalign(&s->tmap_mm4, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm4 = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
+    if (!s->tmap_mm4 && posix_memalign(&s->tmap_mm4, 64, 2 * sizeof(CUtensorMap)) != 0) { s->tmap_mm4 = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
     encode_tiled_fn encode = nullptr;
     { int rc = get_encode_tiled(&encode); if (rc != GWASDEV_OK) return rc; }
     cuuint64_t gdim[2] = {s->mm4_kbytes, s->mm4_rows};
@@ -1378,6 +1405,15 @@ static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
     CUresult r = encode((CUtensorMap *)s->tmap_mm4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s->d_mm4, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (four-plane operand matrix) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
+    {   // the B side of the missing-call layouts: planes 0..2 of 32 SNPs as one dense 96-row box
+        cuuint64_t gdim3[3] = {s->mm4_kbytes, (cuuint64_t)M4_PLANES, s->mm4_rows / M4_PLANES};
+        cuuint64_t gstride3[2] = {s->mm4_kbytes, (cuuint64_t)M4_PLANES * s->mm4_kbytes};
+        cuuint32_t box3[3] = {(cuuint32_t)MMA_KB, 3, (cuuint32_t)(MMA_B_SNPS / 4)};
+        cuuint32_t estr3[3] = {1, 1, 1};
+        r = encode((CUtensorMap *)s->tmap_mm4 + 1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s->d_mm4, gdim3, gstride3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (three-plane B box) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
+    }
     s->mm4_tiles = m4_schedule_tiles(TB);
     s->mm4_built = true;
     s->mm4_mode = mode;
@@ -1427,7 +1463,7 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, const CandSink &sink, uint32_
 #define SCREEN4(MODE_)                                                                                                         \
     do {                                                                                                                       \
         GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-        pair_screen_mma4_kernel<MODE_><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm4, p);      \
+        pair_screen_mma4_kernel<MODE_><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(((const CUtensorMap *)s->tmap_mm4)[0], ((const CUtensorMap *)s->tmap_mm4)[1], p); \
     } while (0)
     if (mode == 1) SCREEN4(1); else if (mode == 2) SCREEN4(2); else SCREEN4(0);
 #undef SCREEN4
