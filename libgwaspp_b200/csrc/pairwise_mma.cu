@@ -765,10 +765,56 @@ __global__ void expand_raw_kernel(const uint32_t *__restrict__ raw, uint32_t Wr,
 // the eight pairs of a 32-column load, builds the 3x3x2 table and evaluates ksa_screen_f32 (the epilogue of the
 // AND+POPC kernel it replaces). Only tiles with a missing call in either block are computed; the others belong to
 // pair_screen_mma_kernel.
+// fp32 screen value of a 3x3x2 table whose SNPs may have missing calls: ksa_screen_f32's formula (pair_common.cuh) with the 27
+// n log n terms as n * lg2.approx(n + 2^-126) in log2 units (the two-plane kernel's form: 0 * lg2(2^-126) = -0 for an empty cell)
+// and the row / column sums taken on the integer table. A column without samples has w = NaN, which reaches tau through
+// 0 * NaN exactly as in ksa_screen_f32: such a pair compares false against any threshold.
+__device__ __forceinline__ float ksa_screen_table(const uint32_t (&n)[2][3][3], const PairSide &A, const PairSide &B, float N, float lnN) {
+    const float tiny = 1.17549435e-38f;
+    float S2 = 0.f, tau = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const float c0 = u2f(n[0][a][b]), c1 = u2f(n[1][a][b]), cab = c0 + c1;
+            const float W = fmaf(B.w[0][b], A.pca[0][a], B.w[1][b] * A.pca[1][a]);
+            tau = fmaf(cab, W, tau);
+            S2 = fmaf(c0, lg2_approx(c0 + tiny), S2);
+            S2 = fmaf(c1, lg2_approx(c1 + tiny), S2);
+            S2 = fmaf(-cab, lg2_approx(cab + tiny), S2);
+        }
+    float L = 0.f;
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            const uint32_t row = n[k][g][0] + n[k][g][1] + n[k][g][2], col = n[k][0][g] + n[k][1][g] + n[k][2][g];
+            L = fmaf(u2f(row), A.lpca[k][g], L);
+            L = fmaf(u2f(col), B.lw[k][g], L);
+            total += row;
+        }
+    L = fmaf(u2f(total), lnN, L);
+    return 2.0f * fmaf(0.69314718056f, fmaf(N, lg2_approx(tau), S2), -L);
+}
+
 constexpr int M4_PLANES = 4;
 constexpr int M4_A_SNPS = 2 * MMA_A_SNPS / M4_PLANES;        // 32 A-SNPs per CTA (128 rows)
 constexpr int M4_BLK = MMA_N / M4_PLANES;                    // 64 SNPs per schedule block = B-SNPs of a tile
 static_assert(M4_BLK == TILE, "the four-plane tiles coincide with the 64-SNP missing-call blocks");
+
+// Shared memory of pair_screen_mma4_kernel<MODE>. The missing-call layouts (modes 0, 2) stage 96 B rows per sample block, and the
+// 24 KiB that frees carry the epilogue's product exchange: 1 600 bytes per warp (32 rows of twelve int32, rows skewed by 16 bytes
+// per eight lanes so that the quads' reads fall on different banks).
+constexpr int M4_XCH_WARP = 1600;
+template <int MODE> struct M4Smem {
+    static constexpr int CPB = MODE == 1 ? 4 : 3;
+    static constexpr int KBB = A_STAGE_BYTES + MMA_B_SNPS / 4 * CPB * MMA_KB;       // 32 KiB (split classes) or 28 KiB
+    static constexpr int STG = KPS * KBB;
+    static constexpr int XCH = MODE == 1 ? 0 : EPI_WARPS * M4_XCH_WARP;
+    static constexpr size_t BYTES = 1024 + (size_t)MMA_STAGES * STG + XCH + EPI_WARPS * COL_STAGE_BYTES + (2 * MMA_STAGES + 4) * sizeof(uint64_t) + 16;
+    static_assert(KBB % 1024 == 0 && BYTES <= 232448, "stage blocks keep the 1 KiB swizzle alignment; at most 227 KiB per CTA");
+};
 
 struct Mma4Params {
     uint32_t TB, NKB, n_bands;
@@ -805,10 +851,12 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
     constexpr int CPB = SPLIT ? 4 : 3;                            // accumulator columns per B-SNP
     constexpr int B_BYTES = MMA_B_SNPS / 4 * CPB * MMA_KB;        // this CTA's half of B per sample block (32 SNPs)
     constexpr uint32_t IDESC = idesc_i8(M4_BLK * CPB);
+    constexpr int KBB = M4Smem<MODE>::KBB, STG = M4Smem<MODE>::STG;   // bytes per sample block / per stage of this CTA
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *sm = smem_raw + (base - smem_u32(smem_raw));
-    unsigned char *col_sm = sm + MMA_STAGES * STAGE_BYTES_MMA;                 // per epilogue warp: PairSide records of its 16 B-SNPs
+    unsigned char *xch_sm = sm + MMA_STAGES * STG;                              // per epilogue warp: product exchange rows (missing-call layouts)
+    unsigned char *col_sm = xch_sm + M4Smem<MODE>::XCH;                         // per epilogue warp: PairSide records of its 16 B-SNPs
     uint64_t *full = reinterpret_cast<uint64_t *>(col_sm + EPI_WARPS * COL_STAGE_BYTES);
     uint64_t *empty = full + MMA_STAGES;
     uint64_t *tfull = empty + MMA_STAGES;
@@ -852,13 +900,13 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
                     const int st = (int)(it % MMA_STAGES);
                     const uint32_t nk = min((uint32_t)KPS, p.NKB - kb);
                     mbar_wait_wd(&empty[st], (uint32_t)(((it / MMA_STAGES) & 1) ^ 1));
-                    unsigned char *dst = sm + st * STAGE_BYTES_MMA;
+                    unsigned char *dst = sm + st * STG;
                     if (rank == 0) mbar_expect_tx(&full[st], nk * 2 * (A_STAGE_BYTES + B_BYTES));
                     else mbar_arrive_remote(&full[st], 0);
                     for (uint32_t k2 = 0; k2 < nk; ++k2) {
-                        tma_load_2d_pair(dst + k2 * KB_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), a_row, &full[st]);
-                        if (SPLIT) tma_load_2d_pair(dst + k2 * KB_BYTES + A_STAGE_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), b_row, &full[st]);
-                        else tma_load_3d_pair(dst + k2 * KB_BYTES + A_STAGE_BYTES, &map_b3, (int)((kb + k2) * MMA_KB), 0, b_row / M4_PLANES, &full[st]);
+                        tma_load_2d_pair(dst + k2 * KBB, &map_ab, (int)((kb + k2) * MMA_KB), a_row, &full[st]);
+                        if (SPLIT) tma_load_2d_pair(dst + k2 * KBB + A_STAGE_BYTES, &map_ab, (int)((kb + k2) * MMA_KB), b_row, &full[st]);
+                        else tma_load_3d_pair(dst + k2 * KBB + A_STAGE_BYTES, &map_b3, (int)((kb + k2) * MMA_KB), 0, b_row / M4_PLANES, &full[st]);
                     }
                 }
             }
@@ -883,7 +931,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
                     mbar_wait_wd(&full[st], (uint32_t)((it / MMA_STAGES) & 1));
                     tc_fence_after();
                     for (uint32_t k2 = 0; k2 < nk; ++k2) {
-                        const uint32_t a_addr = base + st * STAGE_BYTES_MMA + k2 * KB_BYTES, b_addr = a_addr + A_STAGE_BYTES;
+                        const uint32_t a_addr = base + st * STG + k2 * KBB, b_addr = a_addr + A_STAGE_BYTES;
                         const uint64_t ad = umma_desc(a_addr), bd = umma_desc(b_addr);
                         const uint32_t blk = kb + k2;                                      // 128-byte sample block of the row
                         const bool ctrl = TWOACC && blk >= p.case_kb;
@@ -904,7 +952,6 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
         const int ew = warp;
         const int q = warp & 3;                       // TMEM lane quadrant: rows 32q.. = A-SNPs 8q..8q+7 of this CTA
         const int g = ew >> 2;                        // column group: 16 B-SNPs = 16 * CPB accumulator columns
-        auto ld_half = [&](uint32_t taddr, uint32_t (&v)[32]) { if (SPLIT) tc_ld32(taddr, v); else tc_ld24(taddr, v); };
         const int a_loc = 8 * q + (lane >> 2);        // A-SNP of this lane inside the CTA's 32
         const uint32_t pl = (uint32_t)lane & 3u;      // plane held by this lane's TMEM row (0 aa, 1 bb, 2 xx, 3 padding)
         const unsigned qbase = (unsigned)lane & ~3u;
@@ -931,93 +978,115 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
             if (lane == 0) mbar_wait_wd(&tfull[buf], TWOACC ? (uint32_t)(tile_it & 1) : (uint32_t)((tile_it >> 1) & 1));
             __syncwarp();
             tc_fence_after();
+            // one pair's 3x3x2 table from its products and both SNPs' class counts, then the screen statistic
+            auto finish_pair = [&](uint64_t gj, const PairSide &B, const uint32_t (&prod)[CPB][CPB], const uint32_t (&prod_ctl)[3][3]) {
+                uint32_t n[2][3][3];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t *ca = A.cnt[k], *cb = B.cnt[k];     // aa, ab, bb, xx
+                    if (SPLIT) {
+                        const uint32_t AB = prod[2 * k][2 * k], Ab = prod[2 * k][2 * k + 1], aB = prod[2 * k + 1][2 * k], ab = prod[2 * k + 1][2 * k + 1];
+                        n[k][0][0] = AB; n[k][0][2] = Ab; n[k][2][0] = aB; n[k][2][2] = ab;
+                        n[k][0][1] = ca[0] - AB - Ab;
+                        n[k][2][1] = ca[2] - aB - ab;
+                        n[k][1][0] = cb[0] - AB - aB;
+                        n[k][1][2] = cb[2] - Ab - ab;
+                        n[k][1][1] = cb[1] - n[k][0][1] - n[k][2][1];
+                    } else {
+                        uint32_t x[3][3];   // x[P][c]: class-k count of (plane P of A) & (plane c of B); planes aa, bb, xx
+#pragma unroll
+                        for (int P = 0; P < 3; ++P)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c)
+                                x[P][c] = TWOACC ? (k ? prod_ctl[P][c] : prod[P][c]) : (k ? (prod[P][c] >> CTRL_SHIFT) : (prod[P][c] & 0x3fffu));
+                        n[k][0][0] = x[0][0]; n[k][0][2] = x[0][1]; n[k][2][0] = x[1][0]; n[k][2][2] = x[1][1];
+                        n[k][0][1] = ca[0] - x[0][0] - x[0][1] - x[0][2];
+                        n[k][2][1] = ca[2] - x[1][0] - x[1][1] - x[1][2];
+                        n[k][1][0] = cb[0] - x[0][0] - x[1][0] - x[2][0];
+                        n[k][1][2] = cb[2] - x[0][1] - x[1][1] - x[2][1];
+                        n[k][1][1] = ca[1] - n[k][1][0] - n[k][1][2] - (cb[3] - x[0][2] - x[1][2] - x[2][2]);
+                    }
+                }
+                const float stat = ksa_screen_table(n, A, B, p.N, p.lnN);
+                if (stat > thr_now) sink_push(p.sink, (uint32_t)gi, (uint32_t)gj, stat);
+            };
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 uint32_t v[32];
-                uint32_t Dctl[2][4][3];                  // TWOACC: the control accumulator's products, exchanged first
-                if (TWOACC) {
-                    ld_half(tmem_base + ((uint32_t)(32 * q) << 16) + ACC_COLS + 8 * CPB * (2 * g + h), v);
+                const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 8 * CPB * (2 * g + h);
+                // columns CPB s .. CPB s + CPB - 1 = planes of B-SNP s of this load (s < 8). Lane o of the quad owns the
+                // pairs (a, s) for s = o and o + 4 and needs the products of the quad's other planes for them.
+                if constexpr (SPLIT) {
+                    // through the registers: in rotation r every lane reads from quad lane (o + r) & 3 the four products that lane
+                    // holds for the reader's two pairs: D[e][r][c] = product (plane (o + r) & 3 of A, plane c of B-SNP o + 4e).
+                    tc_ld32(taddr, v);
                     tc_wait_ld();
+                    uint32_t D[2][4][4];
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const uint32_t d = (pl - (uint32_t)r) & 3u;
+                        const uint32_t d = (pl - (uint32_t)r) & 3u;          // the lane that reads from me in this rotation
                         const unsigned src = qbase | ((pl + (uint32_t)r) & 3u);
 #pragma unroll
                         for (int e = 0; e < 2; ++e)
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const uint32_t mine = sel4(d, v[4 * CPB * e + c], v[4 * CPB * e + CPB + c], v[4 * CPB * e + 2 * CPB + c], v[4 * CPB * e + 3 * CPB + c]);
-                                Dctl[e][r][c] = __shfl_sync(0xffffffffu, mine, src);
+                            for (int c = 0; c < 4; ++c) {
+                                const uint32_t mine = sel4(d, v[16 * e + c], v[16 * e + 4 + c], v[16 * e + 8 + c], v[16 * e + 12 + c]);
+                                D[e][r][c] = r == 0 ? mine : __shfl_sync(0xffffffffu, mine, src);
                             }
                     }
-                }
-                ld_half(tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS + 8 * CPB * (2 * g + h), v);
-                tc_wait_ld();
-                // columns CPB s .. CPB s + CPB - 1 = planes of B-SNP s of this load (s < 8). Lane o of the quad owns the
-                // pairs (a, s) for s = o and o + 4. In rotation r every lane reads from quad lane (o + r) & 3 the three
-                // products that lane holds for the reader's two pairs: D[e][r][c] = product (plane (o + r) & 3 of A,
-                // plane c of B-SNP o + 4e).
-                constexpr int NC = SPLIT ? 4 : 3;       // B planes a pair needs (the padding plane of the missing-call layout is never read)
-                uint32_t D[2][4][NC];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const uint32_t d = (pl - (uint32_t)r) & 3u;          // the lane that reads from me in this rotation
-                    const unsigned src = qbase | ((pl + (uint32_t)r) & 3u);
+                    for (int e = 0; e < 2; ++e) {
+                        const int b_loc = 16 * g + 8 * h + 4 * e + (int)pl;
+                        const uint64_t gj = (uint64_t)J * M4_BLK + b_loc;
+                        if (!(gi < gj && gj < p.M)) continue;
+                        uint32_t prod[CPB][CPB], none[3][3];                 // plane P of A is what arrived in rotation (P - o) & 3
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                        for (int P = 0; P < 4; ++P) {
+                            const uint32_t r = ((uint32_t)P - pl) & 3u;
 #pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            const uint32_t mine = sel4(d, v[4 * CPB * e + c], v[4 * CPB * e + CPB + c], v[4 * CPB * e + 2 * CPB + c], v[4 * CPB * e + 3 * CPB + c]);
-                            D[e][r][c] = __shfl_sync(0xffffffffu, mine, src);
+                            for (int c = 0; c < 4; ++c) prod[P][c] = sel4(r, D[e][0][c], D[e][1][c], D[e][2][c], D[e][3][c]);
                         }
-                }
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int b_loc = 16 * g + 8 * h + 4 * e + (int)pl;
-                    const uint64_t gj = (uint64_t)J * M4_BLK + b_loc;
-                    if (!(gi < gj && gj < p.M)) continue;
-                    // plane P of A is what arrived in rotation (P - o) & 3
-                    uint32_t prod[NC][NC], prod_ctl[3][3];
-#pragma unroll
-                    for (int P = 0; P < NC; ++P) {
-                        const uint32_t r = ((uint32_t)P - pl) & 3u;
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) prod[P][c] = sel4(r, D[e][0][c], D[e][1][c], D[e][2][c], D[e][3][c]);
-                        if (TWOACC && P < 3) {
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) prod_ctl[P][c] = sel4(r, Dctl[e][0][c], Dctl[e][1][c], Dctl[e][2][c], Dctl[e][3][c]);
-                        }
+                        finish_pair(gj, *reinterpret_cast<const PairSide *>(my_col + (8 * h + 4 * e + (int)pl) * 128), prod, none);
                     }
-                    const PairSide &B = *reinterpret_cast<const PairSide *>(my_col + (8 * h + 4 * e + (int)pl) * 128);
-                    uint32_t n[2][3][3];
+                } else {
+                    // through shared memory: every lane writes the twelve products it holds for four B-SNPs to its row of the warp's
+                    // exchange block (three 16-byte stores) and reads the nine of its pair from the rows of its quad: no selects,
+                    // no shuffles, conflict-free both ways (row = 12 words, skewed by 4 words per eight lanes).
+                    uint32_t vc[32];
+                    if (TWOACC) tc_ld24(taddr + ACC_COLS, vc);
+                    tc_ld24(taddr, v);
+                    tc_wait_ld();
+                    uint32_t *xw = reinterpret_cast<uint32_t *>(xch_sm + ew * M4_XCH_WARP) + 4 * (lane >> 3);
+                    uint4 *mine = reinterpret_cast<uint4 *>(xw + 12 * lane);
+                    const uint32_t *theirs = xw + 12 * (int)qbase + 3 * (int)pl;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint32_t *ca = A.cnt[k], *cb = B.cnt[k];     // aa, ab, bb, xx
-                        if (SPLIT) {
-                            const uint32_t AB = prod[2 * k][2 * k], Ab = prod[2 * k][2 * k + 1], aB = prod[2 * k + 1][2 * k], ab = prod[2 * k + 1][2 * k + 1];
-                            n[k][0][0] = AB; n[k][0][2] = Ab; n[k][2][0] = aB; n[k][2][2] = ab;
-                            n[k][0][1] = ca[0] - AB - Ab;
-                            n[k][2][1] = ca[2] - aB - ab;
-                            n[k][1][0] = cb[0] - AB - aB;
-                            n[k][1][2] = cb[2] - Ab - ab;
-                            n[k][1][1] = cb[1] - n[k][0][1] - n[k][2][1];
-                        } else {
-                            uint32_t x[3][3];   // x[P][c]: class-k count of (plane P of A) & (plane c of B); planes aa, bb, xx
+                    for (int e = 0; e < 2; ++e) {
+                        uint32_t prod[CPB][CPB], prod_ctl[3][3];
+                        __syncwarp();
+                        mine[0] = make_uint4(v[12 * e + 0], v[12 * e + 1], v[12 * e + 2], v[12 * e + 3]);
+                        mine[1] = make_uint4(v[12 * e + 4], v[12 * e + 5], v[12 * e + 6], v[12 * e + 7]);
+                        mine[2] = make_uint4(v[12 * e + 8], v[12 * e + 9], v[12 * e + 10], v[12 * e + 11]);
+                        __syncwarp();
+#pragma unroll
+                        for (int P = 0; P < 3; ++P)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) prod[P][c] = theirs[12 * P + c];
+                        if (TWOACC) {
+                            __syncwarp();
+                            mine[0] = make_uint4(vc[12 * e + 0], vc[12 * e + 1], vc[12 * e + 2], vc[12 * e + 3]);
+                            mine[1] = make_uint4(vc[12 * e + 4], vc[12 * e + 5], vc[12 * e + 6], vc[12 * e + 7]);
+                            mine[2] = make_uint4(vc[12 * e + 8], vc[12 * e + 9], vc[12 * e + 10], vc[12 * e + 11]);
+                            __syncwarp();
 #pragma unroll
                             for (int P = 0; P < 3; ++P)
 #pragma unroll
-                                for (int c = 0; c < 3; ++c)
-                                    x[P][c] = TWOACC ? (k ? prod_ctl[P][c] : prod[P][c]) : (k ? (prod[P][c] >> CTRL_SHIFT) : (prod[P][c] & 0x3fffu));
-                            n[k][0][0] = x[0][0]; n[k][0][2] = x[0][1]; n[k][2][0] = x[1][0]; n[k][2][2] = x[1][1];
-                            n[k][0][1] = ca[0] - x[0][0] - x[0][1] - x[0][2];
-                            n[k][2][1] = ca[2] - x[1][0] - x[1][1] - x[1][2];
-                            n[k][1][0] = cb[0] - x[0][0] - x[1][0] - x[2][0];
-                            n[k][1][2] = cb[2] - x[0][1] - x[1][1] - x[2][1];
-                            n[k][1][1] = ca[1] - n[k][1][0] - n[k][1][2] - (cb[3] - x[0][2] - x[1][2] - x[2][2]);
+                                for (int c = 0; c < 3; ++c) prod_ctl[P][c] = theirs[12 * P + c];
                         }
+                        const int b_loc = 16 * g + 8 * h + 4 * e + (int)pl;
+                        const uint64_t gj = (uint64_t)J * M4_BLK + b_loc;
+                        if (gi < gj && gj < p.M)
+                            finish_pair(gj, *reinterpret_cast<const PairSide *>(my_col + (8 * h + 4 * e + (int)pl) * 128), prod, prod_ctl);
                     }
-                    const float stat = ksa_screen_f32(n, A, B, p.N, p.lnN);
-                    if (stat > thr_now) sink_push(p.sink, (uint32_t)gi, (uint32_t)gj, stat);
                 }
             }
             tc_fence_before();
@@ -1458,10 +1527,10 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, const CandSink &sink, uint32_
     if (my_tiles == 0) return GWASDEV_OK;
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-    const size_t smem = mma_smem_bytes();
     const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));
 #define SCREEN4(MODE_)                                                                                                         \
     do {                                                                                                                       \
+        const size_t smem = M4Smem<MODE_>::BYTES;                                                                              \
         GW_CUDA(cudaFuncSetAttribute(pair_screen_mma4_kernel<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
         pair_screen_mma4_kernel<MODE_><<<2 * pairs, MMA_THREADS, smem, s->stream>>>(((const CUtensorMap *)s->tmap_mm4)[0], ((const CUtensorMap *)s->tmap_mm4)[1], p); \
     } while (0)
