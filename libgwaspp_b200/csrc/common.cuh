@@ -178,6 +178,7 @@ struct gwasdev_store {
     void *d_mma_row = nullptr, *d_mma_col = nullptr;   // per-SNP epilogue records (MmaRow / MmaCol)
     uint8_t *d_plane_derived = nullptr;                // per SNP: the genotype class (0 aa, 1 ab, 2 bb) the two-plane operands leave out
     size_t cap_plane = 0;
+    unsigned long long *d_tile_counter = nullptr;      // next tile of the running tensor-core screen (its CTA pairs draw their tiles from it)
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
     // four-plane operands (aa, bb, xx, padding) for the tiles with missing calls (pair_screen_mma4_kernel)
     bool mm4_built = false;

@@ -95,6 +95,7 @@ struct MmaParams {
     float N;
     float qc, q0;               // upper-bound pre-filter: S <= qc * sum_ab c0^2/cab - q0 (see ksa_upper_bound)
     CandSink sink;
+    unsigned long long *tile_counter;   // zero at launch: the CTA pairs draw the shard's tiles from it in schedule order
     uint32_t *dump;             // debug: raw corner counts of tile `dump_tile` only, rows of CTA `dump_rank`
     uint64_t dump_tile;
     uint32_t dump_rank;
@@ -189,6 +190,66 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// ---- tile feed ---------------------------------------------------------------------------------------
+// The CTA pairs draw their tiles from one device-wide counter, in schedule order, instead of owning every n-th tile: whatever
+// their relative speed, the tiles in flight on the GPU are then ~74 consecutive ones of the schedule (one band of A-blocks and
+// a window of ~10 B-blocks, ~50 MB: L2-resident). With fixed ownership the pairs drift apart over the 100 000 tiles each
+// processes at configs[3] and the window outgrows the L2 (DRAM reads 6.3 TB per pass against 3.1 TB for eight 1/8 shards).
+// One thread of the pair -- the leader's TMA producer -- draws the index, decodes it and publishes (I2, J) in a ring of
+// SCHED_SLOTS slots in BOTH CTAs' shared memory; every other role (peer producer, MMA issuer, 2 x 16 epilogue warps) waits on
+// its CTA's sfull[slot], reads the slot and arrives on the leader's sempty[slot].
+constexpr int SCHED_SLOTS = 4;                 // producer at tile n, epilogue at n - 2: four slots never stall the producer
+constexpr uint32_t SCHED_END = 0xffffffffu;
+constexpr uint32_t SCHED_CONSUMERS = 2 * EPI_WARPS + 2;   // epilogue warps of both CTAs, the leader's MMA issuer, the peer's producer
+__device__ __forceinline__ void mbar_wait_wd_cluster(uint64_t *bar, uint32_t parity) {    // acquires what a remote thread released
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+// publish (I2, J) in slot `slot` of both CTAs (called by the leader's producer thread)
+__device__ __forceinline__ void sched_publish(uint2 *slots, uint64_t *sfull, int slot, uint32_t I2, uint32_t J) {
+    asm volatile(
+        "{\n\t.reg .b32 rs, rb;\n\t"
+        "st.shared.v2.u32 [%0], {%2, %3};\n\t"
+        "mapa.shared::cluster.u32 rs, %0, 1;\n\t"
+        "st.shared::cluster.v2.u32 [rs], {%2, %3};\n\t"
+        "mapa.shared::cluster.u32 rb, %1, 1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [rb];\n\t"
+        "mbarrier.arrive.release.cta.shared::cta.b64 _, [%1];\n\t}"
+        ::"r"(smem_u32(&slots[slot])), "r"(smem_u32(&sfull[slot])), "r"(I2), "r"(J) : "memory");
+}
+// single-thread consumer: next tile of the pair, false at the end of the shard
+__device__ __forceinline__ bool sched_next(const uint2 *slots, uint64_t *sfull, uint64_t *sempty, uint32_t &n, uint32_t &I2, uint32_t &J) {
+    const int slot = (int)(n % SCHED_SLOTS);
+    mbar_wait_wd_cluster(&sfull[slot], (n / SCHED_SLOTS) & 1u);
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(I2), "=r"(J) : "r"(smem_u32(&slots[slot])) : "memory");
+    if (I2 == SCHED_END) return false;
+    mbar_arrive_remote(&sempty[slot], 0);
+    ++n;
+    return true;
+}
+// warp-wide consumer (epilogue): lane 0 waits and releases
+__device__ __forceinline__ bool sched_next_warp(const uint2 *slots, uint64_t *sfull, uint64_t *sempty, int lane, uint32_t &n, uint32_t &I2, uint32_t &J) {
+    const int slot = (int)(n % SCHED_SLOTS);
+    if (lane == 0) mbar_wait_wd_cluster(&sfull[slot], (n / SCHED_SLOTS) & 1u);
+    __syncwarp();
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(I2), "=r"(J) : "r"(smem_u32(&slots[slot])) : "memory");
+    __syncwarp();
+    if (I2 == SCHED_END) return false;
+    if (lane == 0) mbar_arrive_remote(&sempty[slot], 0);
+    ++n;
+    return true;
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -256,6 +317,36 @@ struct TileCursor {
         if (r < tri) { c = 0; uint32_t q = (uint32_t)r; while (q > c) { q -= c + 1; ++c; } ii = q; }
         else { const uint64_t q = r - tri; c = na - 1 + (uint32_t)(q / na); ii = (uint32_t)(q % na); }
         I2 = BAND * b + ii; J = BAND * b + c;
+    }
+};
+
+// The leader producer's side of the tile feed when a kernel computes only some tiles of the schedule (the four-plane kernel:
+// those with / without missing calls): draws local indices from the device counter and walks them until a wanted tile turns
+// up. The batch drawn at once adapts -- doubled (up to 64) after a batch without a wanted tile, halved after every wanted one --
+// so that a cohort whose tiles are all wanted keeps drawing single tiles (tiles in flight stay consecutive) and one with few
+// wanted tiles does not pay an atomic per skipped tile.
+struct TileDraw {
+    unsigned long long *counter;
+    uint32_t shard, n_shards, TB, n_bands;
+    uint64_t last;
+    uint64_t u_lo = 0, u_hi = 0, pend = 0, t_cur = 0;
+    uint32_t batch = 1, pend_n = 0;
+    bool located = false;
+    TileCursor cur;
+    __device__ __forceinline__ void prefetch() {       // issue the next draw early: its latency hides behind the tile's loads
+        if (u_lo == u_hi && pend_n == 0) { pend = atomicAdd(counter, (unsigned long long)batch); pend_n = batch; }
+    }
+    template <class Wanted> __device__ __forceinline__ bool next(uint32_t &I2, uint32_t &J, Wanted wanted) {
+        for (;;) {
+            if (u_lo == u_hi) { prefetch(); u_lo = pend; u_hi = pend + pend_n; pend_n = 0; }
+            const uint64_t t = shard_tile(u_lo++, shard, n_shards);
+            if (t >= last) return false;
+            if (!located) { cur.locate(t, TB, n_bands); located = true; } else cur.advance(t - t_cur, TB, n_bands);
+            t_cur = t;
+            cur.decode(TB, I2, J);
+            if (wanted(I2, J)) { batch = max(1u, batch >> 1); return true; }
+            if (u_lo == u_hi) batch = min(batch << 1, 64u);
+        }
     }
 };
 
@@ -385,7 +476,10 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
     uint64_t *empty = full + MMA_STAGES;
     uint64_t *tfull = empty + MMA_STAGES;
     uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *sfull = tempty + 2;                      // tile feed (see above): slot published / slot read by every consumer of the pair
+    uint64_t *sempty = sfull + SCHED_SLOTS;
+    uint2 *sched = reinterpret_cast<uint2 *>(sempty + SCHED_SLOTS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sched + SCHED_SLOTS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();          // 0: leader of the CTA pair (issues the MMAs, owns full / tempty)
@@ -396,6 +490,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         // empty / tfull: one multicast tcgen05.commit each. tempty: every epilogue warp of both CTAs.
         for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * EPI_WARPS); }
+        for (int b = 0; b < SCHED_SLOTS; ++b) { mbar_init(&sfull[b], 1); mbar_init(&sempty[b], SCHED_CONSUMERS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {   // whole warp, in both CTAs: all 512 TMEM columns (two accumulators)
@@ -407,23 +502,41 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // This CTA pair's tiles: local indices u = pair_id, pair_id + n_pairs, ... of the shard; shard_tile(u) is the schedule
-    // index. Shards own alternating chunks of SHARD_CHUNK consecutive tiles, so that the tiles a GPU works on at the
-    // same time share A- and B-blocks in its L2 whatever the number of GPUs.
-    const uint64_t u_first = p.dump ? 0 : pair_id, u_step = p.dump ? 1 : n_pairs;
-    const uint64_t first = p.dump ? p.dump_tile : shard_tile(u_first, p.shard, p.n_shards);
+    // The shard's tiles have local indices u = 0, 1, ...; shard_tile(u) is the schedule index. Shards own alternating chunks
+    // of SHARD_CHUNK consecutive tiles, so that the tiles a GPU works on at the same time share A- and B-blocks in its L2
+    // whatever the number of GPUs. The pair draws its u from p.tile_counter (tile feed above).
     const uint64_t last = p.dump ? p.dump_tile + 1 : p.n_tiles;
+    (void)pair_id; (void)n_pairs;
 
     if (warp == TMA_WARP) {
         // ===== TMA producer (both CTAs: own 128 A rows, own half of the 256 B rows) =====
         if (lane == 0) {
             uint64_t it = 0;
             GW_PROF(long long prof_pw = 0;)
-            TileCursor cur; cur.locate(first, p.TB, p.n_bands);
-            for (uint64_t t = first, u = u_first; t < last;) {
+            TileCursor cur;
+            uint32_t n_sched = 0, dump_u = 0;
+            uint64_t t_cur = 0;
+            bool located = false;
+            auto draw = [&]() -> uint64_t {            // schedule index of the next tile of the shard (leader only)
+                if (p.dump) return p.dump_tile + dump_u++;
+                return shard_tile(atomicAdd(p.tile_counter, 1ull), p.shard, p.n_shards);
+            };
+            uint64_t t_next = rank == 0 ? draw() : 0;
+            for (;;) {
                 uint32_t I2, J;
-                cur.decode(p.TB, I2, J);
-                { u += u_step; const uint64_t tn = p.dump ? last : shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
+                if (rank == 0) {
+                    const uint64_t t = t_next;
+                    const int slot = (int)(n_sched % SCHED_SLOTS);
+                    mbar_wait_wd(&sempty[slot], ((n_sched / SCHED_SLOTS) & 1u) ^ 1u);
+                    if (t >= last) { sched_publish(sched, sfull, slot, SCHED_END, 0); break; }
+                    if (!located) { cur.locate(t, p.TB, p.n_bands); located = true; }
+                    else cur.advance(t - t_cur, p.TB, p.n_bands);
+                    t_cur = t;
+                    cur.decode(p.TB, I2, J);
+                    sched_publish(sched, sfull, slot, I2, J);
+                    ++n_sched;
+                    t_next = draw();                   // in flight while this tile's loads are issued
+                } else if (!sched_next(sched, sfull, sempty, n_sched, I2, J)) break;
                 const int a_row = (int)((2 * I2 + rank) * (2 * MMA_A_SNPS)), b_row = (int)(J * MMA_N + rank * MMA_B_SNPS);
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
@@ -447,8 +560,8 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         if (lane == 0 && rank == 0) {
             uint64_t it = 0, tile_it = 0;
             GW_PROF(long long prof_te = 0; long long prof_fu = 0; const long long prof_t0 = clock64();)
-            for (uint64_t t = first, u = u_first; t < last; ++tile_it) {
-                { u += u_step; t = p.dump ? last : shard_tile(u, p.shard, p.n_shards); }
+            uint32_t n_sched = 0, I2_, J_;
+            for (; sched_next(sched, sfull, sempty, n_sched, I2_, J_); ++tile_it) {
                 const uint32_t buf = (uint32_t)(tile_it & 1);
                 GW_PROF(const long long w0 = clock64();)
                 mbar_wait_wd(&tempty[buf], (uint32_t)(((tile_it >> 1) & 1) ^ 1));
@@ -487,11 +600,8 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
         const int pl = lane & 1;                      // plane held by this lane's TMEM row (0: aa, 1: bb)
         uint64_t tile_it = 0;
         GW_PROF(long long prof_tw = 0; const long long prof_e0 = clock64();)
-        TileCursor cur; cur.locate(first, p.TB, p.n_bands);
-        for (uint64_t t = first, u = u_first; t < last; ++tile_it) {
-            uint32_t I2, J;
-            cur.decode(p.TB, I2, J);
-            { u += u_step; const uint64_t tn = p.dump ? last : shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
+        uint32_t n_sched = 0, I2, J;
+        for (; sched_next_warp(sched, sfull, sempty, lane, n_sched, I2, J); ++tile_it) {
             const uint32_t I = 2 * I2 + rank;         // this CTA's 64-SNP A-block
             const uint32_t buf = (uint32_t)(tile_it & 1);
             const uint64_t gi = (uint64_t)I * MMA_A_SNPS + a_loc;
@@ -812,7 +922,8 @@ template <int MODE> struct M4Smem {
     static constexpr int KBB = A_STAGE_BYTES + MMA_B_SNPS / 4 * CPB * MMA_KB;       // 32 KiB (split classes) or 28 KiB
     static constexpr int STG = KPS * KBB;
     static constexpr int XCH = MODE == 1 ? 0 : EPI_WARPS * M4_XCH_WARP;
-    static constexpr size_t BYTES = 1024 + (size_t)MMA_STAGES * STG + XCH + EPI_WARPS * COL_STAGE_BYTES + (2 * MMA_STAGES + 4) * sizeof(uint64_t) + 16;
+    static constexpr size_t BYTES = 1024 + (size_t)MMA_STAGES * STG + XCH + EPI_WARPS * COL_STAGE_BYTES + (2 * MMA_STAGES + 4 + 2 * SCHED_SLOTS) * sizeof(uint64_t) +
+                                    SCHED_SLOTS * sizeof(uint2) + 16;
     static_assert(KBB % 1024 == 0 && BYTES <= 232448, "stage blocks keep the 1 KiB swizzle alignment; at most 227 KiB per CTA");
 };
 
@@ -825,6 +936,7 @@ struct Mma4Params {
     const uint8_t *tile_missing;   // per 64-SNP block
     float N, lnN;
     CandSink sink;
+    unsigned long long *tile_counter;   // zero at launch (tile feed)
 };
 
 __device__ __forceinline__ uint32_t sel4(uint32_t k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -861,15 +973,18 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
     uint64_t *empty = full + MMA_STAGES;
     uint64_t *tfull = empty + MMA_STAGES;
     uint64_t *tempty = tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    uint64_t *sfull = tempty + 2;                      // tile feed, as in pair_screen_mma_kernel
+    uint64_t *sempty = sfull + SCHED_SLOTS;
+    uint2 *sched = reinterpret_cast<uint2 *>(sempty + SCHED_SLOTS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sched + SCHED_SLOTS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
-    const uint32_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
     if (tid == 0) {
         for (int s = 0; s < MMA_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * EPI_WARPS); }
+        for (int b = 0; b < SCHED_SLOTS; ++b) { mbar_init(&sfull[b], 1); mbar_init(&sempty[b], SCHED_CONSUMERS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -881,20 +996,26 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint64_t u_first = pair_id, u_step = n_pairs;
-    const uint64_t first = shard_tile(u_first, p.shard, p.n_shards), last = p.n_tiles;
-    // all three roles walk the same tile sequence and skip the tiles without missing calls the same way
+    // the tiles this launch computes: the leader's producer skips the others while it draws (TileDraw), the other roles only see these
     auto wanted = [&](uint32_t I2, uint32_t J) -> bool { return TWOACC || ((p.tile_missing[I2] | p.tile_missing[J]) != 0) != SPLIT; };
 
     if (warp == TMA_WARP) {
         if (lane == 0) {
             uint64_t it = 0;
-            TileCursor cur; cur.locate(first, p.TB, p.n_bands);
-            for (uint64_t t = first, u = u_first; t < last;) {
+            uint32_t n_sched = 0;
+            TileDraw draw;
+            draw.counter = p.tile_counter; draw.shard = p.shard; draw.n_shards = p.n_shards; draw.TB = p.TB; draw.n_bands = p.n_bands; draw.last = p.n_tiles;
+            for (;;) {
                 uint32_t I2, J;
-                cur.decode(p.TB, I2, J);
-                { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
-                if (!wanted(I2, J)) continue;
+                if (rank == 0) {
+                    const bool more = draw.next(I2, J, wanted);
+                    const int slot = (int)(n_sched % SCHED_SLOTS);
+                    mbar_wait_wd(&sempty[slot], ((n_sched / SCHED_SLOTS) & 1u) ^ 1u);
+                    sched_publish(sched, sfull, slot, more ? I2 : SCHED_END, J);
+                    if (!more) break;
+                    ++n_sched;
+                    draw.prefetch();
+                } else if (!sched_next(sched, sfull, sempty, n_sched, I2, J)) break;
                 const int a_row = (int)((2 * I2 + rank) * (2 * MMA_A_SNPS)), b_row = (int)(J * MMA_N + rank * MMA_B_SNPS);
                 for (uint32_t kb = 0; kb < p.NKB; kb += KPS, ++it) {
                     const int st = (int)(it % MMA_STAGES);
@@ -914,12 +1035,8 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
     } else if (warp == MMA_WARP) {
         if (lane == 0 && rank == 0) {
             uint64_t it = 0, tile_it = 0;
-            TileCursor cur; cur.locate(first, p.TB, p.n_bands);
-            for (uint64_t t = first, u = u_first; t < last;) {
-                uint32_t I2, J;
-                cur.decode(p.TB, I2, J);
-                { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
-                if (!wanted(I2, J)) continue;
+            uint32_t n_sched = 0, I2, J;
+            while (sched_next(sched, sfull, sempty, n_sched, I2, J)) {
                 // two accumulators per tile (TWOACC): buffer 0 = cases, buffer 1 = controls, one tile in flight
                 const uint32_t buf = TWOACC ? 0u : (uint32_t)(tile_it & 1);
                 mbar_wait_wd(&tempty[buf], TWOACC ? (uint32_t)((tile_it & 1) ^ 1) : (uint32_t)(((tile_it >> 1) & 1) ^ 1));
@@ -956,12 +1073,8 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
         const uint32_t pl = (uint32_t)lane & 3u;      // plane held by this lane's TMEM row (0 aa, 1 bb, 2 xx, 3 padding)
         const unsigned qbase = (unsigned)lane & ~3u;
         uint64_t tile_it = 0;
-        TileCursor cur; cur.locate(first, p.TB, p.n_bands);
-        for (uint64_t t = first, u = u_first; t < last;) {
-            uint32_t I2, J;
-            cur.decode(p.TB, I2, J);
-            { u += u_step; const uint64_t tn = shard_tile(u, p.shard, p.n_shards); cur.advance(tn - t, p.TB, p.n_bands); t = tn; }
-            if (!wanted(I2, J)) continue;
+        uint32_t n_sched = 0, I2, J;
+        while (sched_next_warp(sched, sfull, sempty, lane, n_sched, I2, J)) {
             const uint32_t buf = TWOACC ? 0u : (uint32_t)(tile_it & 1);
             const uint64_t gi = (uint64_t)I2 * M4_BLK + rank * M4_A_SNPS + a_loc;
             // this warp's 16 column-role records (PairSide, 128 bytes each): 2 KiB contiguous -> its shared-memory slot
@@ -1380,7 +1493,9 @@ uint64_t gwasdev_internal_mma_shard_pairs(const gwasdev_store *s, uint32_t shard
     return pairs;
 }
 
-static size_t mma_smem_bytes() { return 1024 + (size_t)MMA_STAGES * STAGE_BYTES_MMA + EPI_WARPS * COL_STAGE_BYTES + (2 * MMA_STAGES + 4) * sizeof(uint64_t) + 16; }
+static size_t mma_smem_bytes() {
+    return 1024 + (size_t)MMA_STAGES * STAGE_BYTES_MMA + EPI_WARPS * COL_STAGE_BYTES + (2 * MMA_STAGES + 4 + 2 * SCHED_SLOTS) * sizeof(uint64_t) + SCHED_SLOTS * sizeof(uint2) + 16;
+}
 
 static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
     int sms = 0;
@@ -1399,6 +1514,9 @@ static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
         GW_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)2 * pairs * 8 * sizeof(unsigned long long), s->stream));
     }
     p.prof = d_prof;
+    if (!s->d_tile_counter) GW_CUDA(cudaMalloc(&s->d_tile_counter, sizeof(unsigned long long)));
+    GW_CUDA(cudaMemsetAsync(s->d_tile_counter, 0, sizeof(unsigned long long), s->stream));
+    p.tile_counter = s->d_tile_counter;
     pair_screen_mma_kernel<<<2 * pairs, MMA_THREADS, smem, s->stream>>>(*(const CUtensorMap *)s->tmap_mm, p);
     GW_LAUNCHED();
     if (prof) {
@@ -1528,6 +1646,9 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, const CandSink &sink, uint32_
     int sms = 0;
     GW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
     const unsigned pairs = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sms / 2, my_tiles));
+    if (!s->d_tile_counter) GW_CUDA(cudaMalloc(&s->d_tile_counter, sizeof(unsigned long long)));
+    GW_CUDA(cudaMemsetAsync(s->d_tile_counter, 0, sizeof(unsigned long long), s->stream));
+    p.tile_counter = s->d_tile_counter;
 #define SCREEN4(MODE_)                                                                                                         \
     do {                                                                                                                       \
         const size_t smem = M4Smem<MODE_>::BYTES;                                                                              \

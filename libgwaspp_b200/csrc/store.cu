@@ -381,7 +381,7 @@ void gwasdev_destroy(gwasdev_store *s) {
     cudaFree(s->d_masks); cudaFree(s->d_row_tot); cudaFree(s->d_case_idx); cudaFree(s->d_ctrl_idx);
     cudaFree(s->d_sel); cudaFree(s->d_pw); cudaFree(s->d_mi); cudaFree(s->d_side); cudaFree(s->d_tile_missing);
     free(s->tmap); free(s->tmap_mm); free(s->tmap_mm4);
-    cudaFree(s->d_mm); cudaFree(s->d_mm4); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col); cudaFree(s->d_plane_derived);
+    cudaFree(s->d_mm); cudaFree(s->d_mm4); cudaFree(s->d_mma_row); cudaFree(s->d_mma_col); cudaFree(s->d_plane_derived); cudaFree(s->d_tile_counter);
     for (gwasdev_store::Scratch *sc : {&s->sc_out_counts, &s->sc_out_stats, &s->sc_out_mi, &s->sc_cnt, &s->sc_cand, &s->sc_keys,
                                       &s->sc_keys2, &s->sc_vals, &s->sc_vals2, &s->sc_sort, &s->sc_hits, &s->sc_pi, &s->sc_pj,
                                       &s->sc_a, &s->sc_b, &s->sc_stage, &s->sc_gather})
