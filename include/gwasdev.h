@@ -297,10 +297,12 @@ GWASDEV_API int gwasdev_gtest_multi(gwasdev_store *const *stores, uint32_t n_sto
 GWASDEV_API int gwasdev_set_pair_engine(gwasdev_store *s, int engine);
 /* Host arithmetic only (works without a device): the tile pairs (I <= J, as SNP-block indices) of the screen's schedule that
  * `shard` of `n_shards` owns, in schedule order, and the pairs i < j < n_snps they cover. engine 2: the tensor-core
- * schedule (128-SNP blocks, bands of 8 A-blocks, shards own alternating runs of 64 consecutive tiles); engine 1: the
+ * schedule for a table of n_samples individuals (128-SNP blocks; bands of 8 to 16 A-blocks, as many as keep the working set of
+ * the 74 concurrent tiles in the L2: 16 at 4 000 samples, 12 at 10 000, 8 from 12 000; shards own alternating runs of 64
+ * consecutive tiles); engine 1: the
  * AND+POPC schedule (64-SNP blocks, row-major upper triangle, single tiles round-robin). tiles (may be NULL) receives
  * min(*n_tiles, capacity) (I, J) pairs. */
-GWASDEV_API int gwasdev_shard_schedule(uint64_t n_snps, int engine, uint32_t shard, uint32_t n_shards, uint32_t *tiles, uint64_t capacity,
+GWASDEV_API int gwasdev_shard_schedule(uint64_t n_snps, uint64_t n_samples, int engine, uint32_t shard, uint32_t n_shards, uint32_t *tiles, uint64_t capacity,
                            uint64_t *n_tiles, uint64_t *n_pairs);
 /* Parity probe of the tensor-core engine: raw corner counts of one tile pair of its schedule (A-block I of 64
  * SNPs, B-block J of 128 SNPs, I/2 <= J): out[(a*128 + b)*8 + {0,1,2,3}] = cases AA_BB, AA_bb, aa_BB, aa_bb

@@ -108,7 +108,7 @@ def load_library():
     L.gwasdev_pairwise_topk.argtypes = [vp, C.c_double, u64, u32, u32, vp, C.POINTER(u64), C.POINTER(PairStats), i32]
     L.gwasdev_replicate.argtypes = [vp, i32, C.POINTER(vp)]
     L.gwasdev_pairwise_scan_multi.argtypes = [C.POINTER(vp), u32, C.c_double, u64, vp, u64, C.POINTER(u64), C.POINTER(PairStats), i32]
-    L.gwasdev_shard_schedule.argtypes = [u64, i32, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.gwasdev_shard_schedule.argtypes = [u64, u64, i32, u32, u32, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.gwasdev_ksa.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_ksa_screen_f32.argtypes = [vp, u64, vp, vp, vp]
     L.gwasdev_gtest.argtypes = [vp, u64, vp, vp, vp, vp]
@@ -259,14 +259,15 @@ def gtest_multi(stores, pi, pj):
     return s, z
 
 
-def shard_schedule(n_snps: int, shard: int, n_shards: int, engine: int = 2):
+def shard_schedule(n_snps: int, shard: int, n_shards: int, engine: int = 2, n_samples: int = 10_000):
     """Tile pairs ((I, J) SNP-block indices, [n, 2]) the shard owns in the screen's schedule, and the pairs they cover: the
-    library's own enumeration (host arithmetic, no device needed). engine 2: tensor cores (128-SNP blocks), 1: AND+POPC (64)."""
+    library's own enumeration (host arithmetic, no device needed). engine 2: tensor cores (128-SNP blocks; the table's number
+    of individuals n_samples decides how many A-blocks form an L2 band), 1: AND+POPC (64-SNP blocks)."""
     L = load_library()
     nt, npairs = C.c_uint64(), C.c_uint64()
-    _check(L.gwasdev_shard_schedule(n_snps, engine, shard, n_shards, None, 0, C.byref(nt), C.byref(npairs)), "gwasdev_shard_schedule")
+    _check(L.gwasdev_shard_schedule(n_snps, n_samples, engine, shard, n_shards, None, 0, C.byref(nt), C.byref(npairs)), "gwasdev_shard_schedule")
     tiles = np.zeros((nt.value, 2), np.uint32)
-    _check(L.gwasdev_shard_schedule(n_snps, engine, shard, n_shards, _ptr(tiles), nt.value, C.byref(nt), C.byref(npairs)), "gwasdev_shard_schedule")
+    _check(L.gwasdev_shard_schedule(n_snps, n_samples, engine, shard, n_shards, _ptr(tiles), nt.value, C.byref(nt), C.byref(npairs)), "gwasdev_shard_schedule")
     return tiles, int(npairs.value)
 
 

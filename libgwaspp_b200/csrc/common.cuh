@@ -180,6 +180,7 @@ struct gwasdev_store {
     size_t cap_plane = 0;
     unsigned long long *d_tile_counter = nullptr;      // next tile of the running tensor-core screen (its CTA pairs draw their tiles from it)
     uint64_t mm_tiles = 0;        // tile pairs in the tensor-core schedule
+    uint32_t mm_band = 0, mm4_band = 0;   // A-blocks per L2 band of the two schedules (pairwise_mma.cu: schedule_band)
     // four-plane operands (aa, bb, xx, padding) for the tiles with missing calls (pair_screen_mma4_kernel)
     bool mm4_built = false;
     int mm4_mode = 0;             // 0: aa/bb/xx planes, packed classes; 1: per-class planes; 2: aa/bb/xx planes, one accumulator per class

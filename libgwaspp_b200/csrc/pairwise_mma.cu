@@ -26,7 +26,7 @@
 //                           pairs swap the two planes by shuffle, decode the counts, margins -> 3x3x2 table,
 //                           upper bound of the KSA statistic, exact fp32 KSA for the few that pass it,
 //                           candidates above threshold - margin
-// Tile order keeps a band of 8 A-blocks and a sliding window of B-blocks L2-resident.
+// Tile order keeps a band of A-blocks (8 to 16, see schedule_band) and a sliding window of B-blocks L2-resident.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -54,10 +54,15 @@ constexpr int MMA_THREADS = (2 + EPI_WARPS) * 32;
 // above the sixteen epilogue warps (which also makes warp % 4 the TMEM lane quadrant of epilogue warp `warp`).
 constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int COL_STAGE_BYTES = 32 * 64;                           // column-role records of one epilogue warp's 32 B-SNPs
-#ifndef GWASDEV_BAND
-#define GWASDEV_BAND 8
+// A-blocks per L2 band (schedule_band below): with the tile feed the 74 CTA pairs of a B200 work on ~74 consecutive tiles, i.e.
+// on the BD A-blocks of the band and a window of ceil(74 / BD) B-blocks; DRAM traffic falls as 1 / BD while that working set
+// fits the L2. The largest BD (at most BAND_MAX) whose working set stays below GWASDEV_L2_MB is taken; when none fits (rows
+// of 12 000+ samples) the working set is smallest at BD = 8. Measured at configs[3] (2.57 MB blocks): 8 -> 2.77 s, 12 -> 2.69 s
+// (48.8 MB), 16 -> 2.71-2.75 s (54 MB), 24 -> 3.00 s (72 MB).
+#ifndef GWASDEV_L2_MB
+#define GWASDEV_L2_MB 50
 #endif
-constexpr int BAND = GWASDEV_BAND;                                 // A-blocks per L2 band (experiment builds: build.py --variant NAME -DGWASDEV_BAND=n)
+constexpr uint32_t BAND_MAX = 16, BAND_FALLBACK = 8, SCHED_PAIRS = 74;
 constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
 constexpr uint32_t CTRL_SHIFT = 14;                                // (-128)^2 = 2^14
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                        // shared::cluster address of the pair's even CTA
@@ -83,7 +88,7 @@ static_assert(sizeof(MmaRowF) == 64 && sizeof(MmaColF) == 64, "64-byte bound-pas
 struct MmaParams {
     uint32_t TB;                // 128-SNP blocks
     uint32_t NKB;               // 128-byte sample blocks per row
-    uint32_t n_bands;
+    uint32_t n_bands, band;     // bands of the schedule, A-blocks per band
     uint64_t M;
     uint64_t n_tiles;
     uint32_t shard, n_shards;
@@ -265,10 +270,16 @@ constexpr uint32_t idesc_i8(int n) { return (2u << 4) | (1u << 7) | (1u << 10) |
 constexpr uint32_t IDESC_I8 = idesc_i8(MMA_N);
 
 // ---- tile order -------------------------------------------------------------------------------------
-// Tiles are pairs of 128-SNP blocks (I2 <= J). Band b holds A-blocks [8b, 8b+8); inside a band tiles run
-// column-major over B-blocks J >= 8b, and column c = J - 8b holds the band's A-blocks I2 <= J.
-__host__ __device__ inline uint32_t band_height(uint32_t TB, uint32_t b) { return min((uint32_t)BAND, TB - BAND * b); }
+// Tiles are pairs of 128-SNP blocks (I2 <= J). Band b holds A-blocks [BD b, BD b + BD) for the band height BD of the launch;
+// inside a band tiles run column-major over B-blocks J >= BD b, and column c = J - BD b holds the band's A-blocks I2 <= J.
+__host__ __device__ inline uint32_t band_height(uint32_t TB, uint32_t b, uint32_t BD) { return min(BD, TB - BD * b); }
 __host__ __device__ inline uint32_t column_height(uint32_t na, uint32_t c) { return min(na, c + 1); }
+// band height for operand blocks of `block_bytes` (rows of one A-block x bytes per row)
+inline uint32_t schedule_band(uint64_t block_bytes) {
+    for (uint32_t bd = BAND_MAX; bd >= BAND_FALLBACK; --bd)
+        if ((bd + (SCHED_PAIRS + bd - 1) / bd) * block_bytes <= ((uint64_t)GWASDEV_L2_MB << 20)) return bd;
+    return BAND_FALLBACK;
+}
 
 // Schedule index of the u-th tile of a shard: shards take turns in chunks of SHARD_CHUNK consecutive tiles.
 constexpr uint32_t SHARD_CHUNK = 64;
@@ -284,39 +295,45 @@ __host__ __device__ inline uint64_t shard_tiles_before(uint64_t n, uint32_t shar
     return cnt;
 }
 
-// Tiles before band b. Every band before the last is full (8 A-blocks, at least 8 columns): 8 (TB - 8b') - 28 tiles.
-__host__ __device__ inline uint64_t band_offset(uint32_t TB, uint64_t b) {
-    return b * ((uint64_t)BAND * TB) - (uint64_t)(BAND * BAND) * (b * (b - 1) / 2) - b * (uint64_t)(BAND * (BAND - 1) / 2);
+// Tiles before band b. Every band before the last is full (BD A-blocks, at least BD columns): BD (TB - BD b') - BD (BD - 1) / 2 tiles.
+__host__ __device__ inline uint64_t band_offset(uint32_t TB, uint64_t b, uint32_t BD) {
+    return b * ((uint64_t)BD * TB) - (uint64_t)(BD * BD) * (b * (b - 1) / 2) - b * (uint64_t)(BD * (BD - 1) / 2);
 }
 
-__host__ __device__ inline uint64_t band_tiles(uint32_t TB, uint32_t b) {      // tiles in band b (the last one may be short)
-    const uint64_t na = band_height(TB, b), cols = TB - BAND * b;              // cols >= na
+__host__ __device__ inline uint64_t band_tiles(uint32_t TB, uint32_t b, uint32_t BD) {      // tiles in band b (the last one may be short)
+    const uint64_t na = band_height(TB, b, BD), cols = TB - BD * b;             // cols >= na
     return na * (na - 1) / 2 + na * (cols - (na - 1));
 }
+// tiles of the whole schedule
+inline uint64_t schedule_tiles(uint32_t TB, uint32_t BD) {
+    const uint32_t n_bands = (TB + BD - 1) / BD;
+    return band_offset(TB, n_bands - 1, BD) + band_tiles(TB, n_bands - 1, BD);
+}
 
-// Position in the schedule: band and index inside the band. Located once with the closed form, then advanced by
-// the CTA pair's stride with a few integer operations per tile (all three roles walk the same sequence).
+// Position in the schedule: band and index inside the band. Located once with the closed form, then advanced
+// with a few integer operations per tile.
 struct TileCursor {
-    uint32_t b;
+    uint32_t b, BD;
     uint64_t r, len;
-    __device__ void locate(uint64_t t, uint32_t TB, uint32_t n_bands) {
-        const double Bc = (double)BAND * TB + 0.5 * BAND * BAND - 0.5 * BAND * (BAND - 1);
-        int64_t k = (int64_t)((Bc - sqrt(fmax(Bc * Bc - 2.0 * BAND * BAND * (double)t, 0.0))) / (double)(BAND * BAND));
+    __device__ void locate(uint64_t t, uint32_t TB, uint32_t n_bands, uint32_t band) {
+        BD = band;
+        const double Bc = (double)BD * TB + 0.5 * BD * BD - 0.5 * BD * (BD - 1);
+        int64_t k = (int64_t)((Bc - sqrt(fmax(Bc * Bc - 2.0 * BD * BD * (double)t, 0.0))) / (double)(BD * BD));
         k = max((int64_t)0, min(k, (int64_t)n_bands - 1));
-        while (k > 0 && band_offset(TB, (uint64_t)k) > t) --k;
-        while (k + 1 < (int64_t)n_bands && band_offset(TB, (uint64_t)k + 1) <= t) ++k;
-        b = (uint32_t)k; r = t - band_offset(TB, b); len = band_tiles(TB, b);
+        while (k > 0 && band_offset(TB, (uint64_t)k, BD) > t) --k;
+        while (k + 1 < (int64_t)n_bands && band_offset(TB, (uint64_t)k + 1, BD) <= t) ++k;
+        b = (uint32_t)k; r = t - band_offset(TB, b, BD); len = band_tiles(TB, b, BD);
     }
     __device__ __forceinline__ void advance(uint64_t d, uint32_t TB, uint32_t n_bands) {
         r += d;
-        while (r >= len && b + 1 < n_bands) { r -= len; ++b; len = band_tiles(TB, b); }
+        while (r >= len && b + 1 < n_bands) { r -= len; ++b; len = band_tiles(TB, b, BD); }
     }
     __device__ __forceinline__ void decode(uint32_t TB, uint32_t &I2, uint32_t &J) const {
-        const uint32_t na = band_height(TB, b), tri = na * (na - 1) / 2;      // columns 0..na-2 hold c+1 tiles each
+        const uint32_t na = band_height(TB, b, BD), tri = na * (na - 1) / 2;      // columns 0..na-2 hold c+1 tiles each
         uint32_t c, ii;
         if (r < tri) { c = 0; uint32_t q = (uint32_t)r; while (q > c) { q -= c + 1; ++c; } ii = q; }
         else { const uint64_t q = r - tri; c = na - 1 + (uint32_t)(q / na); ii = (uint32_t)(q % na); }
-        I2 = BAND * b + ii; J = BAND * b + c;
+        I2 = BD * b + ii; J = BD * b + c;
     }
 };
 
@@ -327,7 +344,7 @@ struct TileCursor {
 // wanted tiles does not pay an atomic per skipped tile.
 struct TileDraw {
     unsigned long long *counter;
-    uint32_t shard, n_shards, TB, n_bands;
+    uint32_t shard, n_shards, TB, n_bands, band;
     uint64_t last;
     uint64_t u_lo = 0, u_hi = 0, pend = 0, t_cur = 0;
     uint32_t batch = 1, pend_n = 0;
@@ -341,7 +358,7 @@ struct TileDraw {
             if (u_lo == u_hi) { prefetch(); u_lo = pend; u_hi = pend + pend_n; pend_n = 0; }
             const uint64_t t = shard_tile(u_lo++, shard, n_shards);
             if (t >= last) return false;
-            if (!located) { cur.locate(t, TB, n_bands); located = true; } else cur.advance(t - t_cur, TB, n_bands);
+            if (!located) { cur.locate(t, TB, n_bands, band); located = true; } else cur.advance(t - t_cur, TB, n_bands);
             t_cur = t;
             cur.decode(TB, I2, J);
             if (wanted(I2, J)) { batch = max(1u, batch >> 1); return true; }
@@ -529,7 +546,7 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
                     const int slot = (int)(n_sched % SCHED_SLOTS);
                     mbar_wait_wd(&sempty[slot], ((n_sched / SCHED_SLOTS) & 1u) ^ 1u);
                     if (t >= last) { sched_publish(sched, sfull, slot, SCHED_END, 0); break; }
-                    if (!located) { cur.locate(t, p.TB, p.n_bands); located = true; }
+                    if (!located) { cur.locate(t, p.TB, p.n_bands, p.band); located = true; }
                     else cur.advance(t - t_cur, p.TB, p.n_bands);
                     t_cur = t;
                     cur.decode(p.TB, I2, J);
@@ -928,7 +945,7 @@ template <int MODE> struct M4Smem {
 };
 
 struct Mma4Params {
-    uint32_t TB, NKB, n_bands;
+    uint32_t TB, NKB, n_bands, band;
     uint32_t case_kb;              // 128-byte sample blocks of the case range of a row (two-accumulator mode)
     uint64_t M, n_tiles;
     uint32_t shard, n_shards;
@@ -1004,7 +1021,7 @@ pair_screen_mma4_kernel(const __grid_constant__ CUtensorMap map_ab, const __grid
             uint64_t it = 0;
             uint32_t n_sched = 0;
             TileDraw draw;
-            draw.counter = p.tile_counter; draw.shard = p.shard; draw.n_shards = p.n_shards; draw.TB = p.TB; draw.n_bands = p.n_bands; draw.last = p.n_tiles;
+            draw.counter = p.tile_counter; draw.shard = p.shard; draw.n_shards = p.n_shards; draw.TB = p.TB; draw.n_bands = p.n_bands; draw.band = p.band; draw.last = p.n_tiles;
             for (;;) {
                 uint32_t I2, J;
                 if (rank == 0) {
@@ -1415,14 +1432,10 @@ static int ensure_mma_inputs(gwasdev_store *s) {
         if (!s->tmap_mm && posix_memalign(&s->tmap_mm, 64, sizeof(CUtensorMap)) != 0) { s->tmap_mm = nullptr; set_error("out of host memory"); return GWASDEV_ENOMEM; }
         int rc;
         if ((rc = make_mm_map(s, 2 * MMA_A_SNPS, (CUtensorMap *)s->tmap_mm)) != GWASDEV_OK) return rc;   // 128-row boxes: a CTA's A rows / its half of B
-        // schedule size: bands of 8 A-blocks (band_offset), the last one possibly shorter
+        // schedule: bands of as many A-blocks as fit 32 MB of operand rows, the last band possibly shorter
         const uint32_t TB = (uint32_t)(Msnp / MMA_BLK);
-        const uint32_t n_bands = (TB + BAND - 1) / BAND;
-        uint64_t tiles = band_offset(TB, n_bands - 1);
-        {
-            const uint32_t na = band_height(TB, n_bands - 1);
-            for (uint32_t J = BAND * (n_bands - 1); J < TB; ++J) tiles += column_height(na, J - BAND * (n_bands - 1));
-        }
+        s->mm_band = schedule_band((uint64_t)MMA_N * s->mm_kbytes);
+        const uint64_t tiles = schedule_tiles(TB, s->mm_band);
         s->mm_tiles = tiles;
         if (s->mma_bound_ncase != s->n_case || s->mma_bound_n != s->n_case + s->n_ctrl) {   // 2.5 ms of host arithmetic: once per class split
             bound_constants(s->n_case, s->n_case + s->n_ctrl, &s->mma_qc, &s->mma_q0);
@@ -1459,10 +1472,11 @@ uint64_t gwasdev_internal_mma_shard_pairs(const gwasdev_store *s, uint32_t shard
                                           uint64_t *tiles_out) {
     const uint64_t M = s->M;
     const uint32_t TB = (uint32_t)((M + MMA_BLK - 1) / MMA_BLK);
+    const uint32_t BAND = schedule_band((uint64_t)MMA_N * 32 * s->Wr);          // = s->mm_band once the operands exist
     const uint32_t n_bands = (TB + BAND - 1) / BAND;
     uint64_t pairs = 0, tiles = 0, t = 0;
     for (uint32_t b = 0; b < n_bands; ++b) {
-        const uint32_t na = band_height(TB, b);
+        const uint32_t na = band_height(TB, b, BAND);
         for (uint32_t J = BAND * b; J < TB; ++J) {
             const uint32_t h = column_height(na, J - BAND * b);
             const uint64_t j0 = (uint64_t)J * MMA_BLK, j1 = std::min<uint64_t>(j0 + MMA_BLK, M);
@@ -1536,7 +1550,7 @@ static int launch_mma(gwasdev_store *s, MmaParams &p, uint64_t my_tiles) {
 
 static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t n_shards) {
     p.TB = (uint32_t)((s->M + MMA_BLK - 1) / MMA_BLK);
-    p.NKB = s->mm_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M;
+    p.NKB = s->mm_kbytes / MMA_KB; p.band = s->mm_band; p.n_bands = (p.TB + p.band - 1) / p.band; p.M = s->M;
     p.shard = shard; p.n_shards = n_shards;
     const uint64_t Msnp = (s->M + MMA_BLK - 1) / MMA_BLK * MMA_BLK;
     p.row = (const MmaRow *)s->d_mma_row; p.col = (const MmaCol *)s->d_mma_col; p.tile_missing = s->d_tile_missing;
@@ -1550,13 +1564,11 @@ static void fill_params(gwasdev_store *s, MmaParams &p, uint32_t shard, uint32_t
 // ---- four-plane engine: host side ---------------------------------------------------------------------
 static uint32_t m4_blocks(const gwasdev_store *s) { return (uint32_t)((s->M + M4_BLK - 1) / M4_BLK); }
 
-static uint64_t m4_schedule_tiles(uint32_t TB) {
-    const uint32_t n_bands = (TB + BAND - 1) / BAND;
-    uint64_t tiles = band_offset(TB, n_bands - 1);
-    const uint32_t na = band_height(TB, n_bands - 1);
-    for (uint32_t J = BAND * (n_bands - 1); J < TB; ++J) tiles += column_height(na, J - BAND * (n_bands - 1));
-    return tiles;
+// bytes per row of the four-plane operand matrix in `mode` (see ensure_mma4_inputs) and the band height that follows from it
+static uint32_t m4_kbytes(const gwasdev_store *s, int mode) {
+    return mode == 2 ? round_up(s->n_case, MMA_KB) + round_up(s->n_ctrl, MMA_KB) : 32 * s->Wr;
 }
+static uint32_t m4_band(const gwasdev_store *s, int mode) { return schedule_band((uint64_t)MMA_N * m4_kbytes(s, mode)); }
 
 static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
     if (s->mm4_built && s->mm4_mode == mode) return GWASDEV_OK;
@@ -1564,7 +1576,7 @@ static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
     const uint32_t case_bytes = round_up(s->n_case, MMA_KB), ctrl_bytes = round_up(s->n_ctrl, MMA_KB);
     // modes 0 and 1: bytes in raw sample order, straight from the raw rows and the class masks. Mode 2 sends the sample blocks of
     // the case range of K to one accumulator and the control range to the other, so its rows are class-pure: from the compacted rows.
-    s->mm4_kbytes = mode == 2 ? case_bytes + ctrl_bytes : 32 * s->Wr;
+    s->mm4_kbytes = m4_kbytes(s, mode);
     s->mm4_rows = (uint64_t)M4_PLANES * TB * M4_BLK;
     const size_t bytes = (size_t)s->mm4_rows * s->mm4_kbytes;
     GW_CUDA(reserve_raw(s->d_mm4, s->cap_mm4, bytes));
@@ -1601,7 +1613,8 @@ static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (three-plane B box) failed (%d)", (int)r); return GWASDEV_ENODEVICE; }
     }
-    s->mm4_tiles = m4_schedule_tiles(TB);
+    s->mm4_band = m4_band(s, mode);
+    s->mm4_tiles = schedule_tiles(TB, s->mm4_band);
     s->mm4_built = true;
     s->mm4_mode = mode;
     return GWASDEV_OK;
@@ -1610,11 +1623,11 @@ static int ensure_mma4_inputs(gwasdev_store *s, int mode) {
 // pairs (i < j < M) and tiles of the shard among the tiles with missing calls, in the four-plane schedule
 // mode 0: tiles with missing calls; 1: tiles without; 2: all tiles
 uint64_t gwasdev_internal_mma4_shard_pairs(gwasdev_store *s, uint32_t shard, uint32_t n_shards, const uint8_t *flags, int mode, uint64_t *tiles_out) {
-    const uint32_t TB = m4_blocks(s), n_bands = (TB + BAND - 1) / BAND;
+    const uint32_t TB = m4_blocks(s), BAND = m4_band(s, mode), n_bands = (TB + BAND - 1) / BAND;
     const uint64_t M = s->M;
     uint64_t pairs = 0, tiles = 0, t = 0;
     for (uint32_t b = 0; b < n_bands; ++b) {
-        const uint32_t na = band_height(TB, b);
+        const uint32_t na = band_height(TB, b, BAND);
         for (uint32_t J = BAND * b; J < TB; ++J) {
             const uint32_t h = column_height(na, J - BAND * b);
             for (uint32_t ii = 0; ii < h; ++ii, ++t) {
@@ -1635,7 +1648,7 @@ int gwasdev_internal_screen_mma4(gwasdev_store *s, const CandSink &sink, uint32_
     int rc = ensure_mma4_inputs(s, mode);
     if (rc != GWASDEV_OK) return rc;
     Mma4Params p;
-    p.TB = m4_blocks(s); p.NKB = s->mm4_kbytes / MMA_KB; p.n_bands = (p.TB + BAND - 1) / BAND; p.M = s->M; p.n_tiles = s->mm4_tiles;
+    p.TB = m4_blocks(s); p.NKB = s->mm4_kbytes / MMA_KB; p.band = s->mm4_band; p.n_bands = (p.TB + p.band - 1) / p.band; p.M = s->M; p.n_tiles = s->mm4_tiles;
     p.case_kb = round_up(s->n_case, MMA_KB) / MMA_KB;
     p.shard = shard; p.n_shards = n_shards; p.side = s->d_side; p.tile_missing = s->d_tile_missing;
     const uint32_t n_ind = s->n_case + s->n_ctrl;
@@ -1686,12 +1699,12 @@ int gwasdev_internal_screen_mma(gwasdev_store *s, const CandSink &sink, uint32_t
 extern "C" {
 
 // Host arithmetic only (no device): the tile pairs of the screen's schedule that `shard` of `n_shards` owns, in schedule
-// order, and the pairs i < j < n_snps they cover. engine 2: tensor-core schedule (128-SNP blocks, bands of 8 A-blocks,
-// column-major inside a band, shards own alternating runs of 64 consecutive tiles); engine 1: AND+POPC schedule (64-SNP
+// order, and the pairs i < j < n_snps they cover. engine 2: tensor-core schedule (128-SNP blocks, bands of 8 to 16 A-blocks
+// depending on the row length for n_samples samples, column-major inside a band, shards own alternating runs of 64 consecutive tiles); engine 1: AND+POPC schedule (64-SNP
 // blocks, row-major upper triangle, single tiles dealt round-robin).
-int gwasdev_shard_schedule(uint64_t n_snps, int engine, uint32_t shard, uint32_t n_shards, uint32_t *tiles, uint64_t capacity,
+int gwasdev_shard_schedule(uint64_t n_snps, uint64_t n_samples, int engine, uint32_t shard, uint32_t n_shards, uint32_t *tiles, uint64_t capacity,
                            uint64_t *n_tiles, uint64_t *n_pairs) {
-    GW_REQUIRE(n_snps >= 1 && n_shards >= 1 && shard < n_shards && (engine == 1 || engine == 2), "gwasdev_shard_schedule: bad argument");
+    GW_REQUIRE(n_snps >= 1 && n_samples >= 1 && n_shards >= 1 && shard < n_shards && (engine == 1 || engine == 2), "gwasdev_shard_schedule: bad argument");
     uint64_t cnt = 0, pairs = 0;
     auto take = [&](uint32_t I, uint32_t J, uint32_t blk) {
         if (tiles && cnt < capacity) { tiles[2 * cnt] = I; tiles[2 * cnt + 1] = J; }
@@ -1699,10 +1712,11 @@ int gwasdev_shard_schedule(uint64_t n_snps, int engine, uint32_t shard, uint32_t
         pairs += rect_pairs(n_snps, (uint64_t)I * blk, (uint64_t)(I + 1) * blk, (uint64_t)J * blk, (uint64_t)(J + 1) * blk);
     };
     if (engine == 2) {
+        const uint32_t BAND = schedule_band((uint64_t)MMA_N * round_up((uint32_t)n_samples, MMA_KB));   // rows are one byte per sample, padded to 128
         const uint32_t TB = (uint32_t)((n_snps + MMA_BLK - 1) / MMA_BLK), n_bands = (TB + BAND - 1) / BAND;
         uint64_t t = 0;
         for (uint32_t b = 0; b < n_bands; ++b) {
-            const uint32_t na = band_height(TB, b);
+            const uint32_t na = band_height(TB, b, BAND);
             for (uint32_t J = BAND * b; J < TB; ++J)
                 for (uint32_t ii = 0; ii < column_height(na, J - BAND * b); ++ii, ++t)
                     if (tile_in_shard(t, shard, n_shards)) take(BAND * b + ii, J, MMA_BLK);
@@ -1785,8 +1799,8 @@ int gwasdev_mma_tile_counts(gwasdev_store *s, uint32_t I, uint32_t J, uint32_t *
     fill_params(s, p, 0, 1);
     GW_REQUIRE(I / 2 < p.TB && J < p.TB && I / 2 <= J, "gwasdev_mma_tile_counts: tile (%u, %u) is not in the schedule", I, J);
     // linear index of (I, J)
-    const uint32_t I2 = I / 2, b = I2 / BAND, na = band_height(p.TB, b);
-    uint64_t t = band_offset(p.TB, b);
+    const uint32_t BAND = p.band, I2 = I / 2, b = I2 / BAND, na = band_height(p.TB, b, BAND);
+    uint64_t t = band_offset(p.TB, b, BAND);
     for (uint32_t c = 0; c < J - BAND * b; ++c) t += column_height(na, c);
     t += I2 - BAND * b;
     p.n_tiles = s->mm_tiles;

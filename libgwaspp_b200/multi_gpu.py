@@ -116,12 +116,12 @@ def marginal_scan_distributed(store, group=None, gather: bool = False, **kw):
     return (0, store.n_snps), {k: np.concatenate([p[k] for p in parts]) for k in out}
 
 
-def shard_tiles(n_snps: int, shard: int, n_shards: int, engine: int = 2):
+def shard_tiles(n_snps: int, shard: int, n_shards: int, engine: int = 2, n_samples: int = 10_000):
     """Tile pairs (I <= J, SNP-block indices) `shard` handles and the pairs they cover, from the library's own schedule
-    (gwasdev_shard_schedule; host arithmetic, no GPU needed). engine 2 (default, tensor cores): blocks of 128 SNPs;
-    engine 1 (AND+POPC): blocks of 64. Returns (list of (I, J), pairs covered, SNPs per block)."""
+    (gwasdev_shard_schedule; host arithmetic, no GPU needed). engine 2 (default, tensor cores): blocks of 128 SNPs, banded
+    for a table of n_samples individuals; engine 1 (AND+POPC): blocks of 64. Returns (list of (I, J), pairs covered, SNPs per block)."""
     import libgwaspp_b200 as gw
-    tiles, pairs = gw.shard_schedule(n_snps, shard, n_shards, engine)
+    tiles, pairs = gw.shard_schedule(n_snps, shard, n_shards, engine, n_samples)
     return [(int(I), int(J)) for I, J in tiles], pairs, 128 if engine == 2 else 64
 
 

@@ -65,14 +65,15 @@ def test_gloo_gather_of_hits(world):
     assert np.all(np.diff(key) > 0)                                          # the reference's (i, j) emission order
 
 
-@pytest.mark.parametrize("n_snps,world,engine", [(130, 2, 1), (130, 2, 2), (1000, 3, 1), (1000, 3, 2), (64, 4, 2), (50_000, 8, 1), (50_000, 8, 2),
-                                                 (4097, 5, 1), (4097, 5, 2), (150_000, 8, 2), (20_000, 7, 2)])
-def test_shards_partition_the_pair_space(n_snps, world, engine):
+@pytest.mark.parametrize("n_snps,world,engine,n_samples", [(130, 2, 1, 4000), (130, 2, 2, 4000), (1000, 3, 1, 10_000), (1000, 3, 2, 10_000), (64, 4, 2, 500),
+                                                           (50_000, 8, 1, 4000), (50_000, 8, 2, 4000), (4097, 5, 1, 10_000), (4097, 5, 2, 10_000),
+                                                           (150_000, 8, 2, 10_000), (20_000, 7, 2, 40_000), (20_000, 3, 2, 200_000)])
+def test_shards_partition_the_pair_space(n_snps, world, engine, n_samples):
     """The library's own shard enumeration (both engines' schedules): disjoint, complete, every pair counted once,
     and -- tensor-core engine -- balanced to one run of 64 tiles."""
     seen, total, sizes = set(), 0, []
     for r in range(world):
-        tiles, pairs, blk = mg.shard_tiles(n_snps, r, world, engine)
+        tiles, pairs, blk = mg.shard_tiles(n_snps, r, world, engine, n_samples)    # band heights 16, 12 and 8 among the cases
         assert all(I <= J for I, J in tiles)
         assert not (seen & set(tiles))
         seen |= set(tiles)
