@@ -45,8 +45,8 @@ PAIRWISE_CFG3 = dict(n_snps=500_000, n_samples=10_000, n_case=5_000)  # BASELINE
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (valid for these shapes only)
 NCU_TRAFFIC = {
     ("marginal_scan_kernel", 500_000, 10_000): (1.2930e9, "profiles/r1k_marginal_scan_full.md"),
-    ("pair_screen_mma_kernel", 50_000, 4_000): (1.9517e10, "profiles/r1h_pair_screen_mma_full.md"),
-    ("pair_screen_mma_kernel", 500_000, 10_000): (6.949e12, "profiles/r2d_pair_screen_mma_cfg3_whole_full.md"),
+    ("pair_screen_mma_kernel", 50_000, 4_000): (5.19e9, "profiles/r2w_pair_screen_mma_cfg2_full.md"),
+    ("pair_screen_mma_kernel", 500_000, 10_000): (1.843e12, "profiles/r2w_pair_screen_mma_cfg3_whole_metrics.md"),
 }
 CPU_MARGINAL_SAMPLE_SNPS = 2_000
 CPU_PAIRWISE_SAMPLE_SNPS = 1_500     # per process and step in the reference arm: 1 124 250 pairs
