@@ -298,7 +298,7 @@ GWASDEV_API int gwasdev_set_pair_engine(gwasdev_store *s, int engine);
 /* Host arithmetic only (works without a device): the tile pairs (I <= J, as SNP-block indices) of the screen's schedule that
  * `shard` of `n_shards` owns, in schedule order, and the pairs i < j < n_snps they cover. engine 2: the tensor-core
  * schedule for a table of n_samples individuals (128-SNP blocks; bands of 8 to 16 A-blocks, as many as keep the working set of
- * the 74 concurrent tiles in the L2: 16 at 4 000 samples, 12 at 10 000, 8 from 12 000; shards own alternating runs of 64
+ * the 74 concurrent tiles in the L2: 16 at 4 000 samples, 13 at 10 000, 8 from 12 000; shards own alternating runs of 64
  * consecutive tiles); engine 1: the
  * AND+POPC schedule (64-SNP blocks, row-major upper triangle, single tiles round-robin). tiles (may be NULL) receives
  * min(*n_tiles, capacity) (I, J) pairs. */

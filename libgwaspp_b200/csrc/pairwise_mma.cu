@@ -56,11 +56,12 @@ constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int COL_STAGE_BYTES = 32 * 64;                           // column-role records of one epilogue warp's 32 B-SNPs
 // A-blocks per L2 band (schedule_band below): with the tile feed the 74 CTA pairs of a B200 work on ~74 consecutive tiles, i.e.
 // on the BD A-blocks of the band and a window of ceil(74 / BD) B-blocks; DRAM traffic falls as 1 / BD while that working set
-// fits the L2. The largest BD (at most BAND_MAX) whose working set stays below GWASDEV_L2_MB is taken; when none fits (rows
-// of 12 000+ samples) the working set is smallest at BD = 8. Measured at configs[3] (2.57 MB blocks): 8 -> 2.77 s, 12 -> 2.69 s
-// (48.8 MB), 16 -> 2.71-2.75 s (54 MB), 24 -> 3.00 s (72 MB).
+// fits the L2. The largest BD (at most BAND_MAX) whose working set stays below GWASDEV_L2_MB MiB is taken; when none fits
+// (rows of 12 000+ samples) the working set is smallest at BD = 8. Measured at configs[3] (2.59 MB blocks) on one box, two
+// rounds: 8 -> 2.77-2.78 s, 10 -> 2.75-2.77, 12 -> 2.73-2.74 (19 blocks, 49.2 MB), 13 -> 2.74, 14 -> 2.74-2.75 (51.8 MB),
+// 15 -> 2.75-2.76, 16 -> 2.75-2.79 (54.4 MB), 24 -> 3.00 s (72 MB): flat between 12 and 14, the rule picks 13.
 #ifndef GWASDEV_L2_MB
-#define GWASDEV_L2_MB 50
+#define GWASDEV_L2_MB 48
 #endif
 constexpr uint32_t BAND_MAX = 16, BAND_FALLBACK = 8, SCHED_PAIRS = 74;
 constexpr int ACC_COLS = MMA_N;                                    // TMEM columns per accumulator
@@ -276,6 +277,9 @@ __host__ __device__ inline uint32_t band_height(uint32_t TB, uint32_t b, uint32_
 __host__ __device__ inline uint32_t column_height(uint32_t na, uint32_t c) { return min(na, c + 1); }
 // band height for operand blocks of `block_bytes` (rows of one A-block x bytes per row)
 inline uint32_t schedule_band(uint64_t block_bytes) {
+#ifdef GWASDEV_BAND_FORCE                    // experiment builds: build.py --variant NAME -DGWASDEV_BAND_FORCE=n
+    return GWASDEV_BAND_FORCE;
+#endif
     for (uint32_t bd = BAND_MAX; bd >= BAND_FALLBACK; --bd)
         if ((bd + (SCHED_PAIRS + bd - 1) / bd) * block_bytes <= ((uint64_t)GWASDEV_L2_MB << 20)) return bd;
     return BAND_FALLBACK;

@@ -152,6 +152,12 @@ def test_round2_entry_points_fail_loudly_without_a_device(lib):
     # host arithmetic keeps working without a device: the shard schedule of both engines
     tiles, pairs = gw.shard_schedule(1000, 0, 1, engine=2)
     assert len(tiles) == 8 * 9 // 2 and pairs == 1000 * 999 // 2
+    # band height follows the row length: 13 A-blocks at 10 000 samples, 16 at 4 000, 8 from 12 000 (working set of 74 tiles within the L2)
+    for n_samples, band in ((10_000, 13), (4_000, 16), (12_000, 8), (150_000, 8)):
+        t40, _ = gw.shard_schedule(128 * 40, 0, 1, engine=2, n_samples=n_samples)
+        first_of_band_1 = next(k for k, (I, J) in enumerate(t40) if I == band)
+        assert first_of_band_1 == band * (band - 1) // 2 + band * (40 - (band - 1)) and not any(I > band for I, _ in t40[:first_of_band_1])
+        assert [tuple(x) for x in t40[:6]] == [(0, 0), (0, 1), (1, 1), (0, 2), (1, 2), (2, 2)]
     tiles, pairs = gw.shard_schedule(1000, 1, 3, engine=1)
     assert all(I <= J for I, J in tiles) and len(tiles) == (16 * 17 // 2 + 1) // 3
     assert gw.COMPACT_DTYPE.itemsize == 32 and gw.SIG_DTYPE.itemsize == 48

@@ -73,7 +73,7 @@ def test_shards_partition_the_pair_space(n_snps, world, engine, n_samples):
     and -- tensor-core engine -- balanced to one run of 64 tiles."""
     seen, total, sizes = set(), 0, []
     for r in range(world):
-        tiles, pairs, blk = mg.shard_tiles(n_snps, r, world, engine, n_samples)    # band heights 16, 12 and 8 among the cases
+        tiles, pairs, blk = mg.shard_tiles(n_snps, r, world, engine, n_samples)    # band heights 16, 13 and 8 among the cases
         assert all(I <= J for I, J in tiles)
         assert not (seen & set(tiles))
         seen |= set(tiles)
