@@ -339,6 +339,33 @@ def test_hot_paths_never_compact(orc, miss):
         assert np.array_equal(h2, h)
 
 
+@pytest.mark.parametrize("miss,shards", [(0.0, 1), (0.01, 1), (0.0, 5), (0.01, 3)])
+def test_tile_feed_hands_out_every_tile_exactly_once(orc, miss, shards):
+    """The CTA pairs of the tensor-core kernels draw their tiles from a device counter, so which pair computes which tile differs
+    from launch to launch: twelve passes over a cohort of 40 x 40 tile blocks (820 tiles of 128 SNPs, more than the 74 pairs;
+    with missing calls the four-plane kernel's 64-SNP tiles as well) must give the same pair count, candidates and records
+    every time, shard by shard, and the shards together the whole list."""
+    # complete data: threshold 25 over 13 M pairs; with missing calls the statistic of ordinary pairs is far below zero, so every
+    # pair with a statistic of a smaller cohort (136 four-plane tiles) is kept: the list then checks the coverage pair by pair
+    M, N, NCASE, thr = (5100, 1200, 590, 25.0) if miss == 0.0 else (1000, 1200, 590, -1e9)
+    codes, pheno = planted_cohort(orc, 777, M, N, NCASE, miss, 10)
+    with make_store(orc, codes, pheno) as st:
+        st.set_pair_engine(2)
+        whole, s0 = st.pairwise_scan(thr)
+        assert s0.engine == 2 and s0.pairs_tested == M * (M - 1) // 2
+        assert len(whole) >= (10 if miss == 0.0 else 100_000)      # (pairs with an empty genotype column have no statistic: NaN, never kept)
+        for rep in range(12):
+            parts, pairs = [], 0
+            for sh in range(shards):
+                h, s = st.pairwise_scan(thr, shard=sh, n_shards=shards)
+                parts.append(h); pairs += s.pairs_tested
+            got = np.sort(np.concatenate(parts), order=["i", "j"])
+            assert pairs == s0.pairs_tested and np.array_equal(got, whole), rep
+        st.set_pair_engine(1)
+        h1, _ = st.pairwise_scan(thr)
+        assert np.array_equal(h1, whole)
+
+
 def test_tensor_peak_probe_is_plausible():
     burst, sustained = gw.i8_peak(0)
     assert 500.0 < sustained <= burst * 1.02 and burst < 5000.0, (burst, sustained)   # nominal dense int8: 4 500 TOP/s
