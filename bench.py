@@ -195,6 +195,7 @@ class Ctx:
             self.sampler.start()
         # roofline denominators measured once, on the idle device, before any section has warmed it up
         self.i8_burst, self.i8_sustained = gw.i8_peak(self.local)
+        self.l2_read = {mb: gw.l2_read_peak(self.local, mb << 20, 12800 // mb) for mb in (16, 48)}   # GB/s, L2-resident buffers
         self.popc_peak, self.popc_clk = gw.popc_peak(self.local)
 
     def barrier(self):
@@ -247,11 +248,11 @@ def pairwise_section(cx: Ctx, shape, K, W, label, headline):
     cx.barrier()
     l0, t0 = gw.launch_count(), time.perf_counter()
     ev0.record(cx.stream)
-    screen_ms, pairs, cells, n_hits, cand, engine = [], 0, 0, 0, 0, 0
+    screen_ms, pairs, cells, n_hits, cand, engine, tiles = [], 0, 0, 0, 0, 0, 0
     for _ in range(K):
         n_hits, s = step()
         screen_ms.append(s.screen_ms)
-        pairs, cells, cand, engine = s.pairs_tested, s.word_cells, s.candidates, s.engine
+        pairs, cells, cand, engine, tiles = s.pairs_tested, s.word_cells, s.candidates, s.engine, s.tiles
     ev1.record(cx.stream)
     cx.barrier()
     t1, launches = time.perf_counter(), gw.launch_count() - l0
@@ -283,6 +284,17 @@ def pairwise_section(cx: Ctx, shape, K, W, label, headline):
                      "peak_source": f"register-only __popc microbenchmark in this process (clock attr {clk:.0f} MHz); nominal 148 x 16 x 1.965 GHz = 4.65",
                      "note": "north star's popcount roofline; above 1 because the counting runs as an int8 GEMM on the tensor cores"},
     }
+    if engine == 2:
+        # what the kernel actually runs into: every tile pulls 2 x 256 operand rows from L2 (128 MAC per byte, 18.6 TB/s at the full tensor
+        # rate); the cap is what plain 128-bit loads past L1 get out of an L2-resident buffer on this device (gwasdev_l2_read_peak)
+        kb = (N + 127) // 128 * 128
+        cap = max(cx.l2_read.values()) / 1e3
+        l2 = float(tiles) * 512.0 * kb / (k_ms * 1e-3) / 1e12
+        roofline["l2_to_sm"] = {"achieved": round(l2, 2), "cap": round(cap, 2), "frac": round(l2 / cap, 4), "unit": "TB/s",
+                                "operand_bytes_per_launch": int(tiles) * 512 * kb,
+                                "cap_source": "gwasdev_l2_read_peak in this process (ld.global.cg.v4 over L2-resident buffers, one launch of many passes): "
+                                              + ", ".join(f"{mb} MiB {v / 1e3:.2f} TB/s" for mb, v in cx.l2_read.items()),
+                                "note": "operand bytes TMA moves from L2 to shared memory per launch / kernel time"}
     res = {
         "metric": "pairwise SNP x SNP tests/sec", "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -346,6 +346,9 @@ GWASDEV_API int gwasdev_i8_peak(int device, double *tops_burst, double *tops_sus
 /* Read-only streaming bandwidth (GB/s) of a plain 128-bit-load kernel over `bytes` of HBM on `device`:
  * context for the marginal scan's roofline next to the driver-measured copy bandwidth. */
 GWASDEV_API int gwasdev_hbm_read_peak(int device, uint64_t bytes, double *gb_per_s);
+/* The same loads past L1 over a buffer of `bytes` (1 to 64 MiB: L2-resident) read `passes` times in one launch: the rate (GB/s) at which
+ * the L2 delivers to the SMs, what the tensor-core screens' operand stream runs into (bench.py: roofline.l2_to_sm). */
+GWASDEV_API int gwasdev_l2_read_peak(int device, uint64_t bytes, uint32_t passes, double *gb_per_s);
 
 #ifdef __cplusplus
 }

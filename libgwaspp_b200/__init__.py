@@ -63,7 +63,7 @@ ABI_SYMBOLS = [
     "gwasdev_marginal_finalize", "gwasdev_put_tped_text", "gwasdev_tped_dims", "gwasdev_load_tped", "gwasdev_put_bed",
     "gwasdev_bed_dims", "gwasdev_load_bed", "gwasdev_set_select_mode", "gwasdev_epi_pairs", "gwasdev_create_from_tped",
     "gwasdev_set_option", "gwasdev_set_stream_masks", "gwasdev_marginal_scan_compact", "gwasdev_pairwise_topk",
-    "gwasdev_replicate", "gwasdev_pairwise_scan_multi", "gwasdev_shard_schedule", "gwasdev_i8_peak", "gwasdev_gtest_multi", "gwasdev_is_compacted",
+    "gwasdev_replicate", "gwasdev_pairwise_scan_multi", "gwasdev_shard_schedule", "gwasdev_i8_peak", "gwasdev_l2_read_peak", "gwasdev_gtest_multi", "gwasdev_is_compacted",
 ]
 
 
@@ -133,6 +133,7 @@ def load_library():
     L.gwasdev_i8_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.gwasdev_gtest_multi.argtypes = [C.POINTER(vp), u32, u64, vp, vp, vp, vp]
     L.gwasdev_hbm_read_peak.argtypes = [i32, u64, C.POINTER(C.c_double)]
+    L.gwasdev_l2_read_peak.argtypes = [i32, u64, u32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -213,6 +214,13 @@ def i8_peak(device: int = 0) -> tuple[float, float]:
     a, b = C.c_double(), C.c_double()
     _check(load_library().gwasdev_i8_peak(device, C.byref(a), C.byref(b)), "gwasdev_i8_peak")
     return a.value, b.value
+
+
+def l2_read_peak(device: int = 0, nbytes: int = 32 << 20, passes: int = 400) -> float:
+    """GB/s the L2 delivers to the SMs: plain 128-bit loads past L1 over an L2-resident buffer, `passes` times in one launch."""
+    r = C.c_double()
+    _check(load_library().gwasdev_l2_read_peak(device, nbytes, passes, C.byref(r)), "gwasdev_l2_read_peak")
+    return r.value
 
 
 def hbm_read_peak(device: int = 0, nbytes: int = 1 << 31) -> float:
