@@ -371,6 +371,15 @@ def test_tensor_peak_probe_is_plausible():
     assert 500.0 < sustained <= burst * 1.02 and burst < 5000.0, (burst, sustained)   # nominal dense int8: 4 500 TOP/s
 
 
+def test_l2_delivery_probe_is_plausible():
+    """What the L2 hands to the SMs (the rate the screens' operand streams run at) lies between the HBM read rate and the
+    SMs' own load rate (148 x 128 B/clk); a buffer larger than the L2 falls back to the HBM rate and is refused."""
+    l2, hbm = gw.l2_read_peak(0, 48 << 20, 100), gw.hbm_read_peak(0, 1 << 30)
+    assert hbm < l2 < 37_000.0 and 3_000.0 < hbm < 8_500.0, (l2, hbm)
+    with pytest.raises(gw.GwasDevError):
+        gw.l2_read_peak(0, 256 << 20, 10)
+
+
 # ------------------------------------------------------------------------------------------------------
 # several devices in one process
 # ------------------------------------------------------------------------------------------------------
