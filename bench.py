@@ -439,6 +439,16 @@ def pairwise_missing_gpu(cx: Ctx):
         res["and_popc_nine_cells"]["frac_of_popc_roofline"] = round(res["and_popc_nine_cells"]["value"] * cells / peak, 4)
         res["tensor_cores_four_planes"]["x_popc_roofline"] = round(res["tensor_cores_four_planes"]["value"] * cells / peak, 4)
         res["same_hits"] = res["and_popc_nine_cells"]["hits"] == res["tensor_cores_four_planes"]["hits"]
+        # the four-plane kernel's own bound: 256 A rows + 192 B rows (three of the four planes) per 64 x 64-SNP tile from L2
+        t4 = res["tensor_cores_four_planes"]
+        kb = (N + 127) // 128 * 128
+        byts = float(t4["tiles_with_missing_calls"]) * (256 + 192) * kb
+        cap = max(cx.l2_read.values()) / 1e3
+        t4["l2_to_sm"] = {"achieved": round(byts / (t4["kernel_ms"] * 1e-3) / 1e12, 2), "cap": round(cap, 2), "unit": "TB/s",
+                          "frac": round(byts / (t4["kernel_ms"] * 1e-3) / 1e12 / cap, 4), "operand_bytes_per_launch": int(byts),
+                          "mma_floor_ms": round(t4["tiles_with_missing_calls"] / 74.0 * (kb // 32) * 96 / 1.965e6, 2),
+                          "note": "cap = gwasdev_l2_read_peak in this process; mma_floor_ms = tiles / 74 CTA pairs x (row bytes / 32) MMAs x 96 clk "
+                                  "(M 256, N 192, K 32) at 1 965 MHz"}
     return res
 
 
