@@ -160,6 +160,10 @@ def test_round2_entry_points_fail_loudly_without_a_device(lib):
         first_of_band_1 = next(k for k, (I, J) in enumerate(t40) if I == band)
         assert first_of_band_1 == band * (band - 1) // 2 + band * (40 - (band - 1)) and not any(I > band for I, _ in t40[:first_of_band_1])
         assert [tuple(x) for x in t40[:6]] == [(0, 0), (0, 1), (1, 1), (0, 2), (1, 2), (2, 2)]
+    for bad in (dict(n_snps=0, shard=0, n_shards=1), dict(n_snps=10, shard=2, n_shards=2), dict(n_snps=10, shard=0, n_shards=1, n_samples=0),
+                dict(n_snps=10, shard=0, n_shards=1, engine=3)):
+        with pytest.raises(gw.GwasDevError):
+            gw.shard_schedule(**bad)
     tiles, pairs = gw.shard_schedule(1000, 1, 3, engine=1)
     assert all(I <= J for I, J in tiles) and len(tiles) == (16 * 17 // 2 + 1) // 3
     assert gw.COMPACT_DTYPE.itemsize == 32 and gw.SIG_DTYPE.itemsize == 48
