@@ -504,7 +504,6 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();          // 0: leader of the CTA pair (issues the MMAs, owns full / tempty)
-    const uint32_t pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
     if (tid == 0) {
         // full: the leader's own arrive.expect_tx + the peer producer's arrive; both CTAs' TMA bytes land on it.
@@ -527,7 +526,6 @@ pair_screen_mma_kernel(const __grid_constant__ CUtensorMap map_ab, const MmaPara
     // of SHARD_CHUNK consecutive tiles, so that the tiles a GPU works on at the same time share A- and B-blocks in its L2
     // whatever the number of GPUs. The pair draws its u from p.tile_counter (tile feed above).
     const uint64_t last = p.dump ? p.dump_tile + 1 : p.n_tiles;
-    (void)pair_id; (void)n_pairs;
 
     if (warp == TMA_WARP) {
         // ===== TMA producer (both CTAs: own 128 A rows, own half of the 256 B rows) =====
